@@ -1,0 +1,101 @@
+/*
+ * mshds_b200.h -- C ABI of libmshds_b200.so, the B200-native (sm_100a) MSHDS acoustic feature extractor.
+ *
+ * The reference (ayushpradhan-dev/robust-speech-analysis-framework) has no FFI of its own: its hot path is the pure
+ * Python function extract_mshds_features (src/mshds_extractor.py:379-459), whose arithmetic is Praat reached through
+ * praat-parselmouth.  This header is the thin C layer BASELINE.json's north_star asks for; every entry point names the
+ * reference interface it stands in for.  Plain pointers and sizes only, no torch types.  INTEGRATION.md shows the
+ * ctypes binding and the drop-in src/mshds_extractor.py shim.
+ *
+ * Threading: one handle per host thread / process; a handle owns one CUDA device, one stream and all scratch memory;
+ * no global mutable state.  Calls block until results are in the caller's buffers (mirrors the synchronous reference).
+ */
+#ifndef MSHDS_B200_H
+#define MSHDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSHDS_N_FEATURES 25
+
+/* Column order of the output row == feature_names at src/mshds_extractor.py:397-404. */
+enum mshds_feature {
+    MSHDS_SPEAKING_RATE = 0, MSHDS_ARTICULATION_RATE, MSHDS_PHONATION_RATIO, MSHDS_PAUSE_RATE, MSHDS_MEAN_PAUSE_DURATION,
+    MSHDS_MEAN_F0, MSHDS_STDEV_F0_SEMITONE, MSHDS_MEAN_DB, MSHDS_RANGE_RATIO_DB, MSHDS_HNR_DB,
+    MSHDS_SPECTRAL_SLOPE, MSHDS_SPECTRAL_TILT, MSHDS_CPP,
+    MSHDS_MEAN_F1, MSHDS_STD_F1, MSHDS_MEAN_B1, MSHDS_STD_B1, MSHDS_MEAN_F2, MSHDS_STD_F2, MSHDS_MEAN_B2, MSHDS_STD_B2,
+    MSHDS_SPECTRAL_GRAVITY, MSHDS_SPECTRAL_STD_DEV, MSHDS_SPECTRAL_SKEWNESS, MSHDS_SPECTRAL_KURTOSIS
+};
+
+/* Per-clip status word.  A set bit means "this helper's try/except fired" in the reference
+ * (src/mshds_extractor.py:124,161,182,204,224,250,300,337,375 and the whole-file handler :450-457): the columns of
+ * that group are NaN.  Not an error of the call. */
+#define MSHDS_ST_SPEECHRATE          (1u << 0)
+#define MSHDS_ST_PITCHRANGE_FALLBACK (1u << 1)   /* _pitch_values returned (75, 500), :146,151,162 */
+#define MSHDS_ST_PITCH               (1u << 2)
+#define MSHDS_ST_INTENSITY           (1u << 3)
+#define MSHDS_ST_HNR                 (1u << 4)
+#define MSHDS_ST_LTAS                (1u << 5)
+#define MSHDS_ST_CPP                 (1u << 6)
+#define MSHDS_ST_FORMANT             (1u << 7)
+#define MSHDS_ST_MOMENTS             (1u << 8)
+#define MSHDS_ST_FILE                (1u << 31)  /* empty clip: whole row NaN (:450-457) */
+
+/* flags of mshds_extract */
+#define MSHDS_PCM_ON_DEVICE (1u << 0)   /* pcm is a device pointer on the handle's device */
+#define MSHDS_OUT_ON_DEVICE (1u << 1)   /* features / status are device pointers */
+
+/* error codes */
+#define MSHDS_OK 0
+#define MSHDS_ERR_ARG 1
+#define MSHDS_ERR_CUDA 2
+#define MSHDS_ERR_UNSUPPORTED 3
+
+typedef struct mshds_handle mshds_handle;
+
+/* Create / destroy an extractor bound to CUDA device `device`.  The reference keeps no state between calls
+ * (src/mshds_extractor.py:379); the handle only caches window tables and scratch memory. */
+int mshds_create(int device, mshds_handle** out);
+void mshds_destroy(mshds_handle* h);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the handle's own; NULL restores it. */
+int mshds_set_stream(mshds_handle* h, void* cuda_stream);
+
+/* Upper bound, in samples, of the sub-batches the handle processes at once (scratch memory scales with it). */
+int mshds_set_chunk_samples(mshds_handle* h, long long max_samples);
+
+/* Human-readable description of the last non-zero return code of this handle. */
+const char* mshds_last_error(const mshds_handle* h);
+
+/*
+ * The hot path: body of the per-file loop of extract_mshds_features (src/mshds_extractor.py:408-448), for a ragged
+ * batch of mono recordings already decoded to 16-bit PCM (sample value = pcm / 32768, as parselmouth.Sound(path)
+ * gives at :415).  Clip i is pcm[offsets[i] .. offsets[i+1]).  offsets is a HOST array of n_clips + 1 entries.
+ * features: n_clips x 25 float64, row-major, column order as enum mshds_feature; status: n_clips words (may be NULL).
+ * sample_rate must be 16000 (the reference resamples everything to 16 kHz first, :418-419; that front-end is the
+ * caller's job in this version).  Returns MSHDS_OK or an error code; per-clip analysis failures are NOT errors.
+ */
+int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
+                  double* features, uint32_t* status, unsigned flags);
+
+/* Number of kernel launches issued by this handle since creation (bench.py reports it as gpu_launches). */
+long long mshds_launch_count(const mshds_handle* h);
+
+/*
+ * Stage-level read-back for parity tests: after mshds_extract, copy one named intermediate of clip `clip` of the LAST
+ * processed chunk into a host buffer.  Names: "pitch_wide_f", "pitch_main_f", "pitch_main_s", "pitch_cpp_f",
+ * "pitch_ltas_f", "pitch_cc_f", "pitch_sr_f", "hnr_r", "intensity_main", "intensity_sr", "pulses_cpp", "pulses_fmt",
+ * "pulses_ltas", "ltas_bands", "formant_f", "formant_b", "formant_n", "resampled10k", "class", "moments".
+ * Returns the number of elements available through *n_out (copies at most cap elements); element type is float64
+ * except "class"/"formant_n" (int32).
+ */
+int mshds_debug_fetch(mshds_handle* h, const char* name, int clip, void* host_buf, size_t cap_elems, size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

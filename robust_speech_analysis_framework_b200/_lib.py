@@ -1,0 +1,122 @@
+"""ctypes binding of libmshds_b200.so (C ABI: include/mshds_b200.h).
+
+There is deliberately NO fallback: if the CUDA library cannot be built/loaded or no CUDA device is present, every
+compute entry point raises.  The CPU oracle under oracle/ is test infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+FEATURE_NAMES = [  # /root/reference/src/mshds_extractor.py:397-404
+    'Speaking_Rate', 'Articulation_Rate', 'Phonation_Ratio', 'Pause_Rate', 'Mean_Pause_Duration',
+    'mean_F0', 'stdev_F0_Semitone', 'mean_dB', 'range_ratio_dB', 'HNR_dB',
+    'Spectral_Slope', 'Spectral_Tilt', 'Cepstral_Peak_Prominence',
+    'mean_F1_Loc', 'std_F1_Loc', 'mean_B1_Loc', 'std_B1_Loc',
+    'mean_F2_Loc', 'std_F2_Loc', 'mean_B2_Loc', 'std_B2_Loc',
+    'Spectral_Gravity', 'Spectral_Std_Dev', 'Spectral_Skewness', 'Spectral_Kurtosis',
+]
+N_FEATURES = 25
+PCM_ON_DEVICE = 1
+OUT_ON_DEVICE = 2
+
+EXPORTED_SYMBOLS = [
+    "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
+    "mshds_launch_count", "mshds_debug_fetch",
+]
+
+_lib = None
+
+
+class MshdsError(RuntimeError):
+    pass
+
+
+def load(build_if_needed: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_needed and _build.needs_build():
+        _build.build()
+    if not os.path.exists(path):
+        raise MshdsError(f"{path} is missing: build it with `python -m robust_speech_analysis_framework_b200.build`")
+    lib = C.CDLL(path)
+    lib.mshds_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.mshds_destroy.argtypes = [C.c_void_p]
+    lib.mshds_destroy.restype = None
+    lib.mshds_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mshds_set_chunk_samples.argtypes = [C.c_void_p, C.c_longlong]
+    lib.mshds_last_error.argtypes = [C.c_void_p]
+    lib.mshds_last_error.restype = C.c_char_p
+    lib.mshds_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint]
+    lib.mshds_launch_count.argtypes = [C.c_void_p]
+    lib.mshds_launch_count.restype = C.c_longlong
+    lib.mshds_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    _lib = lib
+    return lib
+
+
+class Extractor:
+    """One handle = one CUDA device + stream + scratch (mshds_create / mshds_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.mshds_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise MshdsError(f"mshds_create(device={device}) failed with code {rc}: no usable CUDA device "
+                             "(this package has no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mshds_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MshdsError(f"libmshds_b200 error {rc}: {self._lib.mshds_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.mshds_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_chunk_samples(self, n: int):
+        self._check(self._lib.mshds_set_chunk_samples(self._h, int(n)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.mshds_launch_count(self._h))
+
+    def extract_host(self, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int = 16000):
+        """Host int16 buffer in, host float64 [n,25] + uint32 [n] out (H2D and D2H inside the call)."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        out = np.full((n, N_FEATURES), np.nan, dtype=np.float64)
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self._lib.mshds_extract(self._h, pcm.ctypes.data, offsets.ctypes.data, n, int(sample_rate),
+                                            out.ctypes.data, status.ctypes.data, 0))
+        return out, status
+
+    def extract_device(self, pcm_ptr: int, offsets: np.ndarray, out_ptr: int, status_ptr: int, sample_rate: int = 16000):
+        """Device-resident int16 batch in, device float64 [n,25] / uint32 [n] out (raw device pointers)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        self._check(self._lib.mshds_extract(self._h, C.c_void_p(pcm_ptr), offsets.ctypes.data, n, int(sample_rate),
+                                            C.c_void_p(out_ptr), C.c_void_p(status_ptr), PCM_ON_DEVICE | OUT_ON_DEVICE))
+
+    def debug_fetch(self, name: str, clip: int, dtype=np.float64, cap: int = 1 << 22) -> np.ndarray:
+        buf = np.zeros(cap, dtype=dtype)
+        n = C.c_size_t(0)
+        self._check(self._lib.mshds_debug_fetch(self._h, name.encode(), int(clip), buf.ctypes.data, cap, C.byref(n)))
+        if n.value > cap:
+            return self.debug_fetch(name, clip, dtype, n.value)
+        return buf[: n.value].copy()

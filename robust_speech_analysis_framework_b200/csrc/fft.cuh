@@ -1,0 +1,141 @@
+// fft.cuh -- shared-memory float64 FFT building blocks (hand-written, no cuFFT).
+//
+// Complex radix-2 in place: DIF (natural in -> bit-reversed out) for the forward transform and DIT (bit-reversed in
+// -> natural out) for the inverse, so no explicit permutation pass is ever run.  Real transforms use the packed
+// trick (N real samples as N/2 complex) with the untangle / power / retangle step done pairwise in bit-reversed
+// position.  Twiddles come from one global table tw[j] = exp(-2*pi*i*j/TW_N), j < TW_N/2 (L1/L2 resident).
+#pragma once
+#include "common.cuh"
+
+#define TW_N 8192          // table covers complex FFT sizes up to 8192
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ int bitrev(int k, int logn) { return (int)(__brev((unsigned)k) >> (32 - logn)); }
+
+// tw index for exp(SIGN*2*pi*i*pos/len), len a power of two <= TW_N, pos < len/2
+template <int SIGN>
+__device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int pos, int len) {
+    double2 w = __ldg(tw + pos * (TW_N / len));
+    if (SIGN > 0) w.y = -w.y;
+    return w;
+}
+
+// n complex points, cols interleaved columns (element (r,c) at a[r*cols+c]); all threads of the block participate.
+template <int SIGN>
+__device__ __forceinline__ void fft_dif_cols(double2* a, int n, int cols, const double2* __restrict__ tw) {
+    for (int half = n >> 1; half >= 1; half >>= 1) {
+        int work = (n >> 1) * cols;
+        for (int j = threadIdx.x; j < work; j += blockDim.x) {
+            int c = j % cols, b = j / cols;
+            int pos = b & (half - 1), grp = b / half;
+            int i0 = (grp * 2 * half + pos) * cols + c, i1 = i0 + half * cols;
+            double2 u = a[i0], v = a[i1];
+            a[i0] = make_double2(u.x + v.x, u.y + v.y);
+            double2 d = make_double2(u.x - v.x, u.y - v.y);
+            a[i1] = half > 1 ? cmul(d, twiddle<SIGN>(tw, pos, 2 * half)) : d;
+        }
+        __syncthreads();
+    }
+}
+template <int SIGN>
+__device__ __forceinline__ void fft_dit_cols(double2* a, int n, int cols, const double2* __restrict__ tw) {
+    for (int half = 1; half < n; half <<= 1) {
+        int work = (n >> 1) * cols;
+        for (int j = threadIdx.x; j < work; j += blockDim.x) {
+            int c = j % cols, b = j / cols;
+            int pos = b & (half - 1), grp = b / half;
+            int i0 = (grp * 2 * half + pos) * cols + c, i1 = i0 + half * cols;
+            double2 u = a[i0], v = a[i1];
+            if (half > 1) v = cmul(v, twiddle<SIGN>(tw, pos, 2 * half));
+            a[i0] = make_double2(u.x + v.x, u.y + v.y);
+            a[i1] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+// Single-column versions (the per-frame transforms).
+template <int SIGN>
+__device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __restrict__ tw) {
+    for (int half = n >> 1; half >= 1; half >>= 1) {
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            int pos = b & (half - 1);
+            int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
+            double2 u = a[i0], v = a[i1];
+            a[i0] = make_double2(u.x + v.x, u.y + v.y);
+            double2 d = make_double2(u.x - v.x, u.y - v.y);
+            a[i1] = half > 1 ? cmul(d, twiddle<SIGN>(tw, pos, 2 * half)) : d;
+        }
+        __syncthreads();
+    }
+}
+template <int SIGN>
+__device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __restrict__ tw) {
+    for (int half = 1; half < n; half <<= 1) {
+        for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+            int pos = b & (half - 1);
+            int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
+            double2 u = a[i0], v = a[i1];
+            if (half > 1) v = cmul(v, twiddle<SIGN>(tw, pos, 2 * half));
+            a[i0] = make_double2(u.x + v.x, u.y + v.y);
+            a[i1] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+// Packed real FFT helpers.  `a` holds M = N/2 complex points z[n] = x[2n] + i x[2n+1]; after fft_dif<-1> the
+// spectrum Z sits bit-reversed.  For bin k in [0, M]:  X[k] = (Z[k] + conj Z[M-k])/2 - (i/2) w^k (Z[k] - conj Z[M-k]),
+// w = exp(-2 pi i / N).  power_of_pair returns |X[k]|^2 and |X[M-k]|^2.
+__device__ __forceinline__ void real_bins_from_packed(double2 zk, double2 zmk, double2 wk, double2* xk, double2* xmk) {
+    // e = (Z[k] + conj Z[M-k])/2 ; o = (Z[k] - conj Z[M-k])/2
+    double ex = 0.5 * (zk.x + zmk.x), ey = 0.5 * (zk.y - zmk.y);
+    double ox = 0.5 * (zk.x - zmk.x), oy = 0.5 * (zk.y + zmk.y);
+    // -i * w^k * o
+    double2 wo = cmul(wk, make_double2(ox, oy));
+    *xk = make_double2(ex + wo.y, ey - wo.x);
+    // X[M-k] = conj(e) - (-i w^k o)^*  ... derived from Hermitian symmetry: X[M-k] = conj(e) + i conj(w^k o)... use direct form
+    *xmk = make_double2(ex - wo.y, -ey - wo.x);
+}
+
+// After fft_dif<-1>(a, M): replace the packed spectrum by the packed half-spectrum Y of a real-even spectrum
+// F(P[k]) so that fft_dit<+1>(a, M) yields y[n] = c[2n] + i c[2n+1] with c = sum_{k<N} F(P)[k] exp(+2 pi i k n / N)
+// (unnormalised inverse).  F is applied to the power |X[k]|^2 (identity for autocorrelation, log for the cepstrum).
+// If pw != nullptr the (transformed) half-spectrum values F(P[k]), k = 0..M, are also written there.
+template <class F>
+__device__ __forceinline__ void packed_power_to_inverse_input(double2* a, int M, int logM, const double2* __restrict__ tw,
+                                                              F f, double* pw) {
+    int N = 2 * M;
+    for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
+        if (k == 0) {
+            double2 z0 = a[0];
+            double p0 = f((z0.x + z0.y) * (z0.x + z0.y));
+            double pM = f((z0.x - z0.y) * (z0.x - z0.y));
+            a[0] = make_double2(p0 + pM, p0 - pM);
+            if (pw) { pw[0] = p0; pw[M] = pM; }
+        } else {
+            int ik = bitrev(k, logM), imk = bitrev(M - k, logM);
+            double2 zk = a[ik], zmk = a[imk];
+            double2 wk = __ldg(tw + k * (TW_N / N));           // exp(-2 pi i k / N)
+            double2 xk, xmk;
+            real_bins_from_packed(zk, zmk, wk, &xk, &xmk);
+            double pk = f(xk.x * xk.x + xk.y * xk.y);
+            double pmk = f(xmk.x * xmk.x + xmk.y * xmk.y);
+            if (pw) { pw[k] = pk; pw[M - k] = pmk; }
+            // Y[k] = (P[k] + P[M-k]) + i w'^k (P[k] - P[M-k]),  w' = conj(w);  Y[M-k] likewise with k -> M-k
+            double s = pk + pmk, d = pk - pmk;
+            // i * conj(wk) * d = i*(wk.x - i wk.y)*d = (wk.y*d) + i (wk.x*d)
+            double2 yk = make_double2(s + wk.y * d, wk.x * d);
+            // w'^(M-k) = exp(2 pi i (M-k)/N) = exp(i pi) * conj(w'^k)... = -(wk.x + i wk.y) ; P diff = -d
+            // i * (-(wk.x + i wk.y)) * (-d) = i (wk.x + i wk.y) d = (-wk.y d) + i (wk.x d)
+            double2 ymk = make_double2(s - wk.y * d, wk.x * d);
+            a[ik] = yk;
+            if (imk != ik) a[imk] = ymk;
+        }
+    }
+    __syncthreads();
+}
+
+struct IdentityF { __device__ __forceinline__ double operator()(double p) const { return p; } };

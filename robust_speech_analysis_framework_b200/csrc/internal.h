@@ -1,0 +1,106 @@
+// internal.h -- host-side declarations shared by the .cu translation units of libmshds_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MAXCAND 15             // Pitch candidates kept per frame for the Viterbi passes (incl. the voiceless one)
+
+// Per speaker-class configuration of one Sound_to_Pitch_any call (fon/Sound_to_Pitch.cpp set-up section).
+struct PitchCfg {
+    double floor_hz, ceiling, dt, ppw, dt_window, grid_window;
+    double vt, octave_cost, sil, jump_cost, vuv_cost;
+    int method;                // 0 = AC_HANNING, 2 = FCC_NORMAL
+    int nsamp_period, halfnsamp_period, nsamp_window, halfnsamp_window, maximumLag, brent_ixmax;
+    int nsampFFT, M, logM;     // AC only: real FFT size, packed complex size
+    int maxn;                  // maxnCandidates after the floor(ceiling/floor) raise
+    const double* window;      // [nsamp_window]   (AC)
+    const double* windowR;     // [nsampFFT]       (AC) normalised window autocorrelation
+};
+
+// One pitch analysis over the whole chunk (all clips).
+struct PitchPass {
+    PitchCfg cfg[3];           // indexed by speaker class; identical entries for class-independent passes
+    int hnr_mode;              // 1: Sound_to_Harmonicity_cc (per-frame best strength only, no Viterbi)
+    int* nF;                   // [n_clips]   frames per clip (0 when Praat would throw)
+    double* t1;                // [n_clips]   time of first frame
+    int* fstart;               // [n_clips+1] exclusive scan of nF
+    // candidate scratch (shared between passes)
+    double* cand_f;            // [frames*MAXCAND]
+    double* cand_s;
+    double* cand_score;        // local Viterbi score (delta)
+    double* cand_lf;           // log2(f) of voiced candidates, -1 for voiceless
+    uint8_t* ncand;            // [frames]
+    uint8_t* psi;              // [frames*16] Viterbi back-pointers
+    // results
+    double* sel_f;             // [frames] frequency of the chosen candidate (0 = voiceless)
+    double* sel_s;             // [frames] strength of the chosen candidate / HNR: best r (NaN when voiceless)
+};
+
+struct Clips {
+    int n;
+    const int16_t* pcm;        // packed int16 samples of the chunk
+    const long long* off;      // [n+1] sample offsets into pcm
+    double fs, dx;
+    double* mean;              // [n] mean sample value
+    double* gpeak;             // [n] max |s - mean|   (Sound_to_Pitch_any globalPeak)
+    double* apeak;             // [n] max |s|          (Sound_Pitch_to_PointProcess_cc globalPeak)
+    int* cls;                  // [n] speaker class (CLS_*)
+    uint32_t* status;          // [n]
+    double* feat;              // [n*25]
+};
+
+// Glottal pulse sets (PointProcess) per clip
+struct Pulses {
+    int* cap_start;            // [n+1] capacity offsets per clip
+    double* t;                 // pulses, clip c in [cap_start[c], cap_start[c]+count[c])
+    int* count;                // [n]
+    // stretch work-list
+    int* st_count;             // [n]   voiced stretches per clip
+    int* st_start;             // [n+1] exclusive scan
+    int* st_ileft;             // [total stretches] first voiced frame (1-based)
+    int* st_iright;            // last voiced frame
+    // per-stretch raw output
+    double* raw_t;             // scratch [cap_total + extra]
+    double* raw_thr;           // 0.8/f0 of left-walk points (for the addedRight rule)
+    int* raw_nleft;            // [stretch] number of left-walk points
+    int* raw_nright;           // [stretch] number of points in first+right walk
+    double* raw_added_right;   // [stretch] last right-added time or -1e308
+};
+
+// ---- launchers (each in its own .cu) ----------------------------------------------------------------------------
+void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch /* n*16 bytes */, cudaStream_t s);
+void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s);
+
+void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s);
+void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
+void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
+void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
+void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones
+void launch_hnr_mean(const Clips& c, const PitchPass& p, cudaStream_t s);
+
+
+// Sound_to_Intensity pass
+struct IntensityPass {
+    int class_dep;             // 1: minimum pitch = speaker-class floor, 0: min_pitch[0]
+    double min_pitch[3];
+    double dt;
+    int halfN[3];
+    const double* win[3];      // [2*halfN+1] Kaiser-20 window per class
+    int* nF; double* t1; int* fstart;
+    double* out;               // [frames] dB
+};
+void launch_intensity(const Clips& c, const IntensityPass& p, int max_frames_hint, cudaStream_t s);
+void launch_contour_stats(const Clips& c, const IntensityPass& p, double* stats /*[n*4] min,max,q99,mean_energy*/,
+                          int want_quantile, cudaStream_t s);
+void launch_intensity_features(const Clips& c, const IntensityPass& p, const double* stats, cudaStream_t s);
+
+// Sound_to_Spectrogram + spectral moments pass
+struct SpecPass {
+    double physicalAnalysisWidth, timeStep, freqStep, y1, oneByBinWidth;
+    int nsamp_window, halfnsamp_window, nsampFFT, M, logM, numberOfFreqs, binWidth_samples;
+    const double* window;      // [nsamp_window] Gaussian (float32-rounded like Praat)
+    int* nF; double* t1; int* fstart;
+    double* mom;               // [frames*4]
+};
+void launch_moments(const Clips& c, const SpecPass& p, const PitchPass& pp, const double2* tw, int max_frames_hint,
+                    cudaStream_t s);

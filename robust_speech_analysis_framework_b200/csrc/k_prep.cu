@@ -1,0 +1,114 @@
+// k_prep.cu -- per-clip statistics over the packed ragged int16 batch, and the work-list prefix scans.
+//
+// The batch stays int16 in HBM (2 B/sample is the algorithmic traffic of the whole pipeline); every
+// kernel converts on load.  Integer sums are exact, so the clip mean and the two global peaks used by
+// Sound_to_Pitch_any (max |s - mean|) and Sound_Pitch_to_PointProcess_cc (max |s|) are bit-identical to a serial
+// float64 loop over the samples.
+#include "internal.h"
+#include "common.cuh"
+#include <limits.h>
+
+#define STAT_CHUNK 65536
+
+__global__ void k_stats_init(int n, long long* sum, int* mn, int* mx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { sum[i] = 0; mn[i] = INT_MAX; mx[i] = INT_MIN; }
+}
+
+__global__ void __launch_bounds__(256) k_stats_accum(Clips c, long long* sum, int* mn, int* mx) {
+    const int clip = blockIdx.x;
+    const long long base = c.off[clip], nx = c.off[clip + 1] - base;
+    const long long s0 = (long long)blockIdx.y * STAT_CHUNK;
+    if (s0 >= nx) return;
+    long long s1 = s0 + STAT_CHUNK < nx ? s0 + STAT_CHUNK : nx;
+    const int16_t* __restrict__ pcm = c.pcm + base;
+    long long acc = 0;
+    int lo = INT_MAX, hi = INT_MIN;
+    // 4-byte vector body when the clip start is 4-byte aligned, scalar otherwise
+    long long i = s0 + threadIdx.x;
+    for (; i < s1; i += blockDim.x) {
+        int v = __ldg(pcm + i);
+        acc += v; lo = min(lo, v); hi = max(hi, v);
+    }
+    // warp reduce, then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(FULL_MASK, acc, o);
+        lo = min(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+        hi = max(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long*)&sum[clip], (unsigned long long)acc);
+        atomicMin(&mn[clip], lo);
+        atomicMax(&mx[clip], hi);
+    }
+}
+
+__global__ void k_stats_final(Clips c, const long long* sum, const int* mn, const int* mx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    long long nx = c.off[i + 1] - c.off[i];
+    c.cls[i] = 0;
+    c.status[i] = 0;
+    for (int k = 0; k < N_FEAT; k++) c.feat[(size_t)i * N_FEAT + k] = DEVNAN;
+    if (nx <= 0) { c.mean[i] = 0; c.gpeak[i] = 0; c.apeak[i] = 0; c.status[i] = ST_FILE; return; }
+    double mean = ((double)sum[i] / 32768.0) / (double)nx;
+    double smin = (double)mn[i] / 32768.0, smax = (double)mx[i] / 32768.0;
+    c.mean[i] = mean;
+    c.gpeak[i] = fmax(fabs(smax - mean), fabs(smin - mean));
+    c.apeak[i] = fmax(fabs(smax), fabs(smin));
+}
+
+
+void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch, cudaStream_t s) {
+    // scratch: n * (8 + 4 + 4) bytes
+    long long* sum = (long long*)scratch;
+    int* mn = (int*)(sum + c.n);
+    int* mx = mn + c.n;
+    k_stats_init<<<(c.n + 255) / 256, 256, 0, s>>>(c.n, sum, mn, mx);
+    int chunks = (int)((max_clip_len + STAT_CHUNK - 1) / STAT_CHUNK);
+    if (chunks < 1) chunks = 1;
+    dim3 grid(c.n, chunks);
+    k_stats_accum<<<grid, 256, 0, s>>>(c, sum, mn, mx);
+    k_stats_final<<<(c.n + 255) / 256, 256, 0, s>>>(c, sum, mn, mx);
+}
+
+// exclusive scan of n counts into n+1 prefix entries (single CTA; n is the number of clips / segments)
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__ counts, int* __restrict__ prefix, int n) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < n ? counts[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(FULL_MASK, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            int t = wsum[lane];
+            int xs = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(FULL_MASK, xs, o);
+                if (lane >= o) xs += y;
+            }
+            wsum[lane] = xs - t;     // exclusive warp offsets
+        }
+        __syncthreads();
+        int carry = carry_s;
+        int incl = carry + wsum[w] + x;
+        if (i < n) prefix[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) prefix[n] = carry_s;
+}
+
+void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s) {
+    k_exclusive_scan<<<1, 1024, 0, s>>>(counts, prefix, n);
+}

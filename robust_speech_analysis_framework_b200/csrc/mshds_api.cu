@@ -1,0 +1,512 @@
+// mshds_api.cu -- C ABI (include/mshds_b200.h), handle / scratch management and the per-chunk orchestration that mirrors
+// the body of extract_mshds_features (src/mshds_extractor.py:408-448), stage by stage.
+#include "../../include/mshds_b200.h"
+#include "internal.h"
+#include "common.cuh"
+#include "num.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char b_[512];                                                                             \
+            snprintf(b_, sizeof b_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            h->err = b_;                                                                              \
+            return MSHDS_ERR_CUDA;                                                                    \
+        }                                                                                             \
+    } while (0)
+
+struct DebugEntry {
+    const void* base;
+    const int* start;       // device prefix array (per clip) or nullptr => start = clip * fixed
+    const int* count;       // device per-clip count or nullptr => fixed
+    int fixed;
+    int elem_size;
+    int stride;             // elements per item (e.g. 15 for candidates)
+};
+
+struct mshds_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    long long chunk_samples = 1LL << 27;
+    // persistent tables
+    double2* tw = nullptr;
+    std::map<int, std::pair<double*, double*>> ac_windows;      // nsamp_window -> (window, windowR)
+    std::map<long long, double*> kaiser;                        // key -> window
+    std::map<int, double*> gauss_spec;
+    // arena
+    char* arena = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
+    bool arena_overflow = false;
+    std::map<std::string, DebugEntry> debug;
+    int last_n = 0;
+};
+
+// ------------------------------------------------------------------------------------------------ arena
+static void* arena_take(mshds_handle* h, size_t bytes) {
+    size_t o = (h->arena_off + 255) & ~(size_t)255;
+    if (o + bytes > h->arena_cap) { h->arena_overflow = true; h->arena_off = o + bytes; return nullptr; }
+    h->arena_off = o + bytes;
+    return h->arena + o;
+}
+template <class T>
+static T* take(mshds_handle* h, size_t n) { return (T*)arena_take(h, sizeof(T) * (n ? n : 1)); }
+
+// ------------------------------------------------------------------------------------------------ host FFT (set-up only)
+static void host_fft(std::vector<double>& re, std::vector<double>& im, int sign) {
+    size_t n = re.size();
+    for (size_t i = 0, j = 0; i < n - 1; i++) {
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+        size_t m = n >> 1;
+        while (m >= 1 && (j & m)) { j ^= m; m >>= 1; }
+        j |= m;
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        size_t half = len >> 1;
+        for (size_t k = 0; k < half; k++) {
+            double ang = sign * 2.0 * MSHDS_PI * (double)k / (double)len;
+            double wr = cos(ang), wi = sin(ang);
+            for (size_t i = k; i < n; i += len) {
+                size_t b = i + half;
+                double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[i] - xr; im[b] = im[i] - xi;
+                re[i] += xr; im[i] += xi;
+            }
+        }
+    }
+}
+
+static int upload(mshds_handle* h, const std::vector<double>& v, double** out) {
+    CK(cudaMalloc((void**)out, sizeof(double) * v.size()));
+    CK(cudaMemcpy(*out, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+    return MSHDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ configurations
+// fon/Sound_to_Pitch.cpp Sound_to_Pitch_any: everything before the frame loop.
+static int make_pitch_cfg(mshds_handle* h, double fs, double dt, double floor_hz, double ppw, int maxn, int method,
+                          double sil, double vt, double oct, double jump, double vuv, double ceiling, PitchCfg* g) {
+    double dx = 1.0 / fs;
+    memset(g, 0, sizeof(*g));
+    if (maxn < ceiling / floor_hz) maxn = (int)floor(ceiling / floor_hz);
+    if (dt <= 0.0) dt = ppw / floor_hz / 4.0;
+    g->floor_hz = floor_hz; g->dt = dt; g->ppw = ppw; g->method = method;
+    g->sil = sil; g->vt = vt; g->octave_cost = oct; g->jump_cost = jump; g->vuv_cost = vuv;
+    g->nsamp_period = (int)floor(1.0 / dx / floor_hz);
+    g->halfnsamp_period = g->nsamp_period / 2 + 1;
+    if (ceiling > 0.5 / dx) ceiling = 0.5 / dx;
+    g->ceiling = ceiling;
+    g->dt_window = ppw / floor_hz;
+    g->nsamp_window = (int)floor(g->dt_window / dx);
+    g->halfnsamp_window = g->nsamp_window / 2 - 1;
+    g->nsamp_window = g->halfnsamp_window * 2;
+    g->maximumLag = (int)floor(g->nsamp_window / ppw) + 2;
+    if (g->maximumLag > g->nsamp_window) g->maximumLag = g->nsamp_window;
+    g->grid_window = method >= 2 ? 1.0 / floor_hz + g->dt_window : g->dt_window;
+    g->maxn = maxn;
+    if (method >= 2) {
+        g->brent_ixmax = g->nsamp_window;
+        return MSHDS_OK;
+    }
+    int nfft = 1;
+    while (nfft < g->nsamp_window * 1.5) nfft *= 2;
+    g->nsampFFT = nfft; g->M = nfft / 2;
+    g->logM = 0;
+    while ((1 << g->logM) < g->M) g->logM++;
+    g->brent_ixmax = (int)floor(g->nsamp_window * 0.5);
+    auto it = h->ac_windows.find(g->nsamp_window);
+    if (it == h->ac_windows.end()) {
+        int W = g->nsamp_window;
+        std::vector<double> win(W), re(nfft, 0.0), im(nfft, 0.0);
+        for (int i = 1; i <= W; i++) win[i - 1] = 0.5 - 0.5 * cos(i * 2 * MSHDS_PI / (W + 1));
+        for (int i = 0; i < W; i++) re[i] = win[i];
+        host_fft(re, im, -1);
+        for (int i = 0; i < nfft; i++) { re[i] = re[i] * re[i] + im[i] * im[i]; im[i] = 0.0; }
+        host_fft(re, im, +1);
+        std::vector<double> wr(nfft);
+        for (int i = 0; i < nfft; i++) wr[i] = re[i];
+        for (int i = 1; i < W; i++) wr[i] /= wr[0];
+        wr[0] = 1.0;
+        double *dw, *dr;
+        int rc = upload(h, win, &dw); if (rc) return rc;
+        rc = upload(h, wr, &dr); if (rc) return rc;
+        it = h->ac_windows.emplace(W, std::make_pair(dw, dr)).first;
+    }
+    g->window = it->second.first;
+    g->windowR = it->second.second;
+    return MSHDS_OK;
+}
+
+static int make_kaiser(mshds_handle* h, double fs, double minPitch, int* halfN, const double** win) {
+    double dx = 1.0 / fs;
+    double halfWindowDuration = 0.5 * (6.4 / minPitch);
+    int hn = (int)floor(halfWindowDuration / dx);
+    long long key = (long long)llround(minPitch * 1000.0) * 100000 + (long long)llround(fs);
+    auto it = h->kaiser.find(key);
+    if (it == h->kaiser.end()) {
+        std::vector<double> w(2 * hn + 1);
+        for (int i = -hn; i <= hn; i++) {
+            double x = i * dx / halfWindowDuration;
+            double root = 1.0 - x * x;
+            w[i + hn] = root <= 0.0 ? 0.0 : bessel_i0_f((2.0 * MSHDS_PI * MSHDS_PI + 0.5) * sqrt(root));
+        }
+        double* d;
+        int rc = upload(h, w, &d); if (rc) return rc;
+        it = h->kaiser.emplace(key, d).first;
+    }
+    *halfN = hn;
+    *win = it->second;
+    return MSHDS_OK;
+}
+
+// fon/Sound_and_Spectrogram.cpp Sound_to_Spectrogram (0.025, 5000, 0.005, 20, GAUSSIAN, 8, 8): set-up section
+static int make_spec_cfg(mshds_handle* h, double fs, SpecPass* p) {
+    double dx = 1.0 / fs, nyquist = 0.5 / dx;
+    double effectiveAnalysisWidth = 0.025, fmax = 5000.0, minimumTimeStep1 = 0.005, minimumFreqStep1 = 20.0;
+    memset(p, 0, sizeof(*p));
+    double physicalAnalysisWidth = 2 * effectiveAnalysisWidth;
+    double effectiveTimeWidth = effectiveAnalysisWidth / sqrt(MSHDS_PI);
+    double effectiveFreqWidth = 1 / effectiveTimeWidth;
+    double minimumTimeStep2 = effectiveTimeWidth / 8.0, minimumFreqStep2 = effectiveFreqWidth / 8.0;
+    double timeStep = minimumTimeStep1 > minimumTimeStep2 ? minimumTimeStep1 : minimumTimeStep2;
+    double freqStep = minimumFreqStep1 > minimumFreqStep2 ? minimumFreqStep1 : minimumFreqStep2;
+    int nsamp_window = (int)floor(physicalAnalysisWidth / dx);
+    int halfnsamp_window = nsamp_window / 2 - 1;
+    nsamp_window = halfnsamp_window * 2;
+    if (fmax <= 0.0 || fmax > nyquist) fmax = nyquist;
+    int numberOfFreqs = (int)floor(fmax / freqStep);
+    int nsampFFT = 1;
+    while (nsampFFT < nsamp_window || nsampFFT < 2 * numberOfFreqs * (nyquist / fmax)) nsampFFT *= 2;
+    int binWidth_samples = (int)floor(freqStep * dx * nsampFFT);
+    if (binWidth_samples < 1) binWidth_samples = 1;
+    double binWidth_hertz = 1.0 / (dx * nsampFFT);
+    freqStep = binWidth_samples * binWidth_hertz;
+    numberOfFreqs = (int)floor(fmax / freqStep);
+    p->physicalAnalysisWidth = physicalAnalysisWidth; p->timeStep = timeStep; p->freqStep = freqStep;
+    p->y1 = 0.5 * (freqStep - binWidth_hertz);
+    p->nsamp_window = nsamp_window; p->halfnsamp_window = halfnsamp_window; p->nsampFFT = nsampFFT; p->M = nsampFFT / 2;
+    p->logM = 0;
+    while ((1 << p->logM) < p->M) p->logM++;
+    p->numberOfFreqs = numberOfFreqs; p->binWidth_samples = binWidth_samples;
+    std::vector<double> w(nsamp_window);
+    double windowssq = 0.0;
+    for (int i = 1; i <= nsamp_window; i++) {
+        double nSamplesPerWindow_f = physicalAnalysisWidth / dx;
+        double imid = 0.5 * (double)(nsamp_window + 1), edge = exp(-12.0);
+        double phase = ((double)i - imid) / nSamplesPerWindow_f;
+        double value = (exp(-48.0 * phase * phase) - edge) / (1.0 - edge);
+        w[i - 1] = (double)(float)value;
+        windowssq += value * value;
+    }
+    p->oneByBinWidth = 1.0 / windowssq / binWidth_samples;
+    auto it = h->gauss_spec.find(nsamp_window);
+    if (it == h->gauss_spec.end()) {
+        double* d;
+        int rc = upload(h, w, &d); if (rc) return rc;
+        it = h->gauss_spec.emplace(nsamp_window, d).first;
+    }
+    p->window = it->second;
+    return MSHDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pass allocation
+static long long frames_upper_bound(const std::vector<long long>& lens, double dx, double dt) {
+    long long t = 0;
+    for (long long n : lens) t += (long long)floor((double)n * dx / dt) + 2;
+    return t;
+}
+
+struct CandScratchBuf { double *f, *s, *score, *lf; uint8_t *ncand, *psi; long long cap; };
+
+static void alloc_pitch_pass(mshds_handle* h, PitchPass* p, int n, long long fub, const CandScratchBuf& cs) {
+    p->nF = take<int>(h, n);
+    p->t1 = take<double>(h, n);
+    p->fstart = take<int>(h, n + 1);
+    p->sel_f = take<double>(h, fub);
+    p->sel_s = take<double>(h, fub);
+    p->cand_f = cs.f; p->cand_s = cs.s; p->cand_score = cs.score; p->cand_lf = cs.lf; p->ncand = cs.ncand; p->psi = cs.psi;
+}
+
+static void reg_debug(mshds_handle* h, const char* name, const void* base, const int* start, const int* count, int fixed,
+                      int elem_size, int stride = 1) {
+    DebugEntry e{base, start, count, fixed, elem_size, stride};
+    h->debug[name] = e;
+}
+
+// ------------------------------------------------------------------------------------------------ one chunk
+static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vector<long long>& off_host, double fs,
+                         double* d_feat, uint32_t* d_status, bool dry_run) {
+    cudaStream_t s = h->stream;
+    const int n = (int)off_host.size() - 1;
+    const double dx = 1.0 / fs;
+    std::vector<long long> lens(n);
+    long long maxlen = 0;
+    for (int i = 0; i < n; i++) { lens[i] = off_host[i + 1] - off_host[i]; if (lens[i] > maxlen) maxlen = lens[i]; }
+
+    h->arena_off = 0;
+    h->arena_overflow = false;
+    h->debug.clear();
+
+    Clips c;
+    c.n = n; c.pcm = d_pcm; c.fs = fs; c.dx = dx;
+    long long* d_off = take<long long>(h, n + 1);
+    c.off = d_off;
+    c.mean = take<double>(h, n); c.gpeak = take<double>(h, n); c.apeak = take<double>(h, n);
+    c.cls = take<int>(h, n);
+    c.status = d_status; c.feat = d_feat;
+    void* stat_scratch = arena_take(h, (size_t)n * 16);
+
+    // ---- pitch pass configurations (parselmouth defaults unless mshds_extractor.py passes a value)
+    PitchPass wide, mainp, hnr;
+    memset(&wide, 0, sizeof wide); memset(&mainp, 0, sizeof mainp); memset(&hnr, 0, sizeof hnr);
+    int rc;
+    for (int k = 0; k < 3; k++) {
+        // :143 to_pitch_ac(time_step=0.005, pitch_floor=50, pitch_ceiling=600)
+        if ((rc = make_pitch_cfg(h, fs, 0.005, 50.0, 3.0, 15, 0, 0.03, 0.45, 0.01, 0.35, 0.14, 600.0, &wide.cfg[k]))) return rc;
+        // :178 / :355 to_pitch_ac(0.005, floor, ceiling)
+        if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 3.0, 15, 0, 0.03, 0.45, 0.01, 0.35, 0.14, cls_ceiling(k), &mainp.cfg[k]))) return rc;
+        // :221 to_harmonicity_cc(0.005, floor, 0.1, 4.5): FCC, 15 candidates, all path costs 0, ceiling = Nyquist
+        if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 4.5, 15, 2, 0.1, 0.0, 0.0, 0.0, 0.0, 0.5 * fs, &hnr.cfg[k]))) return rc;
+    }
+    hnr.hnr_mode = 1;
+
+    const long long fub5 = frames_upper_bound(lens, dx, 0.005);
+    CandScratchBuf cs;
+    cs.cap = fub5;
+    cs.f = take<double>(h, fub5 * MAXCAND); cs.s = take<double>(h, fub5 * MAXCAND);
+    cs.score = take<double>(h, fub5 * MAXCAND); cs.lf = take<double>(h, fub5 * MAXCAND);
+    cs.ncand = take<uint8_t>(h, fub5); cs.psi = take<uint8_t>(h, fub5 * 16);
+    alloc_pitch_pass(h, &wide, n, fub5, cs);
+    alloc_pitch_pass(h, &mainp, n, fub5, cs);
+    alloc_pitch_pass(h, &hnr, n, fub5, cs);
+
+    // ---- intensity (:198) and spectrogram (:356)
+    IntensityPass imain;
+    memset(&imain, 0, sizeof imain);
+    imain.class_dep = 1; imain.dt = 0.005;
+    for (int k = 0; k < 3; k++) {
+        imain.min_pitch[k] = cls_floor(k);
+        if ((rc = make_kaiser(h, fs, cls_floor(k), &imain.halfN[k], &imain.win[k]))) return rc;
+    }
+    imain.nF = take<int>(h, n); imain.t1 = take<double>(h, n); imain.fstart = take<int>(h, n + 1);
+    imain.out = take<double>(h, fub5);
+    double* imain_stats = take<double>(h, (size_t)n * 4);
+
+    SpecPass spec;
+    if ((rc = make_spec_cfg(h, fs, &spec))) return rc;
+    spec.nF = take<int>(h, n); spec.t1 = take<double>(h, n); spec.fstart = take<int>(h, n + 1);
+    spec.mom = take<double>(h, fub5 * 4);
+
+    if (dry_run) return MSHDS_OK;           // sizing pass only
+    if (h->arena_overflow) { h->err = "internal: arena overflow after sizing"; return MSHDS_ERR_CUDA; }
+
+    CK(cudaMemcpyAsync(d_off, off_host.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
+    const int fhint = (int)(fub5 > 0x3fffffff ? 0x3fffffff : fub5);
+
+    // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
+    launch_clip_stats(c, maxlen, stat_scratch, s); h->launches += 3;
+
+    // ---- _pitch_values (:127-162): wide AC pass -> speaker class
+    launch_pitch_grid(c, wide, s); h->launches += 2;
+    launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1;
+    launch_pitch_viterbi(c, wide, s); h->launches += 1;
+    launch_pitch_class(c, wide, s); h->launches += 1;
+
+    // ---- _extract_pitch (:164-183)
+    launch_pitch_grid(c, mainp, s); h->launches += 2;
+    launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1;
+    launch_pitch_viterbi(c, mainp, s); h->launches += 1;
+    launch_pitch_stats(c, mainp, s); h->launches += 1;
+
+    // ---- _extract_intensity (:185-205)
+    launch_intensity(c, imain, fhint, s); h->launches += 3;
+    launch_contour_stats(c, imain, imain_stats, 0, s); h->launches += 1;
+    launch_intensity_features(c, imain, imain_stats, s); h->launches += 1;
+
+    // ---- _extract_harmonicity (:207-225)
+    launch_pitch_grid(c, hnr, s); h->launches += 2;
+    launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1;
+    launch_hnr_mean(c, hnr, s); h->launches += 1;
+
+    // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
+    launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4;
+
+    CK(cudaGetLastError());
+
+    reg_debug(h, "pitch_wide_f", wide.sel_f, wide.fstart, wide.nF, 0, 8);
+    reg_debug(h, "pitch_main_f", mainp.sel_f, mainp.fstart, mainp.nF, 0, 8);
+    reg_debug(h, "pitch_main_s", mainp.sel_s, mainp.fstart, mainp.nF, 0, 8);
+    reg_debug(h, "hnr_r", hnr.sel_s, hnr.fstart, hnr.nF, 0, 8);
+    reg_debug(h, "intensity_main", imain.out, imain.fstart, imain.nF, 0, 8);
+    reg_debug(h, "moments", spec.mom, spec.fstart, spec.nF, 0, 8, 4);
+    reg_debug(h, "class", c.cls, nullptr, nullptr, 1, 4);
+    h->last_n = n;
+    return MSHDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int mshds_create(int device, mshds_handle** out) {
+    if (!out) return MSHDS_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return MSHDS_ERR_CUDA;
+    mshds_handle* h = new mshds_handle();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return MSHDS_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    // twiddle table exp(-2 pi i j / TW_N), j < TW_N/2
+    const int TWN = 8192;
+    std::vector<double> tw(TWN);
+    for (int j = 0; j < TWN / 2; j++) {
+        tw[2 * j] = cos(2.0 * MSHDS_PI * (double)j / (double)TWN);
+        tw[2 * j + 1] = -sin(2.0 * MSHDS_PI * (double)j / (double)TWN);
+    }
+    if (cudaMalloc((void**)&h->tw, sizeof(double) * TWN) != cudaSuccess ||
+        cudaMemcpy(h->tw, tw.data(), sizeof(double) * TWN, cudaMemcpyHostToDevice) != cudaSuccess) {
+        delete h;
+        return MSHDS_ERR_CUDA;
+    }
+    *out = h;
+    return MSHDS_OK;
+}
+
+void mshds_destroy(mshds_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : h->ac_windows) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
+    for (auto& kv : h->kaiser) cudaFree(kv.second);
+    for (auto& kv : h->gauss_spec) cudaFree(kv.second);
+    cudaFree(h->tw);
+    cudaFree(h->arena);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int mshds_set_stream(mshds_handle* h, void* cuda_stream) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return MSHDS_OK;
+}
+
+int mshds_set_chunk_samples(mshds_handle* h, long long max_samples) {
+    if (!h || max_samples < 1) return MSHDS_ERR_ARG;
+    h->chunk_samples = max_samples;
+    return MSHDS_OK;
+}
+
+const char* mshds_last_error(const mshds_handle* h) { return h ? h->err.c_str() : "null handle"; }
+long long mshds_launch_count(const mshds_handle* h) { return h ? h->launches : 0; }
+
+int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
+                  double* features, uint32_t* status, unsigned flags) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->err.clear();
+    if (n_clips < 0 || (n_clips > 0 && (!pcm || !offsets || !features))) { h->err = "null pointer argument"; return MSHDS_ERR_ARG; }
+    if (sample_rate != 16000) { h->err = "sample_rate must be 16000 (resample(16000, 50) front-end not built yet)"; return MSHDS_ERR_UNSUPPORTED; }
+    if (n_clips == 0) return MSHDS_OK;
+    for (int i = 0; i < n_clips; i++)
+        if (offsets[i + 1] < offsets[i]) { h->err = "offsets must be non-decreasing"; return MSHDS_ERR_ARG; }
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const bool pcm_dev = flags & MSHDS_PCM_ON_DEVICE, out_dev = flags & MSHDS_OUT_ON_DEVICE;
+    const double fs = (double)sample_rate;
+
+    int c0 = 0;
+    while (c0 < n_clips) {
+        // clips [c0, c1) form one chunk
+        int c1 = c0;
+        long long tot = 0;
+        while (c1 < n_clips && (c1 == c0 || tot + (offsets[c1 + 1] - offsets[c1]) <= h->chunk_samples)) {
+            tot += offsets[c1 + 1] - offsets[c1];
+            c1++;
+        }
+        const int n = c1 - c0;
+        std::vector<long long> off(n + 1);
+        for (int i = 0; i <= n; i++) off[i] = offsets[c0 + i] - offsets[c0];
+
+        // sizing pass, then (re)allocate the arena
+        char* saved = h->arena;
+        size_t saved_cap = h->arena_cap;
+        h->arena = nullptr; h->arena_cap = 0;
+        int rc = process_chunk(h, nullptr, off, fs, nullptr, nullptr, true);
+        h->arena = saved; h->arena_cap = saved_cap;
+        if (rc) return rc;
+        size_t need = h->arena_off + (pcm_dev ? 0 : (size_t)tot * 2 + 512) + (out_dev ? 0 : (size_t)n * (25 * 8 + 4) + 512) + 4096;
+        if (need > h->arena_cap) {
+            CK(cudaStreamSynchronize(s));
+            if (h->arena) CK(cudaFree(h->arena));
+            h->arena = nullptr; h->arena_cap = 0;
+            CK(cudaMalloc((void**)&h->arena, need + (need >> 3)));
+            h->arena_cap = need + (need >> 3);
+        }
+        // tail of the arena: staging for pcm / outputs when the caller's buffers live on the host
+        size_t tail = h->arena_cap;
+        const int16_t* d_pcm;
+        if (pcm_dev) d_pcm = pcm + offsets[c0];
+        else {
+            tail = (tail - (size_t)tot * 2 - 256) & ~(size_t)255;
+            CK(cudaMemcpyAsync(h->arena + tail, pcm + offsets[c0], (size_t)tot * 2, cudaMemcpyHostToDevice, s));
+            d_pcm = (const int16_t*)(h->arena + tail);
+        }
+        double* d_feat;
+        uint32_t* d_status;
+        if (out_dev) {
+            d_feat = features + (size_t)c0 * 25;
+            d_status = status ? status + c0 : nullptr;
+        } else {
+            tail = (tail - (size_t)n * 25 * 8 - 256) & ~(size_t)255;
+            d_feat = (double*)(h->arena + tail);
+            d_status = nullptr;
+        }
+        if (!d_status) {
+            tail = (tail - (size_t)n * 4 - 256) & ~(size_t)255;
+            d_status = (uint32_t*)(h->arena + tail);
+        }
+        size_t cap_saved = h->arena_cap;
+        h->arena_cap = tail;                       // scratch may not run into the staging area
+        rc = process_chunk(h, d_pcm, off, fs, d_feat, d_status, false);
+        h->arena_cap = cap_saved;
+        if (rc) return rc;
+        if (!out_dev) {
+            CK(cudaMemcpyAsync(features + (size_t)c0 * 25, d_feat, (size_t)n * 25 * 8, cudaMemcpyDeviceToHost, s));
+            if (status) CK(cudaMemcpyAsync(status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+        c0 = c1;
+    }
+    return MSHDS_OK;
+}
+
+int mshds_debug_fetch(mshds_handle* h, const char* name, int clip, void* host_buf, size_t cap_elems, size_t* n_out) {
+    if (!h || !name || !n_out) return MSHDS_ERR_ARG;
+    auto it = h->debug.find(name);
+    if (it == h->debug.end() || clip < 0 || clip >= h->last_n) { h->err = "unknown debug name or clip"; return MSHDS_ERR_ARG; }
+    const DebugEntry& e = it->second;
+    CK(cudaSetDevice(h->device));
+    int start = clip * e.fixed, count = e.fixed;
+    if (e.start) CK(cudaMemcpy(&start, e.start + clip, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e.count) CK(cudaMemcpy(&count, e.count + clip, sizeof(int), cudaMemcpyDeviceToHost));
+    size_t nel = (size_t)count * e.stride;
+    *n_out = nel;
+    size_t ncopy = nel < cap_elems ? nel : cap_elems;
+    if (ncopy && host_buf)
+        CK(cudaMemcpy(host_buf, (const char*)e.base + (size_t)start * e.stride * e.elem_size, ncopy * e.elem_size, cudaMemcpyDeviceToHost));
+    return MSHDS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// num.cuh -- warp-cooperative restatement of Praat's sinc interpolation and Brent peak refinement
+// (melder/NUMinterpol.cpp NUM_interpolate_sinc / NUMimproveExtremum, dwsys/NUM2.cpp NUMminimize_brent), the
+// arithmetic behind every to_pitch_* / to_harmonicity_cc call in mshds_extractor.py and the Sinc70 extrema at :78.
+//
+// One warp evaluates one interpolation: the 2*depth taps are split over the 32 lanes and combined with a fixed-order
+// butterfly sum, so results are deterministic.  The Brent state machine is replicated in every lane (no divergence).
+#pragma once
+#include "common.cuh"
+
+// y is 1-based: y[1..n] valid.  All 32 lanes must call with identical arguments; all lanes get the result.
+__device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane) {
+    int midleft = (int)floor(x), midright = midleft + 1;
+    if (n < 1) return DEVNAN;
+    if (x > n) return y[n];
+    if (x < 1) return y[1];
+    if (x == midleft) return y[midleft];
+    if (maxDepth > midright - 1) maxDepth = midright - 1;
+    if (maxDepth > n - midleft) maxDepth = n - midleft;
+    if (maxDepth <= 0) return y[(int)floor(x + 0.5)];
+    if (maxDepth == 1) return y[midleft] + (x - midleft) * (y[midright] - y[midleft]);
+    if (maxDepth == 2) {
+        double yl = y[midleft], yr = y[midright];
+        double dyl = 0.5 * (yr - y[midleft - 1]), dyr = 0.5 * (y[midright + 1] - yl);
+        double fil = x - midleft, fir = midright - x;
+        return yl * fir + yr * fil - fil * fir * (0.5 * (dyr - dyl) + (fil - 0.5) * (dyl + dyr - 2 * (yr - yl)));
+    }
+    // left side: taps ix = midleft - k, k = 0..maxDepth-1; a_k = pi*(x-midleft) + k*pi; aa_k = a_k / (x-left+1)
+    // right side: ix = midright + k;  a_k = pi*(midright-x) + k*pi; aa_k = a_k / (right-x+1)
+    double fl = x - midleft, fr = midright - x;
+    double hsl = 0.5 * sinpi(fl), hsr = 0.5 * sinpi(fr);
+    double invl = 1.0 / (fl + maxDepth), invr = 1.0 / (fr + maxDepth);     // x-left+1 = fl + depth ; right-x+1 = fr + depth
+    double acc = 0.0;
+    for (int k = lane; k < maxDepth; k += 32) {
+        double sgn = (k & 1) ? -1.0 : 1.0;
+        double al = fl + k, ar = fr + k;                                    // in units of pi
+        double dl = sgn * hsl / (MSHDS_PI * al) * (1.0 + cospi(al * invl));
+        double dr = sgn * hsr / (MSHDS_PI * ar) * (1.0 + cospi(ar * invr));
+        acc += y[midleft - k] * dl + y[midright + k] * dr;
+    }
+    return warp_sum(acc);
+}
+
+// NUMminimize_brent specialised to f(x) = -/+ sinc_interp(y, x, depth); returns x of the extremum, *fx its value
+// (already sign-corrected: the interpolated y at the extremum).
+__device__ __forceinline__ double brent_sinc_warp(const double* y, int n, double a, double b, int depth, bool isMaximum,
+                                                  double* fx_out, int lane) {
+    const double golden = 1.0 - 0.6180339887498948482045868343656381177203;
+    const double sqrt_epsilon = 1.4901161193847656e-08;   // sqrt(DBL_EPSILON)
+    const double tol = 1e-10;
+    const double sg = isMaximum ? -1.0 : 1.0;
+    double x, v, fv, w, fw, fx;
+    v = a + golden * (b - a);
+    fv = sg * sinc_interp_warp(y, n, v, depth, lane);
+    x = v; w = v;
+    fx = fv; fw = fv;
+    for (int iter = 1; iter <= 60; iter++) {
+        double range = b - a;
+        double middle_range = (a + b) / 2.0;
+        double tol_act = sqrt_epsilon * fabs(x) + tol / 3.0;
+        double new_step;
+        if (fabs(x - middle_range) + range / 2.0 <= 2.0 * tol_act) break;
+        new_step = golden * (x < middle_range ? b - x : a - x);
+        if (fabs(x - w) >= tol_act) {
+            double p, q, t;
+            t = (x - w) * (fx - fv);
+            q = (x - v) * (fx - fw);
+            p = (x - v) * q - (x - w) * t;
+            q = 2.0 * (q - t);
+            if (q > 0.0) p = -p; else q = -q;
+            if (fabs(p) < fabs(new_step * q) && p > q * (a - x + 2.0 * tol_act) && p < q * (b - x - 2.0 * tol_act))
+                new_step = p / q;
+        }
+        if (fabs(new_step) < tol_act) new_step = new_step > 0.0 ? tol_act : -tol_act;
+        {
+            double t = x + new_step;
+            double ft = sg * sinc_interp_warp(y, n, t, depth, lane);
+            if (ft <= fx) {
+                if (t < x) b = x; else a = x;
+                v = w; w = x; x = t;
+                fv = fw; fw = fx; fx = ft;
+            } else {
+                if (t < x) a = t; else b = t;
+                if (ft <= fw || w == x) {
+                    v = w; w = t;
+                    fv = fw; fw = ft;
+                } else if (ft <= fv || v == x || v == w) {
+                    v = t;
+                    fv = ft;
+                }
+            }
+        }
+    }
+    *fx_out = sg * fx;
+    return x;
+}
+
+#define PEAK_NONE 0
+#define PEAK_PARABOLIC 1
+#define PEAK_SINC70 3
+#define PEAK_SINC700 4
+
+// NUMimproveExtremum (warp-cooperative for the sinc modes). y 1-based.
+__device__ __forceinline__ double improve_extremum_warp(const double* y, int n, int ixmid, int interpolation,
+                                                        double* ixmid_real, bool isMaximum, int lane) {
+    if (ixmid <= 1) { *ixmid_real = 1; return y[1]; }
+    if (ixmid >= n) { *ixmid_real = n; return y[n]; }
+    if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y[ixmid]; }
+    if (interpolation == PEAK_PARABOLIC) {
+        double dy = 0.5 * (y[ixmid + 1] - y[ixmid - 1]);
+        double d2y = 2 * y[ixmid] - y[ixmid - 1] - y[ixmid + 1];
+        *ixmid_real = ixmid + dy / d2y;
+        return y[ixmid] + 0.5 * dy * dy / d2y;
+    }
+    double fx;
+    *ixmid_real = brent_sinc_warp(y, n, (double)(ixmid - 1), (double)(ixmid + 1), interpolation == PEAK_SINC70 ? 70 : 700,
+                                  isMaximum, &fx, lane);
+    return fx;
+}
+
+// single-thread parabolic / none variant
+__device__ __forceinline__ double improve_extremum_simple(const double* y, int n, int ixmid, int interpolation,
+                                                          double* ixmid_real) {
+    if (ixmid <= 1) { *ixmid_real = 1; return y[1]; }
+    if (ixmid >= n) { *ixmid_real = n; return y[n]; }
+    if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y[ixmid]; }
+    double dy = 0.5 * (y[ixmid + 1] - y[ixmid - 1]);
+    double d2y = 2 * y[ixmid] - y[ixmid - 1] - y[ixmid + 1];
+    *ixmid_real = ixmid + dy / d2y;
+    return y[ixmid] + 0.5 * dy * dy / d2y;
+}
+
+// NUMbessel_i0_f (Abramowitz & Stegun 9.8.1 / 9.8.2), used by the Kaiser-20 intensity window
+__host__ __device__ inline double bessel_i0_f(double x) {
+    if (x < 0.0) x = -x;
+    if (x < 3.75) {
+        double t = x / 3.75;
+        t *= t;
+        return 1.0 + t * (3.5156229 + t * (3.0899424 + t * (1.2067492 + t * (0.2659732 + t * (0.0360768 + t * 0.0045813)))));
+    }
+    double t = 3.75 / x;
+    return exp(x) / sqrt(x) *
+           (0.39894228 + t * (0.01328592 + t * (0.00225319 + t * (-0.00157565 + t * (0.00916281 +
+            t * (-0.02057706 + t * (0.02635537 + t * (-0.01647633 + t * 0.00392377))))))));
+}
