@@ -49,23 +49,33 @@ struct Clips {
     double* feat;              // [n*25]
 };
 
-// Glottal pulse sets (PointProcess) per clip
-struct Pulses {
-    int* cap_start;            // [n+1] capacity offsets per clip
-    double* t;                 // pulses, clip c in [cap_start[c], cap_start[c]+count[c])
+// Glottal pulse sets (PointProcess) of one pitch pass
+struct PulseSet {
+    double cprime;             // raw slots per second of voiced stretch (ceiling / 0.8 with head-room)
+    int* cap_start;            // [n+1] capacity offsets per clip (host-computed upper bounds)
+    double* t;                 // final pulses of clip c: t[cap_start[c] .. +count[c])
     int* count;                // [n]
-    // stretch work-list
     int* st_count;             // [n]   voiced stretches per clip
     int* st_start;             // [n+1] exclusive scan
-    int* st_ileft;             // [total stretches] first voiced frame (1-based)
+    int* st_ileft;             // [frames] first voiced frame (1-based) of stretch k of clip c at fstart[c]+k
     int* st_iright;            // last voiced frame
-    // per-stretch raw output
-    double* raw_t;             // scratch [cap_total + extra]
+    double* raw_t;             // per-stretch raw points (left walk descending, then first + right walk)
     double* raw_thr;           // 0.8/f0 of left-walk points (for the addedRight rule)
-    int* raw_nleft;            // [stretch] number of left-walk points
-    int* raw_nright;           // [stretch] number of points in first+right walk
-    double* raw_added_right;   // [stretch] last right-added time or -1e308
+    int* raw_nleft;            // [frames]
+    int* raw_nright;
+    double* raw_added_right;
+    long long* raw_region;
 };
+void launch_pulses(const Clips& c, const PitchPass& p, const PulseSet& ps, cudaStream_t s);
+
+// "To Ltas (pitch-corrected)" accumulation (mshds_extractor.py:241-248)
+struct LtasPass {
+    int* part_count;           // [n]   groups of LTAS_PART pulses per clip
+    int* part_start;           // [n+1]
+    double* partial;           // [parts * 100] band energies (50) and counts (50)
+    int* fail;                 // [n] set when Praat would throw
+};
+void launch_ltas(const Clips& c, const PulseSet& ps, const LtasPass& lt, double* ltas_bands /*[n*50]*/, cudaStream_t s);
 
 // ---- launchers (each in its own .cu) ----------------------------------------------------------------------------
 void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch /* n*16 bytes */, cudaStream_t s);
@@ -104,3 +114,14 @@ struct SpecPass {
 };
 void launch_moments(const Clips& c, const SpecPass& p, const PitchPass& pp, const double2* tw, int max_frames_hint,
                     cudaStream_t s);
+
+// _speechrate scratch (per clip: slots [fstart_sr[c] + 2c, +nF+2))
+struct Ivl { double xmin, xmax; int sounding; int pad; };
+struct SpeechRateScratch {
+    Ivl* ivl;
+    double* pk_t;
+    double* pk_v;
+    int* pk_i;
+};
+void launch_speechrate(const Clips& c, const IntensityPass& ip, const double* istats, const PitchPass& pp,
+                       const SpeechRateScratch& sc, cudaStream_t s);

@@ -266,8 +266,9 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     void* stat_scratch = arena_take(h, (size_t)n * 16);
 
     // ---- pitch pass configurations (parselmouth defaults unless mshds_extractor.py passes a value)
-    PitchPass wide, mainp, hnr;
+    PitchPass wide, mainp, hnr, srp, ltp;
     memset(&wide, 0, sizeof wide); memset(&mainp, 0, sizeof mainp); memset(&hnr, 0, sizeof hnr);
+    memset(&srp, 0, sizeof srp); memset(&ltp, 0, sizeof ltp);
     int rc;
     for (int k = 0; k < 3; k++) {
         // :143 to_pitch_ac(time_step=0.005, pitch_floor=50, pitch_ceiling=600)
@@ -276,6 +277,10 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
         if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 3.0, 15, 0, 0.03, 0.45, 0.01, 0.35, 0.14, cls_ceiling(k), &mainp.cfg[k]))) return rc;
         // :221 to_harmonicity_cc(0.005, floor, 0.1, 4.5): FCC, 15 candidates, all path costs 0, ceiling = Nyquist
         if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 4.5, 15, 2, 0.1, 0.0, 0.0, 0.0, 0.0, 0.5 * fs, &hnr.cfg[k]))) return rc;
+        // :104 to_pitch_ac(0.02, 30, 4, False, 0.03, 0.25, 0.01, 0.35, 0.25, 450)
+        if ((rc = make_pitch_cfg(h, fs, 0.02, 30.0, 3.0, 4, 0, 0.03, 0.25, 0.01, 0.35, 0.25, 450.0, &srp.cfg[k]))) return rc;
+        // :241 Sound_to_PointProcess_periodic_cc -> Sound_to_Pitch (0.0, floor, ceiling): dt = 0.75 / floor
+        if ((rc = make_pitch_cfg(h, fs, 0.0, cls_floor(k), 3.0, 15, 0, 0.03, 0.45, 0.01, 0.35, 0.14, cls_ceiling(k), &ltp.cfg[k]))) return rc;
     }
     hnr.hnr_mode = 1;
 
@@ -288,6 +293,58 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     alloc_pitch_pass(h, &wide, n, fub5, cs);
     alloc_pitch_pass(h, &mainp, n, fub5, cs);
     alloc_pitch_pass(h, &hnr, n, fub5, cs);
+    const long long fub20 = frames_upper_bound(lens, dx, 0.02);
+    const long long fub75 = frames_upper_bound(lens, dx, 0.75 / 100.0);
+    alloc_pitch_pass(h, &srp, n, fub20, cs);
+    alloc_pitch_pass(h, &ltp, n, fub75, cs);
+
+    // ---- glottal pulses: raw / final capacity per clip (shared raw scratch, one final set per consumer)
+    const double cprime = 500.0 / 0.8 * 1.15;
+    std::vector<int> pcap(n + 1, 0);
+    for (int i = 0; i < n; i++) {
+        long long nfr = (long long)floor((double)lens[i] * dx / 0.005) + 2;
+        long long cap = (long long)floor((double)lens[i] * dx * cprime) + 8 * (nfr / 2 + 2) + 16;
+        pcap[i + 1] = pcap[i] + (int)cap;
+    }
+    const long long ptotal = pcap[n];
+    PulseSet pl_lt;
+    memset(&pl_lt, 0, sizeof pl_lt);
+    pl_lt.cprime = cprime;
+    int* d_pcap = take<int>(h, n + 1);
+    double* raw_t = take<double>(h, ptotal); double* raw_thr = take<double>(h, ptotal);
+    int* st_il = take<int>(h, fub5); int* st_ir = take<int>(h, fub5);
+    int* raw_nl = take<int>(h, fub5); int* raw_nr = take<int>(h, fub5);
+    double* raw_ar = take<double>(h, fub5); long long* raw_reg = take<long long>(h, fub5);
+    auto alloc_pulses = [&](PulseSet* ps) {
+        ps->cprime = cprime; ps->cap_start = d_pcap;
+        ps->t = take<double>(h, ptotal); ps->count = take<int>(h, n);
+        ps->st_count = take<int>(h, n); ps->st_start = take<int>(h, n + 1);
+        ps->st_ileft = st_il; ps->st_iright = st_ir; ps->raw_t = raw_t; ps->raw_thr = raw_thr;
+        ps->raw_nleft = raw_nl; ps->raw_nright = raw_nr; ps->raw_added_right = raw_ar; ps->raw_region = raw_reg;
+    };
+    alloc_pulses(&pl_lt);
+
+    // ---- LTAS
+    LtasPass lt;
+    lt.part_count = take<int>(h, n); lt.part_start = take<int>(h, n + 1); lt.fail = take<int>(h, n);
+    lt.partial = take<double>(h, (size_t)(ptotal / 64 + n + 1) * 100);
+    double* ltas_bands = take<double>(h, (size_t)n * 50);
+
+    // ---- speech rate: 16 ms intensity contour (:41) and its scratch
+    IntensityPass isr;
+    memset(&isr, 0, sizeof isr);
+    isr.class_dep = 0; isr.dt = 0.016;
+    for (int k = 0; k < 3; k++) {
+        isr.min_pitch[k] = 50.0;
+        if ((rc = make_kaiser(h, fs, 50.0, &isr.halfN[k], &isr.win[k]))) return rc;
+    }
+    const long long fub16 = frames_upper_bound(lens, dx, 0.016);
+    isr.nF = take<int>(h, n); isr.t1 = take<double>(h, n); isr.fstart = take<int>(h, n + 1);
+    isr.out = take<double>(h, fub16);
+    double* isr_stats = take<double>(h, (size_t)n * 4);
+    SpeechRateScratch srs;
+    srs.ivl = take<Ivl>(h, fub16 + 2 * n + 2); srs.pk_t = take<double>(h, fub16 + 2 * n + 2);
+    srs.pk_v = take<double>(h, fub16 + 2 * n + 2); srs.pk_i = take<int>(h, fub16 + 2 * n + 2);
 
     // ---- intensity (:198) and spectrogram (:356)
     IntensityPass imain;
@@ -310,10 +367,19 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     if (h->arena_overflow) { h->err = "internal: arena overflow after sizing"; return MSHDS_ERR_CUDA; }
 
     CK(cudaMemcpyAsync(d_off, off_host.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_pcap, pcap.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
     const int fhint = (int)(fub5 > 0x3fffffff ? 0x3fffffff : fub5);
 
     // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
     launch_clip_stats(c, maxlen, stat_scratch, s); h->launches += 3;
+
+    // ---- _speechrate (:11-125)
+    launch_intensity(c, isr, (int)(fub16 > 0x3fffffff ? 0x3fffffff : fub16), s); h->launches += 3;
+    launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1;
+    launch_pitch_grid(c, srp, s); h->launches += 2;
+    launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1;
+    launch_pitch_viterbi(c, srp, s); h->launches += 1;
+    launch_speechrate(c, isr, isr_stats, srp, srs, s); h->launches += 1;
 
     // ---- _pitch_values (:127-162): wide AC pass -> speaker class
     launch_pitch_grid(c, wide, s); h->launches += 2;
@@ -337,6 +403,13 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1;
     launch_hnr_mean(c, hnr, s); h->launches += 1;
 
+    // ---- _extract_Slope_Tilt (:227-251)
+    launch_pitch_grid(c, ltp, s); h->launches += 2;
+    launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1;
+    launch_pitch_viterbi(c, ltp, s); h->launches += 1;
+    launch_pulses(c, ltp, pl_lt, s); h->launches += 5;
+    launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5;
+
     // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
     launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4;
 
@@ -349,6 +422,11 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     reg_debug(h, "intensity_main", imain.out, imain.fstart, imain.nF, 0, 8);
     reg_debug(h, "moments", spec.mom, spec.fstart, spec.nF, 0, 8, 4);
     reg_debug(h, "class", c.cls, nullptr, nullptr, 1, 4);
+    reg_debug(h, "pitch_sr_f", srp.sel_f, srp.fstart, srp.nF, 0, 8);
+    reg_debug(h, "pitch_ltas_f", ltp.sel_f, ltp.fstart, ltp.nF, 0, 8);
+    reg_debug(h, "intensity_sr", isr.out, isr.fstart, isr.nF, 0, 8);
+    reg_debug(h, "pulses_ltas", pl_lt.t, pl_lt.cap_start, pl_lt.count, 0, 8);
+    reg_debug(h, "ltas_bands", ltas_bands, nullptr, nullptr, 50, 8);
     h->last_n = n;
     return MSHDS_OK;
 }

@@ -59,3 +59,14 @@ for c in range(len(durs)):
     hr = ex.debug_fetch("hnr_r", c)
     want = np.where(ph["freq"] == 0, np.nan, ph["strength"])
     cmp("hnr_r", hr, want)
+    psr = orc.pitch(x, 16000.0, 0, 0.02, 30.0, 3.0, 4, 0.03, 0.25, 0.01, 0.35, 0.25, 450.0)
+    cmp("pitch_sr_f", ex.debug_fetch("pitch_sr_f", c), psr["freq"])
+    isr, _ = orc.intensity(x, 16000.0, 50.0, 0.016)
+    cmp("intensity_sr", ex.debug_fetch("intensity_sr", c), isr)
+    plt_ = orc.pitch(x, 16000.0, 0, 0.0, fl, 3.0, 15, 0.03, 0.45, 0.01, 0.35, 0.14, ce)
+    cmp("pitch_ltas_f", ex.debug_fetch("pitch_ltas_f", c), plt_["freq"])
+    pul = orc.pulses(x, 16000.0, 0, 0.0, fl, 3.0, 0.45, ce)
+    cmp("pulses_ltas", ex.debug_fetch("pulses_ltas", c), pul, tol=1e-9)
+    lb = orc.ltas(x, 16000.0, fl, ce)
+    if lb is not None:
+        cmp("ltas_bands", ex.debug_fetch("ltas_bands", c), lb[0], tol=1e-9)
