@@ -65,6 +65,7 @@ struct PulseSet {
     int* raw_nright;
     double* raw_added_right;
     long long* raw_region;
+    int* valid;                // [n] 1 when the pitch analysis behind this set exists (no Praat exception)
 };
 void launch_pulses(const Clips& c, const PitchPass& p, const PulseSet& ps, cudaStream_t s);
 
@@ -125,3 +126,58 @@ struct SpeechRateScratch {
 };
 void launch_speechrate(const Clips& c, const IntensityPass& ip, const double* istats, const PitchPass& pp,
                        const SpeechRateScratch& sc, cudaStream_t s);
+
+// Sound_resample job: one sound (a whole clip or one voiced segment of it)
+struct ResampleJob {
+    long long clip_off;        // offset of the clip's first sample in the packed pcm
+    long long nclip;           // clip length in samples
+    long long ix1;             // 1-based clip index of source sample 1 (samples outside the clip are virtual zeros)
+    long long nx;              // source samples
+    double x1;                 // time of source sample 1 in the source sound's own time base
+    long long zoff;            // complex work buffer offset (double2 units)
+    long long filt_off;        // filtered float64 signal offset
+    long long out_off;         // resampled signal offset
+    long long nout;            // resampled samples
+    double out_x1, out_dx;
+    int table_id, pad;         // row block of the sinc coefficient table
+};
+void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, const int16_t* pcm, double2* zbuf,
+                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches);
+void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
+                          const int* d_table_rep /*[ntables] representative job per table*/, int ntables, const double* filt,
+                          double* table, double* out, int P, int D, double dx_src, cudaStream_t s, long long* launches);
+
+// Sound_to_Formant_burg over the resampled clips (job index == clip index)
+struct FormantPass {
+    const ResampleJob* jobs;
+    double dt, dt_window, emphasis, nyquist;
+    int nsamp_window;
+    const double* window;      // [nsamp_window] Gaussian
+    int* nF; double* t1; int* fstart;
+    int* nform;                // [frames]
+    double* freq;              // [frames*5]
+    double* bw;                // [frames*5]
+};
+void launch_formants(const Clips& c, const FormantPass& p, int njobs, const double* sig, int max_frames_hint, cudaStream_t s);
+void launch_formant_stats(const Clips& c, const FormantPass& p, const PulseSet& ps, cudaStream_t s);
+
+// voiced segments of PointProcess_to_TextGrid_vuv (per clip, capacity-prefixed)
+struct CppSegs {
+    int* cap_start;            // [n+1]
+    int* count;                // [n]
+    int* fail;                 // [n]
+    double* tmin; double* tmax;
+    long long* ix1;
+    int* nseg;
+};
+struct CepSeg {                // one cepstrogram (host-built from the segment list)
+    double t1, windowDuration, dq;
+    int nwin, nfft, logM, pad;
+};
+void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, cudaStream_t s);
+void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
+                        const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames, cudaStream_t s);
+void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
+                       double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s);
+void launch_cpp_reduce(const Clips& c, const CppSegs& sg, const int* seg_prefix, const int* fprefix, const double* cpp_frame,
+                       cudaStream_t s);

@@ -1,0 +1,315 @@
+// k_cpp.cu -- _extract_CPP (mshds_extractor.py:253-301): PointProcess_to_TextGrid_vuv (0.02, 0.1) + "Down to Table"
+// (6-decimal times), per voiced segment Sound_to_PowerCepstrogram (60, 0.002, 5000, 50) and PowerCepstrogram "Get CPPS"
+// (no, 0.01, 0.001, 60, 330, 0.05, parabolic, 0.001, 0, Straight, Robust); keep segments with CPPS > 4; mean.
+//
+// Praat sources restated: fon/PointProcess.cpp (vuv), LPC/Sound_and_PowerCepstrogram.cpp, LPC/PowerCepstrogram.cpp
+// (smooth, getCPPS), LPC/PowerCepstrum.cpp (fitTiltLine, getPeakProminence), dwsys/NUM2.cpp (Theil line fit).
+//
+// One CTA per cepstrogram frame: mean removal, Gaussian window, packed real FFT-1024, log power and the inverse
+// transform stay in shared memory; a second kernel does the 5-frame / 10-bin box smoothing, the dB conversion, the
+// robust tilt line (medians by rank counting, no sort) and the parabolic peak per frame.
+#include "internal.h"
+#include "common.cuh"
+#include "fft.cuh"
+
+// ------------------------------------------------------------------------------------------------ V segments
+__global__ void k_vuv_segments(Clips c, PulseSet ps, CppSegs sg, double maxT, double meanT) {
+    const int clip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (clip >= c.n) return;
+    const double* t1b = ps.t + ps.cap_start[clip] - 1;           // 1-based pulses
+    const int nt = ps.count[clip];
+    const long long nx = c.off[clip + 1] - c.off[clip];
+    const double dx = c.dx, x1 = 0.5 * dx, xmin = 0.0, xmax = (double)nx * dx;
+    const double halfMeanT = 0.5 * meanT;
+    const int base = sg.cap_start[clip];
+    const int cap = sg.cap_start[clip + 1] - base;
+    int n = 0, fail = 0;
+    int ipointright;
+    for (int ipointleft = 1; ipointleft <= nt; ipointleft = ipointright + 1) {
+        for (ipointright = ipointleft + 1; ipointright <= nt; ipointright++)
+            if (t1b[ipointright] - t1b[ipointright - 1] > maxT) break;
+        ipointright--;
+        double beginVoiced = t1b[ipointleft] - halfMeanT;
+        if (beginVoiced < xmin) beginVoiced = xmin;
+        double endVoiced = t1b[ipointright] + halfMeanT;
+        if (endVoiced > xmax) endVoiced = xmax;
+        // "Down to Table ... 6 decimals" then float(): round to the nearest multiple of 1e-6
+        double tmin = rint(beginVoiced * 1e6) / 1e6, tmax = rint(endVoiced * 1e6) / 1e6;
+        if (tmin >= tmax) continue;                                               // :284
+        // Sound_extractPart (rectangular, preserve_times = False)
+        long long ix1 = 1 + (long long)ceil((tmin - x1) / dx);
+        long long ix2 = 1 + (long long)floor((tmax - x1) / dx);
+        if (ix2 < ix1) { fail = 1; break; }
+        if (n < cap) {
+            sg.tmin[base + n] = tmin; sg.tmax[base + n] = tmax;
+            sg.ix1[base + n] = ix1; sg.nseg[base + n] = (int)(ix2 - ix1 + 1);
+            n++;
+        }
+    }
+    sg.count[clip] = n;
+    sg.fail[clip] = fail || !ps.valid[clip];
+}
+
+// ------------------------------------------------------------------------------------------------ cepstrogram frames
+struct LogPowerF {
+    double dx2, df;
+    __device__ __forceinline__ double operator()(double p) const { return log(p * dx2 + 1e-300) * df; }
+};
+
+__global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix, int nsegs,
+                                                      const ResampleJob* __restrict__ jobs, const double* __restrict__ sig,
+                                                      const double2* __restrict__ tw, double emphasis, double dt,
+                                                      double* __restrict__ cep, int nqmax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2* a = (double2*)smem;                      // 512 complex
+    double* red = (double*)(smem + sizeof(double2) * 512);
+    __shared__ int s_seg;
+    const int total = fprefix[nsegs];
+    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_seg = find_segment(fprefix, nsegs, f);
+        __syncthreads();
+        const int sgi = s_seg;
+        const CepSeg S = segs[sgi];
+        const ResampleJob J = jobs[sgi];
+        const double* y = sig + J.out_off - 1;                                  // 1-based resampled segment
+        const int iframe = f - fprefix[sgi];
+        const double t = S.t1 + (double)iframe * dt;
+        // Sound_into_Sound (sound, sframe, t - windowDuration / 2)
+        const long long index = x_to_nearest(J.out_x1, J.out_dx, t - S.windowDuration / 2);
+        const int nwin = S.nwin, nfft = S.nfft, M = nfft / 2;
+        double* ar = (double*)a;
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < nfft; i += blockDim.x) {
+            double v = 0.0;
+            if (i < nwin) {
+                long long j = index + i;                                         // index - 1 + (i+1)
+                if (j >= 1 && j <= J.nout) v = j >= 2 ? y[j] - emphasis * y[j - 1] : y[j];
+            }
+            ar[i] = v;
+            acc += v;
+        }
+        const double mean = block_sum(acc, red) / (double)nwin;                  // Vector_subtractMean
+        const double imid = 0.5 * (double)(nwin + 1), edge = exp(-12.0);
+        for (int i = threadIdx.x; i < nwin; i += blockDim.x) {
+            double d = (double)(i + 1) - imid;
+            double w = (exp(-48.0 * d * d / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
+            ar[i] = (ar[i] - mean) * w;
+        }
+        __syncthreads();
+        fft_dif<-1>(a, M, tw);
+        LogPowerF F;
+        F.dx2 = J.out_dx * J.out_dx;
+        F.df = 1.0 / (J.out_dx * (double)nfft);
+        packed_power_to_inverse_input(a, M, S.logM, tw, F, (double*)nullptr);
+        fft_dit<+1>(a, M, tw);
+        const int nq = M + 1;
+        double* row = cep + (size_t)f * nqmax;
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            // c[i] for i <= M: natural order ar[i]; c[M] = ar[M] exists since M < nfft
+            double cv = ar[i];
+            row[i] = cv * cv;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ CPPS per frame
+// k-th smallest (1-based) of v[0..n) by rank counting; every thread returns the value
+__device__ double block_rank_select(const double* v, int n, int k, double* s_out) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double vi = v[i];
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            double vj = v[j];
+            rank += (vj < vi) || (vj == vi && j < i);
+        }
+        if (rank == k - 1) *s_out = vi;
+    }
+    __syncthreads();
+    double r = *s_out;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix, int nsegs,
+                                                     const double* __restrict__ cep, int nqmax, int nTimeAvg, double qAvgWindow,
+                                                     double peakLo, double peakHi, double qstartFit, double qendFit,
+                                                     double* __restrict__ cpp_frame) {
+    __shared__ double col[520], y[520], work[520];
+    __shared__ double s_sel[2], s_red[32];
+    __shared__ int s_seg;
+    __shared__ double s_peak[2];
+    const int total = fprefix[nsegs];
+    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_seg = find_segment(fprefix, nsegs, f);
+        __syncthreads();
+        const int sgi = s_seg;
+        const CepSeg S = segs[sgi];
+        const int f0 = fprefix[sgi], nFrames = fprefix[sgi + 1] - f0;
+        const int i1 = f - f0 + 1;                                               // 1-based frame
+        const int nq = S.nfft / 2 + 1;
+        const double dq = S.dq;
+        // PowerCepstrogram_smooth: moving average over time, then over quefrency
+        int jfrom = i1, jto = i1;
+        if (nTimeAvg > 1) {
+            jfrom = i1 - nTimeAvg / 2; jto = i1 + nTimeAvg / 2;
+            if ((nTimeAvg % 2) == 0) jto--;
+            if (jfrom < 1) jfrom = 1;
+            if (jto > nFrames) jto = nFrames;
+        }
+        for (int iq = threadIdx.x; iq < nq; iq += blockDim.x) {
+            double s = 0.0;
+            for (int j = jfrom; j <= jto; j++) s += cep[(size_t)(f0 + j - 1) * nqmax + iq];
+            col[iq] = nTimeAvg > 1 ? s / (double)(jto - jfrom + 1) : s;
+        }
+        __syncthreads();
+        const int nQ = (int)floor(qAvgWindow / dq);
+        for (int iq = threadIdx.x; iq < nq; iq += blockDim.x) {
+            double v;
+            if (nQ > 1) {
+                int i = iq + 1;
+                int qf = i - nQ / 2, qt = i + nQ / 2;
+                if ((nQ % 2) == 0) qt--;
+                if (qf < 1) qf = 1;
+                if (qt > nq) qt = nq;
+                double s = 0.0;
+                for (int j = qf; j <= qt; j++) s += col[j - 1];
+                v = s / (double)(qt - qf + 1);
+            } else v = col[iq];
+            y[iq] = 10.0 * log10(v + 1e-30);                                     // PowerCepstrum dB
+        }
+        __syncthreads();
+        // PowerCepstrum_fitTiltLine (Straight, Robust = incomplete Theil); qmax <= qmin -> whole domain
+        double qlo = qstartFit, qhi = qendFit;
+        const double qmaxDom = dq * (double)(nq - 1);
+        if (qhi <= qlo) { qlo = 0.0; qhi = qmaxDom; }
+        long long imin, imax;
+        double cppv = DEVNAN;
+        if (get_window_samples(0.0, dq, nq, qlo, qhi, &imin, &imax) && imax - imin + 1 >= 2) {
+            const int npts = (int)(imax - imin + 1);
+            const double* yy = y + (imin - 1);                                   // yy[i], x_i = (imin - 1 + i) * dq
+            double slope, intercept;
+            if (npts == 2) {
+                slope = (yy[1] - yy[0]) / dq;
+                intercept = yy[0] - slope * ((double)(imin - 1) * dq);
+            } else {
+                const int numberOfPairs = npts / 2;
+                const int n2 = (npts % 2 == 1) ? numberOfPairs + 1 : numberOfPairs;
+                for (int i = threadIdx.x; i < numberOfPairs; i += blockDim.x) {
+                    double xa = (double)(imin - 1 + i) * dq, xb = (double)(imin - 1 + n2 + i) * dq;
+                    work[i] = (yy[n2 + i] - yy[i]) / (xb - xa);
+                }
+                __syncthreads();
+                {   // NUMquantile (0.5)
+                    double place = 0.5 * numberOfPairs + 0.5;
+                    int left = (int)floor(place);
+                    if (left < 1) slope = block_rank_select(work, numberOfPairs, 1, &s_sel[0]);
+                    else if (left >= numberOfPairs) slope = block_rank_select(work, numberOfPairs, numberOfPairs, &s_sel[0]);
+                    else {
+                        double a0 = block_rank_select(work, numberOfPairs, left, &s_sel[0]);
+                        double a1 = block_rank_select(work, numberOfPairs, left + 1, &s_sel[1]);
+                        slope = (a1 == a0) ? a0 : a0 + (place - left) * (a1 - a0);
+                    }
+                }
+                for (int i = threadIdx.x; i < npts; i += blockDim.x) work[i] = yy[i] - slope * ((double)(imin - 1 + i) * dq);
+                __syncthreads();
+                {
+                    double place = 0.5 * npts + 0.5;
+                    int left = (int)floor(place);
+                    if (left < 1) intercept = block_rank_select(work, npts, 1, &s_sel[0]);
+                    else if (left >= npts) intercept = block_rank_select(work, npts, npts, &s_sel[0]);
+                    else {
+                        double a0 = block_rank_select(work, npts, left, &s_sel[0]);
+                        double a1 = block_rank_select(work, npts, left + 1, &s_sel[1]);
+                        intercept = (a1 == a0) ? a0 : a0 + (place - left) * (a1 - a0);
+                    }
+                }
+            }
+            // PowerCepstrum_getMaximumAndQuefrency: Vector_getMaximumAndX (1/ceiling, 1/floor, parabolic)
+            if (threadIdx.x == 0) {
+                long long pmin, pmax;
+                double maximum, x;
+                const double xlo = peakLo, xhi = peakHi;
+                if (!get_window_samples(0.0, dq, nq, xlo, xhi, &pmin, &pmax)) {
+                    // no sample centre inside: linear values at the two ends
+                    double il = xlo / dq + 1.0, ir = xhi / dq + 1.0;
+                    int l0 = (int)floor(il), r0 = (int)floor(ir);
+                    double yl = (l0 >= 1 && l0 < nq) ? y[l0 - 1] + (il - l0) * (y[l0] - y[l0 - 1]) : y[nq - 1];
+                    double yr = (r0 >= 1 && r0 < nq) ? y[r0 - 1] + (ir - r0) * (y[r0] - y[r0 - 1]) : y[nq - 1];
+                    maximum = yl > yr ? yl : yr;
+                    x = yl == yr ? (xlo + xhi) / 2 : yl > yr ? xlo : xhi;
+                } else {
+                    maximum = y[pmin - 1];
+                    double xi = (double)pmin;
+                    if (y[pmax - 1] > maximum) { maximum = y[pmax - 1]; xi = (double)pmax; }
+                    long long lo = pmin == 1 ? 2 : pmin, hi = pmax == nq ? nq - 1 : pmax;
+                    for (long long i = lo; i <= hi; i++) {
+                        double yi = y[i - 1], ym = y[i - 2], yp = y[i];
+                        if (yi > ym && yi >= yp) {
+                            double dy = 0.5 * (yp - ym), d2y = 2 * yi - ym - yp;
+                            double loc = yi + 0.5 * dy * dy / d2y;
+                            if (loc > maximum) { maximum = loc; xi = (double)i + dy / d2y; }
+                        }
+                    }
+                    x = (xi - 1.0) * dq;
+                    if (x < xlo) x = xlo; else if (x > xhi) x = xhi;
+                }
+                s_peak[0] = maximum; s_peak[1] = x;
+            }
+            __syncthreads();
+            cppv = s_peak[0] - (slope * s_peak[1] + intercept);
+        }
+        if (threadIdx.x == 0) cpp_frame[f] = cppv;
+        (void)s_red;
+    }
+}
+
+// CPPS per segment = mean over frames; clip value = mean of the segments with CPPS > 4 (mshds_extractor.py:293,298)
+__global__ void __launch_bounds__(128) k_cpp_reduce(Clips c, CppSegs sg, const int* __restrict__ seg_prefix,
+                                                     const int* __restrict__ fprefix, const double* __restrict__ cpp_frame) {
+    __shared__ double red[32];
+    const int clip = blockIdx.x;
+    const int s0 = seg_prefix[clip], ns = seg_prefix[clip + 1] - s0;
+    double sum = 0.0;
+    int cnt = 0;
+    for (int k = 0; k < ns; k++) {
+        const int f0 = fprefix[s0 + k], nF = fprefix[s0 + k + 1] - f0;
+        double a = 0.0;
+        bool bad = false;
+        for (int i = threadIdx.x; i < nF; i += blockDim.x) { double v = cpp_frame[f0 + i]; if (is_undef(v)) bad = true; else a += v; }
+        a = block_sum(a, red);
+        double nb = block_sum(bad ? 1.0 : 0.0, red);
+        if (nF >= 1 && nb == 0.0) {
+            double cpps = a / (double)nF;
+            if (cpps > 4.0) { sum += cpps; cnt++; }
+        }
+    }
+    if (threadIdx.x == 0) {
+        const bool fail = sg.fail[clip] != 0;
+        c.feat[(size_t)clip * N_FEAT + 12] = (!fail && cnt > 0) ? sum / (double)cnt : DEVNAN;
+        if (fail || cnt == 0) atomicOr(&c.status[clip], ST_CPP);
+    }
+}
+
+void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, cudaStream_t s) {
+    k_vuv_segments<<<(c.n + 63) / 64, 64, 0, s>>>(c, ps, sg, 0.02, 0.1);
+}
+void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
+                        const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames, cudaStream_t s) {
+    int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
+    if (grid < 1) grid = 1;
+    size_t smem = sizeof(double2) * 512 + sizeof(double) * 32;
+    k_cepstrogram<<<grid, 256, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax);
+}
+void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
+                       double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {
+    int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
+    if (grid < 1) grid = 1;
+    k_cpp_frames<<<grid, 256, 0, s>>>(segs, fprefix, nsegs, cep, nqmax, nTimeAvg, qAvgWindow, 1.0 / 330.0, 1.0 / 60.0, 0.001, 0.0,
+                                      cpp_frame);
+}
+void launch_cpp_reduce(const Clips& c, const CppSegs& sg, const int* seg_prefix, const int* fprefix, const double* cpp_frame,
+                       cudaStream_t s) {
+    k_cpp_reduce<<<c.n, 128, 0, s>>>(c, sg, seg_prefix, fprefix, cpp_frame);
+}

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(128) k_stretch_list(Clips c, PitchPass p, Puls
     if (lane == 0) {
         if (inrun) { ps.st_ileft[f0 + count] = start; ps.st_iright[f0 + count] = nF; count++; }
         ps.st_count[clip] = count;
+        ps.valid[clip] = nF >= 1;
     }
 }
 

@@ -1,0 +1,314 @@
+// k_resample.cu -- Sound_resample (fon/Sound.cpp): FFT brick-wall low-pass of the zero-padded sound followed by
+// windowed-sinc interpolation at the new sampling times.
+//
+// Serves the resample-to-10-kHz inside "To Formant (burg)" (precision 500, whole clip, mshds_extractor.py:319) and
+// inside "To PowerCepstrogram" (precision 50, one voiced segment at a time, :289).
+//
+// The low-pass needs one FFT of nfft = 2^k >= nx + 2000 points per sound (2^19 for a 30 s clip, 2^24 for 10 min).  It is
+// a hand-written multi-pass FFT: strided radix-2^b passes (<= 256 points per column, 16 columns per CTA so every global
+// access is a 256-byte row segment) down to contiguous 4096-point blocks; the innermost kernel runs forward DIF ->
+// Praat's packed-spectrum zeroing -> inverse DIT on the block without leaving shared memory; the strided passes are then
+// undone in reverse.  Forward output is bit-reversed and the inverse consumes bit-reversed input, so no transposition
+// pass exists.  The first pass converts the int16 samples on load, the last one writes the filtered real samples.
+#include "internal.h"
+#include "common.cuh"
+#include "fft.cuh"
+
+#define RS_NTHR 256
+#define TB 16                      // columns per CTA in the strided passes
+#define ANTI_TURN 1000             // Praat's antiTurnAround
+
+__device__ __forceinline__ double job_src(const ResampleJob& J, const int16_t* __restrict__ pcm, long long pos /*0-based in data*/) {
+    long long i = pos - (ANTI_TURN - 1);                 // data[antiTurnAround + i] = z[i], i = 1..nx
+    if (i < 1 || i > J.nx) return 0.0;
+    long long ic = J.ix1 + i - 1;                        // sample index within the clip (1-based); outside -> virtual zero
+    if (ic < 1 || ic > J.nclip) return 0.0;
+    return samp(pcm + J.clip_off, ic - 1);
+}
+
+// One strided DIF / DIT pass over blocks of length Nl = 2^nl: R = 2^rb point transforms at stride M = Nl / R.
+template <bool INVERSE, bool FIRST_FROM_SRC, bool LAST_TO_REAL>
+__global__ void __launch_bounds__(RS_NTHR) k_fft_strided(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
+                                                          const int16_t* __restrict__ pcm, double2* __restrict__ zbuf,
+                                                          double* __restrict__ filt, const double2* __restrict__ tw,
+                                                          int logn, int nl, int rb) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2* a = (double2*)smem;
+    const int R = 1 << rb;
+    const long long N = 1LL << logn, Nl = 1LL << nl, M = Nl >> rb;
+    const long long tilesPerJob = N / ((long long)R * TB);
+    const long long tile = blockIdx.x % tilesPerJob;
+    const ResampleJob J = jobs[ids[blockIdx.x / tilesPerJob]];
+    const long long tilesPerBlk = M / TB;
+    const long long blk = tile / tilesPerBlk, col0 = (tile % tilesPerBlk) * TB;
+    double2* z = zbuf + J.zoff + blk * Nl;
+    for (int e = threadIdx.x; e < R * TB; e += RS_NTHR) {
+        int r = e / TB, b = e % TB;
+        long long pos = (long long)r * M + col0 + b;
+        double2 v;
+        if (FIRST_FROM_SRC) v = make_double2(job_src(J, pcm, blk * Nl + pos), 0.0);
+        else v = z[pos];
+        if (INVERSE) {
+            int cidx = bitrev(r, rb);
+            if (cidx != 0) {
+                double s, co;
+                sincospi(2.0 * (double)((col0 + b) * cidx) / (double)Nl, &s, &co);
+                v = cmul(v, make_double2(co, s));
+            }
+        }
+        a[e] = v;
+    }
+    __syncthreads();
+    if (INVERSE) fft_dit_cols<+1>(a, R, TB, tw);
+    else fft_dif_cols<-1>(a, R, TB, tw);
+    for (int e = threadIdx.x; e < R * TB; e += RS_NTHR) {
+        int r = e / TB, b = e % TB;
+        long long pos = (long long)r * M + col0 + b;
+        double2 v = a[e];
+        if (!INVERSE) {
+            int cidx = bitrev(r, rb);
+            if (cidx != 0) {
+                double s, co;
+                sincospi(-2.0 * (double)((col0 + b) * cidx) / (double)Nl, &s, &co);
+                v = cmul(v, make_double2(co, s));
+            }
+            z[pos] = v;
+        } else if (LAST_TO_REAL) {
+            long long gp = blk * Nl + pos;
+            long long i = gp - ANTI_TURN;                    // to[i] = data[i + antiTurnAround] / nfft, i = 1..nx (0-based i here)
+            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = v.x * (1.0 / (double)N);
+        } else {
+            z[pos] = v;
+        }
+    }
+}
+
+// Praat: "for (i = floor(upfactor*nfft); i <= nfft; i++) data[i] = 0;  data[2] = 0;" on the NUMrealft-packed spectrum
+// (data[1] = DC, data[2] = Nyquist, data[2k+1] = Re X_k, data[2k+2] = Im X_k).  Returns the masked bin.
+__device__ __forceinline__ double2 apply_lowpass_mask(double2 v, long long k, long long N, long long i0) {
+    long long kk = k <= N / 2 ? k : N - k;
+    if (kk == 0) { if (i0 <= 1) v.x = 0.0; v.y = v.y; return v; }
+    if (kk == N / 2) return make_double2(0.0, 0.0);
+    if (2 * kk + 1 >= i0) v.x = 0.0;
+    if (2 * kk + 2 >= i0) v.y = 0.0;
+    return v;
+}
+
+// Innermost kernel: contiguous blocks of Cn = 2^cb points: forward DIF, mask, inverse DIT, all in shared memory.
+template <bool WHOLE>     // WHOLE: logn == cb (load from the source, write filtered reals)
+__global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
+                                                        const int16_t* __restrict__ pcm, double2* __restrict__ zbuf,
+                                                        double* __restrict__ filt, const double2* __restrict__ tw, int logn,
+                                                        int cb, double upfactor) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double2* a = (double2*)smem;
+    const int Cn = 1 << cb;
+    const long long N = 1LL << logn;
+    const long long chunksPerJob = N >> cb;
+    const long long chunk = blockIdx.x % chunksPerJob;
+    const ResampleJob J = jobs[ids[blockIdx.x / chunksPerJob]];
+    double2* z = zbuf + J.zoff + chunk * Cn;
+    for (int e = threadIdx.x; e < Cn; e += RS_NTHR) a[e] = WHOLE ? make_double2(job_src(J, pcm, e), 0.0) : z[e];
+    __syncthreads();
+    fft_dif<-1>(a, Cn, tw);
+    const long long i0 = (long long)floor(upfactor * (double)N);
+    for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
+        long long pos = chunk * Cn + e;
+        long long k = (long long)(__brevll((unsigned long long)pos) >> (64 - logn));
+        a[e] = apply_lowpass_mask(a[e], k, N, i0);
+    }
+    __syncthreads();
+    fft_dit<+1>(a, Cn, tw);
+    for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
+        if (WHOLE) {
+            long long i = (long long)e - ANTI_TURN;
+            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = a[e].x * (1.0 / (double)N);
+        } else z[e] = a[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sinc interpolation
+// Coefficient table of NUM_interpolate_sinc for the P distinct fractional positions of a rational rate change.
+__global__ void k_sinc_table(const ResampleJob* __restrict__ jobs, const int* __restrict__ rep, int ntables,
+                             double* __restrict__ table, double* __restrict__ table_fl, int P, int D, double dx_src) {
+    const int tab = blockIdx.x;
+    if (tab >= ntables) return;
+    const ResampleJob J = jobs[rep[tab]];
+    double* T = table + (size_t)tab * P * 2 * D;
+    if (threadIdx.x < P) {
+        long long j = (long long)(J.nout / 2 / P) * P + threadIdx.x + 1;
+        double x = J.out_x1 + (double)(j - 1) * J.out_dx;
+        double index = (x - J.x1) / dx_src + 1.0;
+        table_fl[(size_t)tab * P + threadIdx.x] = index - floor(index);
+    }
+    for (int e = threadIdx.x; e < P * 2 * D; e += blockDim.x) {
+        int ph = e / (2 * D), k = e % (2 * D);
+        // representative output sample of this phase near the middle of the sound
+        long long j = (long long)(J.nout / 2 / P) * P + ph + 1;
+        double x = J.out_x1 + (double)(j - 1) * J.out_dx;
+        double index = (x - J.x1) / dx_src + 1.0;
+        double fl = index - floor(index), fr = 1.0 - fl;
+        double v;
+        if (fl == 0.0) v = (k == 0) ? 1.0 : 0.0;
+        else if (k < D) {          // left tap k: sample midleft - k
+            double sgn = (k & 1) ? -1.0 : 1.0;
+            double al = fl + k;
+            v = sgn * (0.5 * sinpi(fl)) / (MSHDS_PI * al) * (1.0 + cospi(al * (1.0 / (fl + D))));
+        } else {                   // right tap kk: sample midright + kk
+            int kk = k - D;
+            double sgn = (kk & 1) ? -1.0 : 1.0;
+            double ar = fr + kk;
+            v = sgn * (0.5 * sinpi(fr)) / (MSHDS_PI * ar) * (1.0 + cospi(ar * (1.0 / (fr + D))));
+        }
+        T[e] = v;
+    }
+}
+
+// exact NUM_interpolate_sinc, one warp per evaluation (edge samples where the depth is clipped, and samples whose
+// fractional position falls on the other side of an integer than the table's representative)
+__device__ double sinc_interp_warp_ll(const double* __restrict__ y /*1-based*/, long long n, double x, long long maxDepth, int lane) {
+    long long midleft = (long long)floor(x), midright = midleft + 1;
+    if (n < 1) return DEVNAN;
+    if (x > n) return y[n];
+    if (x < 1) return y[1];
+    if (x == midleft) return y[midleft];
+    if (maxDepth > midright - 1) maxDepth = midright - 1;
+    if (maxDepth > n - midleft) maxDepth = n - midleft;
+    if (maxDepth <= 0) return y[(long long)floor(x + 0.5)];
+    if (maxDepth == 1) return y[midleft] + (x - midleft) * (y[midright] - y[midleft]);
+    if (maxDepth == 2) {
+        double yl = y[midleft], yr = y[midright];
+        double dyl = 0.5 * (yr - y[midleft - 1]), dyr = 0.5 * (y[midright + 1] - yl);
+        double fil = x - midleft, fir = midright - x;
+        return yl * fir + yr * fil - fil * fir * (0.5 * (dyr - dyl) + (fil - 0.5) * (dyl + dyr - 2 * (yr - yl)));
+    }
+    double fl = x - midleft, fr = midright - x;
+    double hsl = 0.5 * sinpi(fl), hsr = 0.5 * sinpi(fr);
+    double invl = 1.0 / (fl + maxDepth), invr = 1.0 / (fr + maxDepth);
+    double acc = 0.0;
+    for (long long k = lane; k < maxDepth; k += 32) {
+        double sgn = (k & 1) ? -1.0 : 1.0;
+        double al = fl + k, ar = fr + k;
+        acc += y[midleft - k] * (sgn * hsl / (MSHDS_PI * al) * (1.0 + cospi(al * invl)));
+        acc += y[midright + k] * (sgn * hsr / (MSHDS_PI * ar) * (1.0 + cospi(ar * invr)));
+    }
+    return warp_sum(acc);
+}
+
+// One warp per output sample: lanes split the 2*D taps (coalesced reads of the filtered signal and the table row).
+__global__ void __launch_bounds__(256) k_sinc_apply(const ResampleJob* __restrict__ jobs, const long long* __restrict__ out_prefix,
+                                                     int njobs, const double* __restrict__ filt, const double* __restrict__ table,
+                                                     const double* __restrict__ table_fl, double* __restrict__ out, int P, int D,
+                                                     double dx_src) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long total = out_prefix[njobs];
+    for (long long o = gw; o < total; o += nw) {
+        const int job = find_segment_ll(out_prefix, njobs, o);
+        const ResampleJob J = jobs[job];
+        const long long j = o - out_prefix[job] + 1;                   // 1-based output sample
+        const double x = J.out_x1 + (double)(j - 1) * J.out_dx;
+        const double index = (x - J.x1) / dx_src + 1.0;
+        const double* y = filt + J.filt_off - 1;                        // 1-based
+        const long long midleft = (long long)floor(index);
+        double v;
+        bool fast = P > 0 && midleft >= D && midleft + D <= J.nx && index != (double)midleft;
+        if (fast) {
+            // the table row was built for one representative fractional position; a sample whose floating-point index
+            // lands on the other side of an integer (fraction ~0 vs ~1) must take the exact path
+            double tfl = table_fl[(size_t)J.table_id * P + (size_t)((j - 1) % P)];
+            fast = fabs((index - (double)midleft) - tfl) < 1e-8;
+        }
+        if (fast) {
+            const double* T = table + ((size_t)J.table_id * P + (size_t)((j - 1) % P)) * 2 * D;
+            double acc = 0.0;
+            for (int k = lane; k < D; k += 32) {
+                acc = fma(y[midleft - k], T[k], acc);
+                acc = fma(y[midleft + 1 + k], T[D + k], acc);
+            }
+            v = warp_sum(acc);
+        } else {
+            v = sinc_interp_warp_ll(y, J.nx, index, D, lane);
+        }
+        if (lane == 0) out[J.out_off + j - 1] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host driver
+static void plan_passes(int logn, int* cb, int* npass, int rbits[4]) {
+    *cb = logn < 12 ? logn : 12;
+    int rem = logn - *cb;
+    *npass = 0;
+    if (rem <= 0) return;
+    int np = (rem + 7) / 8;
+    for (int i = 0; i < np; i++) { rbits[i] = rem / np + (i < rem % np ? 1 : 0); }
+    *npass = np;
+}
+
+// jobs of one FFT size: d_ids lists the job indices, cnt of them
+void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, const int16_t* pcm, double2* zbuf,
+                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches) {
+    int cb, npass, rbits[4];
+    plan_passes(logn, &cb, &npass, rbits);
+    const long long N = 1LL << logn;
+    if (npass == 0) {
+        size_t smem = sizeof(double2) * (1u << cb);
+        cudaFuncSetAttribute(k_fft_inner<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_fft_inner<true><<<cnt, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor);
+        (*launches)++;
+        return;
+    }
+    // forward strided passes (outermost first)
+    int nl = logn;
+    for (int i = 0; i < npass; i++) {
+        int rb = rbits[i];
+        size_t smem = sizeof(double2) * ((size_t)1 << rb) * TB;
+        long long tiles = N / (((long long)1 << rb) * TB);
+        unsigned grid = (unsigned)(tiles * cnt);
+        if (i == 0) {
+            cudaFuncSetAttribute(k_fft_strided<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_fft_strided<false, true, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+        } else {
+            cudaFuncSetAttribute(k_fft_strided<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_fft_strided<false, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+        }
+        (*launches)++;
+        nl -= rb;
+    }
+    {
+        size_t smem = sizeof(double2) * (1u << cb);
+        unsigned grid = (unsigned)((N >> cb) * cnt);
+        cudaFuncSetAttribute(k_fft_inner<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_fft_inner<false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor);
+        (*launches)++;
+    }
+    // inverse strided passes (innermost first)
+    for (int i = npass - 1; i >= 0; i--) {
+        int rb = rbits[i];
+        nl += rb;
+        size_t smem = sizeof(double2) * ((size_t)1 << rb) * TB;
+        long long tiles = N / (((long long)1 << rb) * TB);
+        unsigned grid = (unsigned)(tiles * cnt);
+        if (i == 0) {
+            cudaFuncSetAttribute(k_fft_strided<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_fft_strided<true, false, true><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+        } else {
+            cudaFuncSetAttribute(k_fft_strided<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_fft_strided<true, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+        }
+        (*launches)++;
+    }
+}
+
+void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
+                          const int* d_table_rep, int ntables, const double* filt, double* table, double* out, int P, int D,
+                          double dx_src, cudaStream_t s, long long* launches) {
+    double* table_fl = table + (size_t)ntables * (P > 0 ? P : 1) * 2 * D;      // stored behind the coefficient rows
+    if (P > 0 && ntables > 0) { k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, P, D, dx_src); (*launches)++; }
+    long long blocks = (total_out_hint + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_sinc_apply<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table, table_fl, out, P, D, dx_src);
+    (*launches)++;
+}

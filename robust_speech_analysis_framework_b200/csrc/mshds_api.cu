@@ -11,6 +11,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <utility>
 
 #define CK(call)                                                                                      \
     do {                                                                                              \
@@ -30,6 +31,7 @@ struct DebugEntry {
     int fixed;
     int elem_size;
     int stride;             // elements per item (e.g. 15 for candidates)
+    std::vector<long long> host_prefix;   // optional host-side segment offsets (n+1) instead of start / count
 };
 
 struct mshds_handle {
@@ -43,6 +45,10 @@ struct mshds_handle {
     std::map<int, std::pair<double*, double*>> ac_windows;      // nsamp_window -> (window, windowR)
     std::map<long long, double*> kaiser;                        // key -> window
     std::map<int, double*> gauss_spec;
+    std::map<int, double*> gauss_formant;
+    // growable scratch for the CPP stage (sized after the voiced-segment list is known)
+    char* cpp_buf = nullptr;
+    size_t cpp_cap = 0;
     // arena
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -238,8 +244,205 @@ static void alloc_pitch_pass(mshds_handle* h, PitchPass* p, int n, long long fub
 
 static void reg_debug(mshds_handle* h, const char* name, const void* base, const int* start, const int* count, int fixed,
                       int elem_size, int stride = 1) {
-    DebugEntry e{base, start, count, fixed, elem_size, stride};
+    DebugEntry e{base, start, count, fixed, elem_size, stride, {}};
     h->debug[name] = e;
+}
+
+// ------------------------------------------------------------------------------------------------ resample planning
+static int ilog2_ceil(long long v) { int k = 0; while ((1LL << k) < v) k++; return k; }
+
+// Sound_resample bookkeeping for one source sound: xmin = 0, xmax given
+static void fill_resample_job(ResampleJob* J, long long clip_off, long long nclip, long long ix1, long long nx, double x1,
+                              double xmax, double fs_new) {
+    memset(J, 0, sizeof(*J));
+    J->clip_off = clip_off; J->nclip = nclip; J->ix1 = ix1; J->nx = nx; J->x1 = x1;
+    long long nout = (long long)floor((xmax - 0.0) * fs_new + 0.5);
+    J->nout = nout;
+    J->out_dx = 1.0 / fs_new;
+    J->out_x1 = 0.5 * (0.0 + xmax - (double)(nout - 1) / fs_new);
+}
+
+struct ResamplePlan {
+    std::vector<ResampleJob> jobs;
+    std::vector<int> ids;                 // job indices grouped by FFT size
+    std::vector<std::pair<int, int>> groups;   // (logn, count) in ids order
+    std::vector<long long> out_prefix;
+    std::vector<int> table_rep;
+    long long ztotal = 0, ftotal = 0, ototal = 0;
+};
+
+static void finish_plan(ResamplePlan* P, bool share_tables_by_length) {
+    const int nj = (int)P->jobs.size();
+    std::map<int, std::vector<int>> bylog;
+    std::map<long long, int> table_of_len;
+    P->out_prefix.assign(nj + 1, 0);
+    for (int j = 0; j < nj; j++) {
+        ResampleJob& J = P->jobs[j];
+        int logn = ilog2_ceil(J.nx + 2000);
+        bylog[logn].push_back(j);
+        J.zoff = P->ztotal; P->ztotal += (logn > 12) ? (1LL << logn) : 0;
+        J.filt_off = P->ftotal; P->ftotal += J.nx;
+        J.out_off = P->ototal; P->ototal += J.nout;
+        P->out_prefix[j + 1] = P->out_prefix[j] + J.nout;
+        if (share_tables_by_length) {
+            auto it = table_of_len.find(J.nx);
+            if (it == table_of_len.end()) { it = table_of_len.emplace(J.nx, (int)P->table_rep.size()).first; P->table_rep.push_back(j); }
+            J.table_id = it->second;
+        } else { J.table_id = (int)P->table_rep.size(); P->table_rep.push_back(j); }
+    }
+    for (auto& kv : bylog) {
+        P->groups.push_back(std::make_pair(kv.first, (int)kv.second.size()));
+        for (int j : kv.second) P->ids.push_back(j);
+    }
+}
+
+struct ResampleDev { ResampleJob* jobs; int* ids; long long* out_prefix; int* table_rep; double2* zbuf; double* filt; double* out; double* table; };
+
+static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, const int16_t* pcm, double fs, double fs_new,
+                         int precision, cudaStream_t s) {
+    const double dx = 1.0 / fs;
+    const double upfactor = fs_new * dx;
+    int pos = 0;
+    for (auto& g : P.groups) {
+        launch_resample_fft_group(D.jobs, D.ids + pos, g.second, g.first, pcm, D.zbuf, D.filt, h->tw, upfactor, s, &h->launches);
+        pos += g.second;
+    }
+    // polyphase period of the rate change (16 kHz -> 10 kHz: 5 phases)
+    long long a = (long long)llround(fs), b = (long long)llround(fs_new), gg = a, r = b;
+    while (r) { long long t = gg % r; gg = r; r = t; }
+    int phases = (int)(b / gg);
+    if (phases > 16) phases = 0;
+    launch_sinc_resample(D.jobs, D.out_prefix, (int)P.jobs.size(), P.ototal, D.table_rep, (int)P.table_rep.size(), D.filt, D.table,
+                         D.out, phases, precision, dx, s, &h->launches);
+}
+
+static int upload_plan(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, cudaStream_t s) {
+    const int nj = (int)P.jobs.size();
+    if (nj == 0) return MSHDS_OK;
+    CK(cudaMemcpyAsync(D.jobs, P.jobs.data(), sizeof(ResampleJob) * nj, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(D.ids, P.ids.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(D.out_prefix, P.out_prefix.data(), sizeof(long long) * (nj + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(D.table_rep, P.table_rep.data(), sizeof(int) * P.table_rep.size(), cudaMemcpyHostToDevice, s));
+    return MSHDS_OK;
+}
+
+static int make_formant_window(mshds_handle* h, int nsw, const double** win) {
+    auto it = h->gauss_formant.find(nsw);
+    if (it == h->gauss_formant.end()) {
+        std::vector<double> w(nsw);
+        for (int i = 1; i <= nsw; i++) {
+            double imid = 0.5 * (nsw + 1), edge = exp(-12.0);
+            w[i - 1] = (exp(-48.0 * (i - imid) * (i - imid) / (nsw + 1) / (nsw + 1)) - edge) / (1.0 - edge);
+        }
+        double* d;
+        int rc = upload(h, w, &d); if (rc) return rc;
+        it = h->gauss_formant.emplace(nsw, d).first;
+    }
+    *win = it->second;
+    return MSHDS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CPP stage
+// The voiced-segment list only exists on the device; one small read-back per chunk sizes the per-segment FFTs.
+static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long long>& off_host, const std::vector<long long>& lens,
+                         const CppSegs& sg, const std::vector<int>& scap, int* d_seg_prefix, double fs, cudaStream_t s) {
+    const int n = c.n;
+    const double dx = 1.0 / fs, fs10 = 10000.0;
+    std::vector<int> cnt(n);
+    CK(cudaMemcpyAsync(cnt.data(), sg.count, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    std::vector<int> sprefix(n + 1, 0);
+    for (int i = 0; i < n; i++) sprefix[i + 1] = sprefix[i] + cnt[i];
+    const int nsegs = sprefix[n];
+    CK(cudaMemcpyAsync(d_seg_prefix, sprefix.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    std::vector<double> tmin(scap[n]), tmax(scap[n]);
+    std::vector<long long> ix1(scap[n]);
+    std::vector<int> nseg(scap[n]);
+    if (nsegs > 0) {
+        CK(cudaMemcpyAsync(tmin.data(), sg.tmin, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(tmax.data(), sg.tmax, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ix1.data(), sg.ix1, sizeof(long long) * scap[n], cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(nseg.data(), sg.nseg, sizeof(int) * scap[n], cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    ResamplePlan plan;
+    std::vector<CepSeg> cseg(nsegs);
+    std::vector<int> fprefix(nsegs + 1, 0);
+    plan.jobs.resize(nsegs);
+    const double dt = 0.002, pitchFloor = 60.0;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < cnt[i]; k++) {
+            const int src = scap[i] + k, j = sprefix[i] + k;
+            // Sound_extractPart: xmin = 0, xmax = t2 - t1, x1 = my x1 + (ix1 - 1) dx - t1
+            const double xmax = tmax[src] - tmin[src];
+            const double x1 = (0.5 * dx + (double)(ix1[src] - 1) * dx) - tmin[src];
+            fill_resample_job(&plan.jobs[j], off_host[i], lens[i], ix1[src], nseg[src], x1, xmax, fs10);
+            // Sound_to_PowerCepstrogram set-up
+            CepSeg& S = cseg[j];
+            double windowDuration = 2.0 * (3.0 / pitchFloor);
+            if (windowDuration > dx * (double)nseg[src]) windowDuration = dx * (double)nseg[src];
+            int nFrames = 0;
+            double t1 = 0.0;
+            if (!short_term_analysis(nseg[src], dx, x1, windowDuration, dt, &nFrames, &t1)) nFrames = 0;
+            S.t1 = t1; S.windowDuration = windowDuration;
+            S.nwin = (int)floor(windowDuration * fs10 + 0.5);
+            int nfft = 2;
+            while (nfft < S.nwin) nfft *= 2;
+            if (S.nwin < 1 || plan.jobs[j].nout < 1 || nfft > 1024) nFrames = 0;     // (nwin <= 1000 by construction)
+            S.nfft = nfft;
+            S.logM = 0;
+            while ((1 << S.logM) < nfft / 2) S.logM++;
+            const int nq = nfft / 2 + 1;
+            const double qmax = 0.5 * nfft / fs10;
+            S.dq = qmax / (nq - 1);
+            S.pad = 0;
+            fprefix[j + 1] = fprefix[j] + nFrames;
+        }
+    finish_plan(&plan, false);
+    const int totalFrames = fprefix[nsegs];
+    const int nqmax = 513;
+    // carve the CPP scratch
+    size_t need = 0;
+    auto sz = [&](size_t bytes) { size_t o = (need + 255) & ~(size_t)255; need = o + bytes; return o; };
+    size_t o_jobs = sz(sizeof(ResampleJob) * (nsegs + 1)), o_ids = sz(sizeof(int) * (nsegs + 1));
+    size_t o_opre = sz(sizeof(long long) * (nsegs + 2)), o_trep = sz(sizeof(int) * (nsegs + 1));
+    size_t o_z = sz(sizeof(double2) * (size_t)(plan.ztotal + 1)), o_filt = sz(sizeof(double) * (size_t)(plan.ftotal + 1));
+    size_t o_out = sz(sizeof(double) * (size_t)(plan.ototal + 1)), o_tab = sz(sizeof(double) * ((size_t)nsegs * (5 * 100 + 16) + 1));
+    size_t o_cseg = sz(sizeof(CepSeg) * (nsegs + 1)), o_fpre = sz(sizeof(int) * (nsegs + 2));
+    size_t o_cep = sz(sizeof(double) * ((size_t)totalFrames * nqmax + 1)), o_cppf = sz(sizeof(double) * ((size_t)totalFrames + 1));
+    if (need > h->cpp_cap) {
+        CK(cudaStreamSynchronize(s));
+        if (h->cpp_buf) CK(cudaFree(h->cpp_buf));
+        h->cpp_buf = nullptr; h->cpp_cap = 0;
+        size_t cap = need + (need >> 2);
+        CK(cudaMalloc((void**)&h->cpp_buf, cap));
+        h->cpp_cap = cap;
+    }
+    char* B = h->cpp_buf;
+    ResampleDev D;
+    D.jobs = (ResampleJob*)(B + o_jobs); D.ids = (int*)(B + o_ids); D.out_prefix = (long long*)(B + o_opre);
+    D.table_rep = (int*)(B + o_trep); D.zbuf = (double2*)(B + o_z); D.filt = (double*)(B + o_filt); D.out = (double*)(B + o_out);
+    D.table = (double*)(B + o_tab);
+    CepSeg* d_cseg = (CepSeg*)(B + o_cseg);
+    int* d_fprefix = (int*)(B + o_fpre);
+    double* d_cep = (double*)(B + o_cep);
+    double* d_cppf = (double*)(B + o_cppf);
+    if (nsegs > 0) {
+        int rc = upload_plan(h, plan, D, s);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(d_cseg, cseg.data(), sizeof(CepSeg) * nsegs, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(d_fprefix, fprefix.data(), sizeof(int) * (nsegs + 1), cudaMemcpyHostToDevice, s));
+    if (nsegs > 0 && totalFrames > 0) {
+        run_resample(h, plan, D, c.pcm, fs, fs10, 50, s);
+        const double emphasis = exp(-2.0 * MSHDS_PI * 50.0 * (1.0 / fs10));
+        launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, s); h->launches += 1;
+        const int nTimeAvg = (int)floor(0.01 / dt);
+        launch_cpp_frames(d_cseg, d_fprefix, nsegs, d_cep, nqmax, nTimeAvg, 0.001, d_cppf, totalFrames, s); h->launches += 1;
+    }
+    launch_cpp_reduce(c, sg, d_seg_prefix, d_fprefix, d_cppf, s); h->launches += 1;
+    CK(cudaStreamSynchronize(s));       // host vectors above must outlive the async copies
+    return MSHDS_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ one chunk
@@ -266,9 +469,9 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     void* stat_scratch = arena_take(h, (size_t)n * 16);
 
     // ---- pitch pass configurations (parselmouth defaults unless mshds_extractor.py passes a value)
-    PitchPass wide, mainp, hnr, srp, ltp;
+    PitchPass wide, mainp, hnr, srp, ltp, ccp, cpp_p;
     memset(&wide, 0, sizeof wide); memset(&mainp, 0, sizeof mainp); memset(&hnr, 0, sizeof hnr);
-    memset(&srp, 0, sizeof srp); memset(&ltp, 0, sizeof ltp);
+    memset(&srp, 0, sizeof srp); memset(&ltp, 0, sizeof ltp); memset(&ccp, 0, sizeof ccp); memset(&cpp_p, 0, sizeof cpp_p);
     int rc;
     for (int k = 0; k < 3; k++) {
         // :143 to_pitch_ac(time_step=0.005, pitch_floor=50, pitch_ceiling=600)
@@ -281,6 +484,10 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
         if ((rc = make_pitch_cfg(h, fs, 0.02, 30.0, 3.0, 4, 0, 0.03, 0.25, 0.01, 0.35, 0.25, 450.0, &srp.cfg[k]))) return rc;
         // :241 Sound_to_PointProcess_periodic_cc -> Sound_to_Pitch (0.0, floor, ceiling): dt = 0.75 / floor
         if ((rc = make_pitch_cfg(h, fs, 0.0, cls_floor(k), 3.0, 15, 0, 0.03, 0.45, 0.01, 0.35, 0.14, cls_ceiling(k), &ltp.cfg[k]))) return rc;
+        // :320 to_pitch_cc(0.005, floor, ceiling): forward cross-correlation, 1 period per window
+        if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 1.0, 15, 2, 0.03, 0.45, 0.01, 0.35, 0.14, cls_ceiling(k), &ccp.cfg[k]))) return rc;
+        // :270 to_pitch_ac(0.005, floor, ceiling, voicing_threshold=0.3)
+        if ((rc = make_pitch_cfg(h, fs, 0.005, cls_floor(k), 3.0, 15, 0, 0.03, 0.3, 0.01, 0.35, 0.14, cls_ceiling(k), &cpp_p.cfg[k]))) return rc;
     }
     hnr.hnr_mode = 1;
 
@@ -297,6 +504,8 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     const long long fub75 = frames_upper_bound(lens, dx, 0.75 / 100.0);
     alloc_pitch_pass(h, &srp, n, fub20, cs);
     alloc_pitch_pass(h, &ltp, n, fub75, cs);
+    alloc_pitch_pass(h, &ccp, n, fub5, cs);
+    alloc_pitch_pass(h, &cpp_p, n, fub5, cs);
 
     // ---- glottal pulses: raw / final capacity per clip (shared raw scratch, one final set per consumer)
     const double cprime = 500.0 / 0.8 * 1.15;
@@ -317,12 +526,50 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     double* raw_ar = take<double>(h, fub5); long long* raw_reg = take<long long>(h, fub5);
     auto alloc_pulses = [&](PulseSet* ps) {
         ps->cprime = cprime; ps->cap_start = d_pcap;
-        ps->t = take<double>(h, ptotal); ps->count = take<int>(h, n);
+        ps->t = take<double>(h, ptotal); ps->count = take<int>(h, n); ps->valid = take<int>(h, n);
         ps->st_count = take<int>(h, n); ps->st_start = take<int>(h, n + 1);
         ps->st_ileft = st_il; ps->st_iright = st_ir; ps->raw_t = raw_t; ps->raw_thr = raw_thr;
         ps->raw_nleft = raw_nl; ps->raw_nright = raw_nr; ps->raw_added_right = raw_ar; ps->raw_region = raw_reg;
     };
     alloc_pulses(&pl_lt);
+    PulseSet pl_fm, pl_cp;
+    memset(&pl_fm, 0, sizeof pl_fm); memset(&pl_cp, 0, sizeof pl_cp);
+    alloc_pulses(&pl_fm);
+    alloc_pulses(&pl_cp);
+
+    // ---- formants (:319): whole-clip resample to 10 kHz (precision 500) + Burg frames
+    const double fs10 = 10000.0;
+    ResamplePlan fplan;
+    fplan.jobs.resize(n);
+    for (int i = 0; i < n; i++)
+        fill_resample_job(&fplan.jobs[i], off_host[i], lens[i], 1, lens[i], 0.5 * dx, (double)lens[i] * dx, fs10);
+    finish_plan(&fplan, true);
+    ResampleDev fdev;
+    fdev.jobs = take<ResampleJob>(h, n); fdev.ids = take<int>(h, n); fdev.out_prefix = take<long long>(h, n + 1);
+    fdev.table_rep = take<int>(h, fplan.table_rep.size());
+    fdev.zbuf = take<double2>(h, fplan.ztotal); fdev.filt = take<double>(h, fplan.ftotal); fdev.out = take<double>(h, fplan.ototal);
+    fdev.table = take<double>(h, fplan.table_rep.size() * (5 * 1000 + 16));
+    FormantPass fm;
+    memset(&fm, 0, sizeof fm);
+    fm.jobs = fdev.jobs; fm.dt = 0.005; fm.dt_window = 2.0 * 0.025;
+    {
+        double dx10 = 1.0 / fs10;
+        fm.nsamp_window = (int)floor(fm.dt_window / dx10);
+        fm.emphasis = exp(-2.0 * MSHDS_PI * 50.0 * dx10);
+        fm.nyquist = 0.5 / dx10;
+        if ((rc = make_formant_window(h, fm.nsamp_window, &fm.window))) return rc;
+    }
+    fm.nF = take<int>(h, n); fm.t1 = take<double>(h, n); fm.fstart = take<int>(h, n + 1);
+    fm.nform = take<int>(h, fub5); fm.freq = take<double>(h, fub5 * 5); fm.bw = take<double>(h, fub5 * 5);
+
+    // ---- CPP (:253-301): voiced segment list (capacity: one segment per 20 ms at most)
+    std::vector<int> scap(n + 1, 0);
+    for (int i = 0; i < n; i++) scap[i + 1] = scap[i] + (int)floor((double)lens[i] * dx * 50.0) + 2;
+    CppSegs sg;
+    sg.cap_start = take<int>(h, n + 1); sg.count = take<int>(h, n); sg.fail = take<int>(h, n);
+    sg.tmin = take<double>(h, scap[n]); sg.tmax = take<double>(h, scap[n]);
+    sg.ix1 = take<long long>(h, scap[n]); sg.nseg = take<int>(h, scap[n]);
+    int* seg_prefix = take<int>(h, n + 1);
 
     // ---- LTAS
     LtasPass lt;
@@ -368,6 +615,8 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
 
     CK(cudaMemcpyAsync(d_off, off_host.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_pcap, pcap.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sg.cap_start, scap.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
+    if ((rc = upload_plan(h, fplan, fdev, s))) return rc;
     const int fhint = (int)(fub5 > 0x3fffffff ? 0x3fffffff : fub5);
 
     // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
@@ -410,6 +659,23 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     launch_pulses(c, ltp, pl_lt, s); h->launches += 5;
     launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5;
 
+    // ---- _measureFormants (:303-338)
+    run_resample(h, fplan, fdev, d_pcm, fs, fs10, 500, s);
+    launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3;
+    launch_pitch_grid(c, ccp, s); h->launches += 2;
+    launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1;
+    launch_pitch_viterbi(c, ccp, s); h->launches += 1;
+    launch_pulses(c, ccp, pl_fm, s); h->launches += 5;
+    launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
+
+    // ---- _extract_CPP (:253-301)
+    launch_pitch_grid(c, cpp_p, s); h->launches += 2;
+    launch_pitch_frames(c, cpp_p, h->tw, fhint, s); h->launches += 1;
+    launch_pitch_viterbi(c, cpp_p, s); h->launches += 1;
+    launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5;
+    launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;
+    if ((rc = run_cpp_stage(h, c, off_host, lens, sg, scap, seg_prefix, fs, s))) return rc;
+
     // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
     launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4;
 
@@ -427,6 +693,15 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     reg_debug(h, "intensity_sr", isr.out, isr.fstart, isr.nF, 0, 8);
     reg_debug(h, "pulses_ltas", pl_lt.t, pl_lt.cap_start, pl_lt.count, 0, 8);
     reg_debug(h, "ltas_bands", ltas_bands, nullptr, nullptr, 50, 8);
+    reg_debug(h, "pitch_cc_f", ccp.sel_f, ccp.fstart, ccp.nF, 0, 8);
+    reg_debug(h, "pitch_cpp_f", cpp_p.sel_f, cpp_p.fstart, cpp_p.nF, 0, 8);
+    reg_debug(h, "pulses_fmt", pl_fm.t, pl_fm.cap_start, pl_fm.count, 0, 8);
+    reg_debug(h, "pulses_cpp", pl_cp.t, pl_cp.cap_start, pl_cp.count, 0, 8);
+    reg_debug(h, "formant_f", fm.freq, fm.fstart, fm.nF, 0, 8, 5);
+    reg_debug(h, "formant_b", fm.bw, fm.fstart, fm.nF, 0, 8, 5);
+    reg_debug(h, "formant_n", fm.nform, fm.fstart, fm.nF, 0, 4);
+    reg_debug(h, "resampled10k", fdev.out, nullptr, nullptr, 0, 8);
+    h->debug["resampled10k"].host_prefix = fplan.out_prefix;
     h->last_n = n;
     return MSHDS_OK;
 }
@@ -469,6 +744,8 @@ void mshds_destroy(mshds_handle* h) {
     for (auto& kv : h->ac_windows) { cudaFree(kv.second.first); cudaFree(kv.second.second); }
     for (auto& kv : h->kaiser) cudaFree(kv.second);
     for (auto& kv : h->gauss_spec) cudaFree(kv.second);
+    for (auto& kv : h->gauss_formant) cudaFree(kv.second);
+    cudaFree(h->cpp_buf);
     cudaFree(h->tw);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -576,8 +853,11 @@ int mshds_debug_fetch(mshds_handle* h, const char* name, int clip, void* host_bu
     if (it == h->debug.end() || clip < 0 || clip >= h->last_n) { h->err = "unknown debug name or clip"; return MSHDS_ERR_ARG; }
     const DebugEntry& e = it->second;
     CK(cudaSetDevice(h->device));
-    int start = clip * e.fixed, count = e.fixed;
-    if (e.start) CK(cudaMemcpy(&start, e.start + clip, sizeof(int), cudaMemcpyDeviceToHost));
+    long long start = (long long)clip * e.fixed;
+    int count = e.fixed;
+    if (!e.host_prefix.empty()) { start = e.host_prefix[clip]; count = (int)(e.host_prefix[clip + 1] - e.host_prefix[clip]); }
+    int start_i = 0;
+    if (e.start) { CK(cudaMemcpy(&start_i, e.start + clip, sizeof(int), cudaMemcpyDeviceToHost)); start = start_i; }
     if (e.count) CK(cudaMemcpy(&count, e.count + clip, sizeof(int), cudaMemcpyDeviceToHost));
     size_t nel = (size_t)count * e.stride;
     *n_out = nel;

@@ -70,3 +70,16 @@ for c in range(len(durs)):
     lb = orc.ltas(x, 16000.0, fl, ce)
     if lb is not None:
         cmp("ltas_bands", ex.debug_fetch("ltas_bands", c), lb[0], tol=1e-9)
+    rs, rx1 = orc.resample(x, 16000.0, 10000.0, 500)
+    cmp("resampled10k", ex.debug_fetch("resampled10k", c), rs, tol=1e-9)
+    fo = orc.formants(x, 16000.0)
+    gn = ex.debug_fetch("formant_n", c, np.int32)
+    print("  formant_n equal:", np.array_equal(gn, fo["n"]), len(gn), len(fo["n"]))
+    gf = ex.debug_fetch("formant_f", c).reshape(-1, 5)
+    gb = ex.debug_fetch("formant_b", c).reshape(-1, 5)
+    cmp("formant_f", gf.ravel(), fo["f"].ravel(), tol=1e-7)
+    cmp("formant_b", gb.ravel(), fo["bw"].ravel(), tol=1e-6)
+    pcc = orc.pitch(x, 16000.0, 2, 0.005, fl, 1.0, 15, 0.03, 0.45, 0.01, 0.35, 0.14, ce)
+    cmp("pitch_cc_f", ex.debug_fetch("pitch_cc_f", c), pcc["freq"])
+    cmp("pulses_fmt", ex.debug_fetch("pulses_fmt", c), orc.pulses(x, 16000.0, 2, 0.005, fl, 1.0, 0.45, ce))
+    cmp("pulses_cpp", ex.debug_fetch("pulses_cpp", c), orc.pulses(x, 16000.0, 0, 0.005, fl, 3.0, 0.3, ce))
