@@ -253,9 +253,12 @@ __global__ void __launch_bounds__(256) k_formant_stats(Clips c, FormantPass p, P
                 sd = sqrt(v2 / (n - 1.0));
             }
         }
-        if (threadIdx.x == 0) { feat[2 * q] = mean; feat[2 * q + 1] = sd; }
+        if (threadIdx.x == 0) {
+            feat[2 * q] = mean; feat[2 * q + 1] = sd;
+            // status bit = "mean_F1_Loc is NaN" (helper raised, or no pulse produced a value)
+            if (q == 0 && is_undef(mean)) atomicOr(&c.status[clip], ST_FORMANT);
+        }
     }
-    if (threadIdx.x == 0 && !valid) atomicOr(&c.status[clip], ST_FORMANT);
 }
 
 void launch_formants(const Clips& c, const FormantPass& p, int njobs, const double* sig, int max_frames_hint, cudaStream_t s) {

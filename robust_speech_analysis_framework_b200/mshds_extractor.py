@@ -1,0 +1,137 @@
+"""Host-side mirror of the reference's MSHDS extractor interface.
+
+Reference: /root/reference/src/mshds_extractor.py
+  * extract_mshds_features(input_df, audio_file_column='filepath', verbose=True) -> DataFrame   (:379-459)
+    one row per input row, in input order, columns ['filename'] + the 25 names of :397-404, float64 values;
+    it never raises: a helper failure gives NaN for that helper's columns (:124,161,182,204,224,250,300,337,375) and a
+    file that cannot be loaded gives a NaN row with the filename kept and, iff verbose, the printed message of :452-453.
+
+Here the per-file Praat calls are replaced by ONE batched call into libmshds_b200.so (include/mshds_b200.h) per group
+of recordings; WAV decoding and mono mix-down stay on the host (the reference does them inside parselmouth.Sound, :415-417).
+There is no CPU fallback: without the CUDA library / a CUDA device the function raises at the first call.
+"""
+from __future__ import annotations
+
+import os
+import wave
+
+import numpy as np
+
+from . import _lib
+
+FEATURE_NAMES = list(_lib.FEATURE_NAMES)
+TARGET_RATE = 16000
+
+
+class AudioLoadError(Exception):
+    pass
+
+
+def read_wav_mono_int16(path: str):
+    """Decode a PCM WAV into (int16 mono samples, sample_rate).
+
+    16-bit files are passed through bit-exactly (what parselmouth.Sound(path) holds is sample/32768, :415); multi-channel
+    audio is averaged like Sound.convert_to_mono (:416-417).  8/24/32-bit PCM is re-quantised to int16.
+    """
+    try:
+        with wave.open(path, "rb") as w:
+            nch, sw, fs, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+            raw = w.readframes(n)
+    except Exception as e:  # includes FileNotFoundError, wave.Error, EOFError
+        raise AudioLoadError(str(e)) from e
+    if sw == 2:
+        x = np.frombuffer(raw, dtype="<i2").astype(np.int32)
+    elif sw == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.int32) - 128) << 8
+    elif sw == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        x = ((b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)) << 8 >> 8) >> 8
+    elif sw == 4:
+        x = np.frombuffer(raw, dtype="<i4").astype(np.int64) >> 16
+    else:
+        raise AudioLoadError(f"unsupported sample width {sw}")
+    if nch > 1:
+        x = x.reshape(-1, nch)
+        x = np.floor(x.mean(axis=1) + 0.5)
+    return np.clip(x, -32768, 32767).astype(np.int16), int(fs)
+
+
+_EXTRACTORS = {}
+
+
+def get_extractor(device: int = 0) -> "_lib.Extractor":
+    ex = _EXTRACTORS.get(device)
+    if ex is None:
+        ex = _lib.Extractor(device)
+        _EXTRACTORS[device] = ex
+    return ex
+
+
+def extract_mshds_from_pcm(pcm: np.ndarray, offsets: np.ndarray, sample_rate: int = TARGET_RATE, device: int = 0):
+    """Tensor-level entry: packed int16 batch + offsets -> (features [n,25] float64, status [n] uint32)."""
+    return get_extractor(device).extract_host(pcm, offsets, sample_rate)
+
+
+def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True, device: int = 0, max_batch_seconds: float = 7200.0):
+    """Drop-in for /root/reference/src/mshds_extractor.py:379 (same name, arguments, columns, NaN conventions).
+
+    `device` and `max_batch_seconds` are additions with defaults; every recording is still processed independently.
+    """
+    import pandas as pd
+
+    ex = get_extractor(device)
+    paths = [row[audio_file_column] for _, row in input_df.iterrows()]
+    filenames = [os.path.basename(p) for p in paths]
+    n = len(paths)
+    feats = np.full((n, len(FEATURE_NAMES)), np.nan, dtype=np.float64)
+
+    batch_idx, batch_pcm, batch_samples = [], [], 0
+
+    def flush():
+        nonlocal batch_idx, batch_pcm, batch_samples
+        if not batch_idx:
+            return
+        offs = np.cumsum([0] + [len(p) for p in batch_pcm]).astype(np.int64)
+        pcm = np.concatenate(batch_pcm) if batch_pcm else np.zeros(0, np.int16)
+        try:
+            out, _status = ex.extract_host(pcm, offs, TARGET_RATE)
+            feats[np.asarray(batch_idx)] = out
+        except Exception as e:  # mirrors the whole-file handler at :450-457
+            if verbose:
+                for i in batch_idx:
+                    print(f"ERROR processing file '{filenames[i]}': {e}. Appending NaNs.")
+        batch_idx, batch_pcm, batch_samples = [], [], 0
+
+    iterator = range(n)
+    if verbose:
+        try:
+            from tqdm.auto import tqdm
+            iterator = tqdm(iterator, total=n, desc="Extracting MSHDS Features")
+        except Exception:
+            pass
+    for i in iterator:
+        try:
+            pcm, fs = read_wav_mono_int16(paths[i])
+            if fs != TARGET_RATE:
+                # :418-419 snd.resample(16000, 50): front-end row of SURVEY 8f-2, not built in this round
+                raise AudioLoadError(f"sampling frequency {fs} Hz: only 16 kHz input is supported by the device path yet")
+            if len(pcm) == 0:
+                raise AudioLoadError("empty sound")
+        except Exception as e:
+            if verbose:
+                print(f"ERROR processing file '{filenames[i]}': {e}. Appending NaNs.")
+            continue
+        batch_idx.append(i)
+        batch_pcm.append(pcm)
+        batch_samples += len(pcm)
+        if batch_samples >= max_batch_seconds * TARGET_RATE:
+            flush()
+    flush()
+
+    rows = []
+    for i in range(n):
+        d = {'filename': filenames[i]}
+        for k, name in enumerate(FEATURE_NAMES):
+            d[name] = float(feats[i, k])
+        rows.append(d)
+    return pd.DataFrame(rows)

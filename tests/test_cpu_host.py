@@ -1,0 +1,198 @@
+"""CPU-side tests (no GPU): oracle vs frozen golden vectors, C-ABI export check, host logic of the drop-in, sharding."""
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "mshds_golden_v1.npz")
+
+
+def test_oracle_reproduces_golden(orc):
+    g = np.load(GOLDEN)
+    feats, status = orc.extract(g["pcm"], g["offsets"], 16000.0, nthreads=os.cpu_count() or 1)
+    assert list(g["feature_names"]) == orc.FEATURE_NAMES
+    assert np.array_equal(np.isnan(feats), np.isnan(g["features"]))
+    np.testing.assert_allclose(feats, g["features"], rtol=1e-9, atol=1e-12, equal_nan=True)
+    assert np.array_equal(status, g["status"])
+
+
+def test_golden_values_are_plausible_against_reference_printout():
+    # the only numbers the reference repo shows (5 Androids files, inputs unavailable): unit sanity.
+    g = np.load(GOLDEN)
+    f = g["features"][:4]
+    names = list(g["feature_names"])
+    col = lambda n: f[:, names.index(n)]
+    assert np.all((col("Speaking_Rate") > 0.5) & (col("Speaking_Rate") < 8))
+    assert np.all((col("Phonation_Ratio") > 0.3) & (col("Phonation_Ratio") <= 1.0))
+    assert np.all((col("mean_F0") > 60) & (col("mean_F0") < 400))
+    assert np.all((col("mean_dB") > 40) & (col("mean_dB") < 95))          # dB re 2e-5 Pa
+    assert np.all((col("Spectral_Tilt") < 0) & (col("Spectral_Tilt") > -0.05))   # dB/Hz
+    assert np.all((col("Cepstral_Peak_Prominence") > 4) & (col("Cepstral_Peak_Prominence") < 40))
+    assert np.all((col("mean_F1_Loc") > 200) & (col("mean_F1_Loc") < 1000))
+    # pause durations live on the 16 ms intensity grid (App. B note)
+    mp, pr = col("Mean_Pause_Duration"), col("Pause_Rate")
+    assert np.all(mp >= 0)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from robust_speech_analysis_framework_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "mshds_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mshds_[a-z_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/mshds_b200.h but not exported"
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from robust_speech_analysis_framework_b200 import _lib
+    with pytest.raises(_lib.MshdsError):
+        _lib.Extractor(0)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "robust_speech_analysis_framework_b200")
+    pat = re.compile(r"^\s*(import\s+oracle|from\s+oracle|from\s+\.\.?oracle)|libmshds_oracle|#include\s+\".*oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, fn)).read()), fn
+
+
+def _write_wav(path, x, fs=16000, nch=1):
+    import wave
+    with wave.open(path, "wb") as w:
+        w.setnchannels(nch)
+        w.setsampwidth(2)
+        w.setframerate(fs)
+        w.writeframes(np.asarray(x, dtype="<i2").tobytes())
+
+
+def test_wav_reader(tmp_path):
+    from robust_speech_analysis_framework_b200.mshds_extractor import AudioLoadError, read_wav_mono_int16
+    x = (np.arange(-500, 500) * 13).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    _write_wav(p, x)
+    y, fs = read_wav_mono_int16(p)
+    assert fs == 16000 and np.array_equal(x, y)
+    st = np.stack([x, -x], axis=1).ravel()
+    _write_wav(p, st, nch=2)
+    y, _ = read_wav_mono_int16(p)
+    assert np.all(y == 0)
+    with pytest.raises(AudioLoadError):
+        read_wav_mono_int16(str(tmp_path / "missing.wav"))
+
+
+class _FakeExtractor:
+    """Stands in for the CUDA handle so the DataFrame / error-convention logic can be tested without a GPU."""
+    def extract_host(self, pcm, offsets, sample_rate=16000):
+        n = len(offsets) - 1
+        out = np.zeros((n, 25))
+        for i in range(n):
+            seg = pcm[offsets[i]:offsets[i + 1]].astype(np.float64)
+            out[i] = seg.sum() + np.arange(25)
+        return out, np.zeros(n, np.uint32)
+
+
+def test_dataframe_contract_matches_reference(tmp_path, monkeypatch, capsys):
+    import pandas as pd
+    from robust_speech_analysis_framework_b200 import mshds_extractor as mx
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: _FakeExtractor())
+    a, b = np.full(4000, 3, np.int16), np.full(2000, -5, np.int16)
+    pa, pb = str(tmp_path / "s1" / "a.wav"), str(tmp_path / "b.wav")
+    os.makedirs(os.path.dirname(pa))
+    _write_wav(pa, a)
+    _write_wav(pb, b)
+    _write_wav(str(tmp_path / "c44.wav"), a, fs=44100)
+    df = pd.DataFrame({"other": [1, 2, 3, 4], "filepath": [pa, str(tmp_path / "nope.wav"), pb, str(tmp_path / "c44.wav")]})
+    out = mx.extract_mshds_features(df, verbose=True)
+    # mshds_extractor.py:240 smoke check shape (n, 26); column order :397-404; filename = basename (:410)
+    assert list(out.columns) == ["filename"] + mx.FEATURE_NAMES and out.shape == (4, 26)
+    assert list(out["filename"]) == ["a.wav", "nope.wav", "b.wav", "c44.wav"]
+    assert out.iloc[0]["Speaking_Rate"] == 12000.0 and out.iloc[2]["Spectral_Kurtosis"] == -10000.0 + 24
+    assert out.iloc[1][mx.FEATURE_NAMES].isna().all() and out.iloc[3][mx.FEATURE_NAMES].isna().all()
+    assert "ERROR processing file 'nope.wav'" in capsys.readouterr().out      # :452-453
+    quiet = mx.extract_mshds_features(df, verbose=False)
+    assert capsys.readouterr().out == "" and quiet.shape == (4, 26)
+    assert out[mx.FEATURE_NAMES].dtypes.map(lambda d: d == np.float64).all()
+    # custom column name (:379 audio_file_column)
+    out2 = mx.extract_mshds_features(df.rename(columns={"filepath": "p"}), audio_file_column="p", verbose=False)
+    assert out2.equals(quiet)
+    # drop-in import path of the notebooks (01_feature_extraction_setup.ipynb:31)
+    sys.path.insert(0, ROOT)
+    from src.mshds_extractor import extract_mshds_features as shim
+    assert shim is mx.extract_mshds_features
+
+
+def test_lpt_sharding_is_a_partition_and_balanced():
+    from robust_speech_analysis_framework_b200.sharding import lpt_assign, pack_subset
+    rng = np.random.default_rng(0)
+    lens = rng.integers(60, 600, size=230) * 16000
+    for w in (1, 2, 4, 8):
+        parts = lpt_assign(lens, w)
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(230))
+        loads = [int(lens[p].sum()) for p in parts]
+        assert max(loads) - min(loads) <= lens.max()
+    pcm = np.arange(30, dtype=np.int16)
+    off = np.array([0, 10, 10, 25, 30])
+    d, o = pack_subset(pcm, off, [3, 0, 1])
+    assert list(o) == [0, 5, 15, 15] and list(d[:5]) == list(range(25, 30))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, pcm, off, q):
+    import torch.distributed as dist
+    from robust_speech_analysis_framework_b200.sharding import extract_sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    out, st = extract_sharded(pcm, off, _FakeExtractor().extract_host, rank, world)
+    if rank == 0:
+        q.put((out, st))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_process_gloo_shard_and_gather_equals_single_process():
+    import torch.multiprocessing as mp
+    from robust_speech_analysis_framework_b200.sharding import extract_sharded
+    rng = np.random.default_rng(1)
+    lens = rng.integers(100, 3000, size=13)
+    lens[4] = 0                                      # an empty recording must keep its row
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = rng.integers(-2000, 2000, size=int(off[-1])).astype(np.int16)
+    want, wst = extract_sharded(pcm, off, _FakeExtractor().extract_host, 0, 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, pcm, off, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, gst = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got, want) and np.array_equal(gst, wst)
+
+
+def test_synth_is_deterministic_and_well_formed():
+    from robust_speech_analysis_framework_b200.synth import synth_batch, synth_clip
+    a, b = synth_clip(3, 1.5), synth_clip(3, 1.5)
+    assert a.dtype.is_signed and a.numel() == 24000 and bool((a == b).all())
+    assert int(a.abs().max()) > 8000 and int(a.abs().max()) <= 32767
+    pcm, off = synth_batch(3, [0.5, 0.25, 0.75])
+    assert list(off) == [0, 8000, 12000, 24000] and pcm.numel() == 24000

@@ -1,0 +1,223 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (ctypes binding of
+include/mshds_b200.h), against the CPU oracle and the frozen golden vectors.
+
+Tolerances (BASELINE.md / north_star): spectral, LTAS, CPP, intensity, HNR columns <= 1e-4 relative; mean_F0 <= 0.5 Hz;
+formant statistics <= 1e-3 relative; count-derived speech-rate columns exact.  The kernels do everything decision-critical
+in float64, so the tests hold them to much tighter bounds (written next to each assert).
+"""
+import os
+import wave
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden", "mshds_golden_v1.npz")
+
+SPEECHRATE = slice(0, 5)
+REL_TOL = {  # per column group: (rtol, atol)
+    "speechrate": (1e-12, 1e-12),      # decisions agree exactly; only the final divisions could differ in the last bit
+    "pitch": (1e-7, 1e-7),             # north_star: 0.5 Hz
+    "continuous": (1e-6, 1e-9),        # north_star: 1e-4 relative
+    "formant": (1e-5, 1e-6),           # north_star: 1e-3 relative (different root finders: Aberth vs Hessenberg QR)
+}
+GROUP_OF = ["speechrate"] * 5 + ["pitch"] * 2 + ["continuous"] * 6 + ["formant"] * 8 + ["continuous"] * 4
+
+
+@pytest.fixture(scope="module")
+def ex():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from robust_speech_analysis_framework_b200 import _lib
+    e = _lib.Extractor(0)
+    yield e
+    e.close()
+
+
+def assert_features_close(got, want, what=""):
+    assert got.shape == want.shape
+    assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: NaN pattern differs\n{got}\n{want}"
+    for k in range(25):
+        rtol, atol = REL_TOL[GROUP_OF[k]]
+        np.testing.assert_allclose(got[:, k], want[:, k], rtol=rtol, atol=atol, equal_nan=True, err_msg=f"{what} column {k}")
+
+
+def test_golden_vectors(ex):
+    g = np.load(GOLDEN)
+    got, status = ex.extract_host(g["pcm"], g["offsets"])
+    assert_features_close(got, g["features"], "golden")
+    assert np.array_equal(status, g["status"])
+
+
+def _batch(durs, start=0):
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    clips = [synth_clip(start + i, d).numpy() for i, d in enumerate(durs)]
+    return np.concatenate(clips), np.cumsum([0] + [len(c) for c in clips]).astype(np.int64), clips
+
+
+def test_parity_with_oracle_on_ragged_batch(ex, orc):
+    pcm, off, _ = _batch([6.0, 2.00006, 9.3, 4.1, 12.0, 3.33339], start=20)
+    got, st = ex.extract_host(pcm, off)
+    want, wst = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
+    assert_features_close(got, want, "ragged batch")
+    assert np.array_equal(st, wst)
+    # the count-derived columns must be bit-identical unless a decision flipped (none may)
+    assert np.array_equal(got[:, SPEECHRATE], want[:, SPEECHRATE])
+
+
+def test_stage_level_parity(ex, orc):
+    pcm, off, clips = _batch([5.0, 4.00006], start=40)
+    ex.extract_host(pcm, off)
+    for c, clip in enumerate(clips):
+        x = orc.pcm_to_float(clip)
+        fl, ce, _ = orc.pitch_values(x)
+        cls = int(ex.debug_fetch("class", c, np.int32)[0])
+        assert (60.0, 100.0, 75.0)[cls] == fl
+        ref = orc.pitch(x, 16000.0, 0, 0.005, fl, 3.0, 15, 0.03, 0.45, 0.01, 0.35, 0.14, ce)
+        got_f = ex.debug_fetch("pitch_main_f", c)
+        assert len(got_f) == len(ref["freq"])
+        assert np.array_equal(got_f > 0, ref["freq"] > 0)                       # voicing decisions identical
+        np.testing.assert_allclose(got_f, ref["freq"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(ex.debug_fetch("pitch_main_s", c), ref["strength"], rtol=0, atol=1e-9)
+        ic, _ = orc.intensity(x, 16000.0, fl, 0.005)
+        np.testing.assert_allclose(ex.debug_fetch("intensity_main", c), ic, rtol=0, atol=1e-10)
+        isr, _ = orc.intensity(x, 16000.0, 50.0, 0.016)
+        np.testing.assert_allclose(ex.debug_fetch("intensity_sr", c), isr, rtol=0, atol=1e-10)
+        for name, meth, ppw, vt, dt in (("pulses_ltas", 0, 3.0, 0.45, 0.0), ("pulses_cpp", 0, 3.0, 0.3, 0.005), ("pulses_fmt", 2, 1.0, 0.45, 0.005)):
+            want_p = orc.pulses(x, 16000.0, meth, dt, fl, ppw, vt, ce)
+            got_p = ex.debug_fetch(name, c)
+            assert len(got_p) == len(want_p), name
+            np.testing.assert_allclose(got_p, want_p, rtol=0, atol=1e-9, err_msg=name)
+        rs, _ = orc.resample(x, 16000.0, 10000.0, 500)
+        np.testing.assert_allclose(ex.debug_fetch("resampled10k", c), rs, rtol=0, atol=1e-10)
+        fo = orc.formants(x, 16000.0)
+        assert np.array_equal(ex.debug_fetch("formant_n", c, np.int32), fo["n"])
+        np.testing.assert_allclose(ex.debug_fetch("formant_f", c).reshape(-1, 5), fo["f"], rtol=1e-6, atol=1e-4, equal_nan=True)
+        bands, _ = orc.ltas(x, 16000.0, fl, ce)
+        np.testing.assert_allclose(ex.debug_fetch("ltas_bands", c), bands, rtol=0, atol=1e-9)
+
+
+def test_edge_cases_follow_reference_error_convention(ex, orc):
+    rng = np.random.default_rng(3)
+    clips = [
+        np.zeros(0, np.int16),                                   # empty recording -> whole row NaN (:450-457)
+        np.zeros(32000, np.int16),                               # digital silence
+        np.full(20000, 1234, np.int16),                          # DC only
+        (rng.normal(scale=300, size=100)).astype(np.int16),      # shorter than every window
+        (rng.normal(scale=500, size=1500)).astype(np.int16),     # ~0.094 s: some analyses fit, others throw
+        (rng.normal(scale=500, size=2300)).astype(np.int16),     # ~0.144 s
+        (rng.normal(scale=900, size=40000)).astype(np.int16),    # unvoiced noise
+    ]
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    got, st = ex.extract_host(pcm, off)
+    assert np.all(np.isnan(got[0])) and (st[0] & (1 << 31))
+    want, wst = orc.extract(pcm, off, 16000.0, nthreads=4)
+    assert_features_close(got[1:], want[1:], "edge cases")
+    assert np.array_equal(st[1:], wst[1:])
+
+
+def test_batch_composition_does_not_change_a_clip(ex):
+    pcm, off, clips = _batch([3.0, 5.5, 2.2, 4.4, 3.3], start=60)
+    full, _ = ex.extract_host(pcm, off)
+    # permuted order
+    perm = [3, 0, 4, 2, 1]
+    p2 = np.concatenate([clips[i] for i in perm])
+    o2 = np.cumsum([0] + [len(clips[i]) for i in perm]).astype(np.int64)
+    permuted, _ = ex.extract_host(p2, o2)
+    assert np.array_equal(permuted, full[perm], equal_nan=True)              # bit-identical
+    # one clip alone, and duplicated
+    alone, _ = ex.extract_host(clips[2], np.array([0, len(clips[2])], np.int64))
+    assert np.array_equal(alone[0], full[2], equal_nan=True)
+    dup, _ = ex.extract_host(np.concatenate([clips[2], clips[2]]), np.array([0, len(clips[2]), 2 * len(clips[2])], np.int64))
+    assert np.array_equal(dup[0], dup[1], equal_nan=True) and np.array_equal(dup[0], full[2], equal_nan=True)
+    # chunked execution (scratch bounded to ~2 clips at a time) gives the same bits
+    ex.set_chunk_samples(100000)
+    try:
+        chunked, _ = ex.extract_host(pcm, off)
+    finally:
+        ex.set_chunk_samples(1 << 27)
+    assert np.array_equal(chunked, full, equal_nan=True)
+
+
+def test_device_resident_entry_point(ex):
+    import torch
+    pcm, off, _ = _batch([2.5, 3.5], start=80)
+    host, hst = ex.extract_host(pcm, off)
+    d_pcm = torch.from_numpy(pcm).cuda()
+    d_out = torch.empty((2, 25), dtype=torch.float64, device="cuda")
+    d_st = torch.empty(2, dtype=torch.int32, device="cuda")
+    ex.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ex.extract_device(d_pcm.data_ptr(), off, d_out.data_ptr(), d_st.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        ex.set_stream(None)
+    assert np.array_equal(d_out.cpu().numpy(), host, equal_nan=True)
+    assert np.array_equal(d_st.cpu().numpy().astype(np.uint32), hst)
+
+
+def test_bad_arguments_are_errors_not_crashes(ex):
+    from robust_speech_analysis_framework_b200 import _lib
+    pcm = np.zeros(1000, np.int16)
+    with pytest.raises(_lib.MshdsError):
+        ex.extract_host(pcm, np.array([0, 1000], np.int64), sample_rate=44100)
+    with pytest.raises(_lib.MshdsError):
+        ex.extract_host(pcm, np.array([500, 100], np.int64))
+    out, st = ex.extract_host(np.zeros(0, np.int16), np.array([0], np.int64))
+    assert out.shape == (0, 25)
+
+
+def _write_wav(path, x, fs=16000):
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(fs)
+        w.writeframes(np.asarray(x, dtype="<i2").tobytes())
+
+
+def test_drop_in_dataframe_api_feeds_the_svm_consumer(tmp_path, orc):
+    """extract_mshds_features on WAV files, then the reference's consumer pipeline (cv_strategies.py:38-78:
+    StandardScaler -> SelectKBest(f_classif) -> linear SVC, stratified 5-fold) runs unchanged on the frame."""
+    import pandas as pd
+    from sklearn.feature_selection import SelectKBest, f_classif
+    from sklearn.model_selection import StratifiedKFold, cross_val_score
+    from sklearn.pipeline import Pipeline
+    from sklearn.preprocessing import StandardScaler
+    from sklearn.svm import SVC
+    from src.mshds_extractor import extract_mshds_features
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+
+    paths, clips = [], []
+    for i in range(12):
+        x = synth_clip(200 + i, 2.5 + 0.25 * (i % 3)).numpy()
+        p = str(tmp_path / f"{i:02d}_clip.wav")
+        _write_wav(p, x)
+        paths.append(p)
+        clips.append(x)
+    paths.insert(5, str(tmp_path / "missing.wav"))
+    df = extract_mshds_features(pd.DataFrame({"filepath": paths}), verbose=False)
+    assert df.shape == (13, 26) and df.iloc[5, 1:].isna().all()
+    assert list(df["filename"])[:2] == ["00_clip.wav", "01_clip.wav"]
+    want, _ = orc.extract(np.concatenate(clips), np.cumsum([0] + [len(c) for c in clips]).astype(np.int64), 16000.0, nthreads=4)
+    got = df.drop(index=5).iloc[:, 1:].to_numpy(dtype=np.float64)
+    assert_features_close(got, want, "dataframe api")
+    X = df.drop(columns=["filename"])
+    X = X.fillna(X.mean())                                     # notebooks/02_model_evaluation.ipynb:155
+    y = np.array([i % 2 for i in range(13)])                  # even / odd synthetic speakers = low / high F0 class
+    pipe = Pipeline([("scaler", StandardScaler()), ("select", SelectKBest(f_classif, k=10)), ("svm", SVC(kernel="linear"))])
+    scores = cross_val_score(pipe, X, y, cv=StratifiedKFold(3, shuffle=True, random_state=42))
+    assert scores.shape == (3,) and np.all(np.isfinite(scores))
+
+
+def test_size_independent_properties_on_a_larger_batch(ex):
+    """64 clips x 10 s: duplicates give identical rows, every column is populated, values stay in physical ranges."""
+    from robust_speech_analysis_framework_b200.synth import synth_batch
+    pcm, off = synth_batch(64, 10.0, unique=16, start_index=300)
+    out, st = ex.extract_host(pcm.numpy(), off.numpy())
+    assert not np.isnan(out).any() and not st.any()
+    for i in range(16, 64):
+        assert np.array_equal(out[i], out[i % 16])
+    assert np.all((out[:, 5] > 80) & (out[:, 5] < 260)) and np.all((out[:, 2] > 0.4) & (out[:, 2] <= 1.0))
