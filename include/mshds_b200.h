@@ -86,6 +86,14 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
 long long mshds_launch_count(const mshds_handle* h);
 
 /*
+ * Per-stage device timing (CUDA events on the handle's stream, accumulated over calls while enabled).  The report is
+ * text: one "stage<TAB>milliseconds<TAB>spans" line per stage in first-use order.  bench.py uses it for the roofline
+ * figure of the dominant kernel; the reference has no counterpart (it only has a tqdm bar, mshds_extractor.py:406).
+ */
+int mshds_profile_enable(mshds_handle* h, int on);
+int mshds_profile_report(mshds_handle* h, char* buf, size_t cap);
+
+/*
  * Stage-level read-back for parity tests: after mshds_extract, copy one named intermediate of clip `clip` of the LAST
  * processed chunk into a host buffer.  Names: "pitch_wide_f", "pitch_main_f", "pitch_main_s", "pitch_cpp_f",
  * "pitch_ltas_f", "pitch_cc_f", "pitch_sr_f", "hnr_r", "intensity_main", "intensity_sr", "pulses_cpp", "pulses_fmt",

@@ -26,7 +26,7 @@ OUT_ON_DEVICE = 2
 
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
-    "mshds_launch_count", "mshds_debug_fetch",
+    "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report",
 ]
 
 _lib = None
@@ -56,6 +56,8 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint]
     lib.mshds_launch_count.argtypes = [C.c_void_p]
     lib.mshds_launch_count.restype = C.c_longlong
+    lib.mshds_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    lib.mshds_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.mshds_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
@@ -112,6 +114,19 @@ class Extractor:
         n = len(offsets) - 1
         self._check(self._lib.mshds_extract(self._h, C.c_void_p(pcm_ptr), offsets.ctypes.data, n, int(sample_rate),
                                             C.c_void_p(out_ptr), C.c_void_p(status_ptr), PCM_ON_DEVICE | OUT_ON_DEVICE))
+
+    def profile(self, on: bool):
+        self._check(self._lib.mshds_profile_enable(self._h, int(on)))
+
+    def profile_report(self) -> dict:
+        """{stage: (milliseconds, spans)} accumulated since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.mshds_profile_report(self._h, buf, len(buf)))
+        rep = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.split("\t")
+            rep[name] = (float(ms), int(cnt))
+        return rep
 
     def debug_fetch(self, name: str, clip: int, dtype=np.float64, cap: int = 1 << 22) -> np.ndarray:
         buf = np.zeros(cap, dtype=dtype)

@@ -55,7 +55,53 @@ struct mshds_handle {
     bool arena_overflow = false;
     std::map<std::string, DebugEntry> debug;
     int last_n = 0;
+    // optional per-stage timing with CUDA events on the handle's stream
+    bool prof_on = false;
+    struct ProfSpan { std::string name; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_open;
+    std::vector<std::string> prof_order;
+    std::map<std::string, std::pair<double, long long>> prof_acc;    // name -> (ms, spans)
 };
+
+static void prof_begin(mshds_handle* h, const char* name) {
+    if (!h->prof_on) return;
+    mshds_handle::ProfSpan sp;
+    sp.name = name;
+    cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, h->stream);
+    h->prof_open.push_back(sp);
+}
+static void prof_end(mshds_handle* h) {
+    if (!h->prof_on || h->prof_open.empty()) return;
+    // close the most recent span that has not been closed yet
+    for (size_t i = h->prof_open.size(); i-- > 0;) {
+        if (h->prof_open[i].name.empty() || h->prof_open[i].name[0] != '\x01') {
+            cudaEventRecord(h->prof_open[i].b, h->stream);
+            h->prof_open[i].name.insert(h->prof_open[i].name.begin(), '\x01');
+            return;
+        }
+    }
+}
+static void prof_collect(mshds_handle* h) {
+    for (auto& sp : h->prof_open) {
+        std::string name = sp.name;
+        bool closed = !name.empty() && name[0] == '\x01';
+        if (closed) {
+            name.erase(name.begin());
+            float ms = 0.f;
+            if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+                if (!h->prof_acc.count(name)) h->prof_order.push_back(name);
+                auto& acc = h->prof_acc[name];
+                acc.first += ms; acc.second += 1;
+            }
+        }
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    h->prof_open.clear();
+}
+#define PB(name) prof_begin(h, name)
+#define PE() prof_end(h)
+
 
 // ------------------------------------------------------------------------------------------------ arena
 static void* arena_take(mshds_handle* h, size_t bytes) {
@@ -434,11 +480,11 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     }
     CK(cudaMemcpyAsync(d_fprefix, fprefix.data(), sizeof(int) * (nsegs + 1), cudaMemcpyHostToDevice, s));
     if (nsegs > 0 && totalFrames > 0) {
-        run_resample(h, plan, D, c.pcm, fs, fs10, 50, s);
+        PB("resample_segments_10k[fft+sinc50]"); run_resample(h, plan, D, c.pcm, fs, fs10, 50, s); PE();
         const double emphasis = exp(-2.0 * MSHDS_PI * 50.0 * (1.0 / fs10));
-        launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, s); h->launches += 1;
+        PB("cepstrogram_frames"); launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, s); h->launches += 1; PE();
         const int nTimeAvg = (int)floor(0.01 / dt);
-        launch_cpp_frames(d_cseg, d_fprefix, nsegs, d_cep, nqmax, nTimeAvg, 0.001, d_cppf, totalFrames, s); h->launches += 1;
+        PB("cpps_frames"); launch_cpp_frames(d_cseg, d_fprefix, nsegs, d_cep, nqmax, nTimeAvg, 0.001, d_cppf, totalFrames, s); h->launches += 1; PE();
     }
     launch_cpp_reduce(c, sg, d_seg_prefix, d_fprefix, d_cppf, s); h->launches += 1;
     CK(cudaStreamSynchronize(s));       // host vectors above must outlive the async copies
@@ -620,64 +666,64 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     const int fhint = (int)(fub5 > 0x3fffffff ? 0x3fffffff : fub5);
 
     // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
-    launch_clip_stats(c, maxlen, stat_scratch, s); h->launches += 3;
+    PB("clip_stats"); launch_clip_stats(c, maxlen, stat_scratch, s); h->launches += 3; PE();
 
     // ---- _speechrate (:11-125)
-    launch_intensity(c, isr, (int)(fub16 > 0x3fffffff ? 0x3fffffff : fub16), s); h->launches += 3;
-    launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1;
+    PB("intensity_sr"); launch_intensity(c, isr, (int)(fub16 > 0x3fffffff ? 0x3fffffff : fub16), s); h->launches += 3;
+    launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1; PE();
     launch_pitch_grid(c, srp, s); h->launches += 2;
-    launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1;
-    launch_pitch_viterbi(c, srp, s); h->launches += 1;
-    launch_speechrate(c, isr, isr_stats, srp, srs, s); h->launches += 1;
+    PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, srp, s); h->launches += 1; PE();
+    PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, s); h->launches += 1; PE();
 
     // ---- _pitch_values (:127-162): wide AC pass -> speaker class
     launch_pitch_grid(c, wide, s); h->launches += 2;
-    launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1;
-    launch_pitch_viterbi(c, wide, s); h->launches += 1;
+    PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, wide, s); h->launches += 1; PE();
     launch_pitch_class(c, wide, s); h->launches += 1;
 
     // ---- _extract_pitch (:164-183)
     launch_pitch_grid(c, mainp, s); h->launches += 2;
-    launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1;
-    launch_pitch_viterbi(c, mainp, s); h->launches += 1;
+    PB("pitch_ac_frames[main]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, mainp, s); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, s); h->launches += 1;
 
     // ---- _extract_intensity (:185-205)
-    launch_intensity(c, imain, fhint, s); h->launches += 3;
-    launch_contour_stats(c, imain, imain_stats, 0, s); h->launches += 1;
+    PB("intensity_main"); launch_intensity(c, imain, fhint, s); h->launches += 3;
+    launch_contour_stats(c, imain, imain_stats, 0, s); h->launches += 1; PE();
     launch_intensity_features(c, imain, imain_stats, s); h->launches += 1;
 
     // ---- _extract_harmonicity (:207-225)
     launch_pitch_grid(c, hnr, s); h->launches += 2;
-    launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1;
+    PB("pitch_cc_frames[hnr]"); launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
     launch_hnr_mean(c, hnr, s); h->launches += 1;
 
     // ---- _extract_Slope_Tilt (:227-251)
     launch_pitch_grid(c, ltp, s); h->launches += 2;
-    launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1;
-    launch_pitch_viterbi(c, ltp, s); h->launches += 1;
-    launch_pulses(c, ltp, pl_lt, s); h->launches += 5;
-    launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5;
+    PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, ltp, s); h->launches += 1; PE();
+    PB("pulses"); launch_pulses(c, ltp, pl_lt, s); h->launches += 5; PE();
+    PB("ltas"); launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5; PE();
 
     // ---- _measureFormants (:303-338)
-    run_resample(h, fplan, fdev, d_pcm, fs, fs10, 500, s);
-    launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3;
+    PB("resample_clip_10k[fft+sinc500]"); run_resample(h, fplan, fdev, d_pcm, fs, fs10, 500, s); PE();
+    PB("formant_burg_frames"); launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3; PE();
     launch_pitch_grid(c, ccp, s); h->launches += 2;
-    launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1;
-    launch_pitch_viterbi(c, ccp, s); h->launches += 1;
-    launch_pulses(c, ccp, pl_fm, s); h->launches += 5;
+    PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, ccp, s); h->launches += 1; PE();
+    PB("pulses"); launch_pulses(c, ccp, pl_fm, s); h->launches += 5; PE();
     launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
 
     // ---- _extract_CPP (:253-301)
     launch_pitch_grid(c, cpp_p, s); h->launches += 2;
-    launch_pitch_frames(c, cpp_p, h->tw, fhint, s); h->launches += 1;
-    launch_pitch_viterbi(c, cpp_p, s); h->launches += 1;
-    launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5;
+    PB("pitch_ac_frames[cpp vt=0.3]"); launch_pitch_frames(c, cpp_p, h->tw, fhint, s); h->launches += 1; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
+    PB("pulses"); launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5; PE();
     launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;
     if ((rc = run_cpp_stage(h, c, off_host, lens, sg, scap, seg_prefix, fs, s))) return rc;
 
     // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
-    launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4;
+    PB("spectrogram_moments"); launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4; PE();
 
     CK(cudaGetLastError());
 
@@ -842,8 +888,29 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             if (status) CK(cudaMemcpyAsync(status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         }
         CK(cudaStreamSynchronize(s));
+        prof_collect(h);
         c0 = c1;
     }
+    return MSHDS_OK;
+}
+
+int mshds_profile_enable(mshds_handle* h, int on) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->prof_on = on != 0;
+    if (on) { h->prof_acc.clear(); h->prof_order.clear(); }
+    return MSHDS_OK;
+}
+
+int mshds_profile_report(mshds_handle* h, char* buf, size_t cap) {
+    if (!h || !buf || cap == 0) return MSHDS_ERR_ARG;
+    std::string out;
+    for (auto& name : h->prof_order) {
+        auto& acc = h->prof_acc[name];
+        char line[256];
+        snprintf(line, sizeof line, "%s\t%.6f\t%lld\n", name.c_str(), acc.first, acc.second);
+        out += line;
+    }
+    snprintf(buf, cap, "%s", out.c_str());
     return MSHDS_OK;
 }
 
