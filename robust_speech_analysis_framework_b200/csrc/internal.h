@@ -17,6 +17,13 @@ struct PitchCfg {
     const double* windowR;     // [nsampFFT]       (AC) normalised window autocorrelation
 };
 
+// lags 0..len-1 of r are kept per frame for the refinement kernel; beyond maximumLag the FCC correlation is zero
+static inline __host__ __device__ int stored_lags(const PitchCfg& g) {
+    int len = g.brent_ixmax + 1;
+    if (g.method >= 2 && g.maximumLag + 73 < len) len = g.maximumLag + 73;
+    return len;
+}
+
 // One pitch analysis over the whole chunk (all clips).
 struct PitchPass {
     PitchCfg cfg[3];           // indexed by speaker class; identical entries for class-independent passes
@@ -31,6 +38,17 @@ struct PitchPass {
     double* cand_lf;           // log2(f) of voiced candidates, -1 for voiceless
     uint8_t* ncand;            // [frames]
     uint8_t* psi;              // [frames*16] Viterbi back-pointers
+    unsigned short* cand_imax; // [frames*MAXCAND] integer lag of the maximum behind each candidate
+    double* inten;             // [frames] relative local peak (Pitch_Frame intensity)
+    double* rbuf;              // [frames*rstride] correlation rows r[0..] kept for the refinement kernel
+    int rstride;
+    int* queue;                // refinement work list: frame*16 + candidate slot
+    int* qcount;
+    // harmonicity pass: every maximum of r is refined; items = frame<<32 | lag<<8 | sinc700 flag
+    unsigned long long* queue64;
+    unsigned long long* qcount64;
+    unsigned long long q64_cap;
+    unsigned long long* best_bits;   // [frames] bits of the largest refined strength (0 = none)
     // results
     double* sel_f;             // [frames] frequency of the chosen candidate (0 = voiceless)
     double* sel_s;             // [frames] strength of the chosen candidate / HNR: best r (NaN when voiceless)
@@ -84,6 +102,7 @@ void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s
 
 void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
+void launch_pitch_refine(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);   // + local scores
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
 void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones

@@ -114,29 +114,39 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ CPPS per frame
-// k-th smallest (1-based) of v[0..n) by rank counting; every thread returns the value
-__device__ double block_rank_select(const double* v, int n, int k, double* s_out) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double vi = v[i];
-        int rank = 0;
-        for (int j = 0; j < n; j++) {
-            double vj = v[j];
-            rank += (vj < vi) || (vj == vi && j < i);
+// ascending bitonic sort of v[0..npow2) in shared memory (npow2 a power of two, padded with +inf by the caller)
+__device__ void block_bitonic_sort(double* v, int npow2) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (npow2 >> 1); t += blockDim.x) {
+                int lo = ((t / j) * 2 * j) + (t % j);          // partner pairs (lo, lo + j)
+                int hi = lo + j;
+                bool up = ((lo & k) == 0);
+                double a = v[lo], b = v[hi];
+                if ((a > b) == up) { v[lo] = b; v[hi] = a; }
+            }
+            __syncthreads();
         }
-        if (rank == k - 1) *s_out = vi;
     }
-    __syncthreads();
-    double r = *s_out;
-    __syncthreads();
-    return r;
+}
+// NUMquantile on a sorted 0-based array
+__device__ __forceinline__ double quantile_sorted(const double* a0, int n, double factor) {
+    double place = factor * n + 0.5;
+    int left = (int)floor(place);
+    if (n < 1) return 0.0;
+    if (left < 1) return a0[0];
+    if (left >= n) return a0[n - 1];
+    if (a0[left] == a0[left - 1]) return a0[left - 1];
+    return a0[left - 1] + (place - left) * (a0[left] - a0[left - 1]);
 }
 
 __global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix, int nsegs,
                                                      const double* __restrict__ cep, int nqmax, int nTimeAvg, double qAvgWindow,
                                                      double peakLo, double peakHi, double qstartFit, double qendFit,
                                                      double* __restrict__ cpp_frame) {
-    __shared__ double col[520], y[520], work[520];
-    __shared__ double s_sel[2], s_red[32];
+    __shared__ double col[520], y[520], work[1024];
+    __shared__ double s_pv[8], s_px[8];
+    __shared__ int s_po[8];
     __shared__ int s_seg;
     __shared__ double s_peak[2];
     const int total = fprefix[nsegs];
@@ -200,68 +210,82 @@ __global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ s
                     double xa = (double)(imin - 1 + i) * dq, xb = (double)(imin - 1 + n2 + i) * dq;
                     work[i] = (yy[n2 + i] - yy[i]) / (xb - xa);
                 }
-                __syncthreads();
-                {   // NUMquantile (0.5)
-                    double place = 0.5 * numberOfPairs + 0.5;
-                    int left = (int)floor(place);
-                    if (left < 1) slope = block_rank_select(work, numberOfPairs, 1, &s_sel[0]);
-                    else if (left >= numberOfPairs) slope = block_rank_select(work, numberOfPairs, numberOfPairs, &s_sel[0]);
-                    else {
-                        double a0 = block_rank_select(work, numberOfPairs, left, &s_sel[0]);
-                        double a1 = block_rank_select(work, numberOfPairs, left + 1, &s_sel[1]);
-                        slope = (a1 == a0) ? a0 : a0 + (place - left) * (a1 - a0);
-                    }
+                {   // median of the pair slopes: sort (padded to a power of two with +inf) and apply NUMquantile (0.5)
+                    int np2 = 1;
+                    while (np2 < numberOfPairs) np2 <<= 1;
+                    for (int i = numberOfPairs + threadIdx.x; i < np2; i += blockDim.x) work[i] = CUDART_INF;
+                    __syncthreads();
+                    block_bitonic_sort(work, np2);
+                    slope = quantile_sorted(work, numberOfPairs, 0.5);
+                    __syncthreads();
                 }
-                for (int i = threadIdx.x; i < npts; i += blockDim.x) work[i] = yy[i] - slope * ((double)(imin - 1 + i) * dq);
-                __syncthreads();
                 {
-                    double place = 0.5 * npts + 0.5;
-                    int left = (int)floor(place);
-                    if (left < 1) intercept = block_rank_select(work, npts, 1, &s_sel[0]);
-                    else if (left >= npts) intercept = block_rank_select(work, npts, npts, &s_sel[0]);
-                    else {
-                        double a0 = block_rank_select(work, npts, left, &s_sel[0]);
-                        double a1 = block_rank_select(work, npts, left + 1, &s_sel[1]);
-                        intercept = (a1 == a0) ? a0 : a0 + (place - left) * (a1 - a0);
-                    }
+                    int np2 = 1;
+                    while (np2 < npts) np2 <<= 1;
+                    for (int i = threadIdx.x; i < np2; i += blockDim.x)
+                        work[i] = i < npts ? yy[i] - slope * ((double)(imin - 1 + i) * dq) : CUDART_INF;
+                    __syncthreads();
+                    block_bitonic_sort(work, np2);
+                    intercept = quantile_sorted(work, npts, 0.5);
+                    __syncthreads();
                 }
             }
             // PowerCepstrum_getMaximumAndQuefrency: Vector_getMaximumAndX (1/ceiling, 1/floor, parabolic)
-            if (threadIdx.x == 0) {
+            {
                 long long pmin, pmax;
-                double maximum, x;
                 const double xlo = peakLo, xhi = peakHi;
-                if (!get_window_samples(0.0, dq, nq, xlo, xhi, &pmin, &pmax)) {
-                    // no sample centre inside: linear values at the two ends
-                    double il = xlo / dq + 1.0, ir = xhi / dq + 1.0;
-                    int l0 = (int)floor(il), r0 = (int)floor(ir);
-                    double yl = (l0 >= 1 && l0 < nq) ? y[l0 - 1] + (il - l0) * (y[l0] - y[l0 - 1]) : y[nq - 1];
-                    double yr = (r0 >= 1 && r0 < nq) ? y[r0 - 1] + (ir - r0) * (y[r0] - y[r0 - 1]) : y[nq - 1];
-                    maximum = yl > yr ? yl : yr;
-                    x = yl == yr ? (xlo + xhi) / 2 : yl > yr ? xlo : xhi;
+                const bool have = get_window_samples(0.0, dq, nq, xlo, xhi, &pmin, &pmax) != 0;
+                if (!have) {
+                    if (threadIdx.x == 0) {
+                        // no sample centre inside: linear values at the two ends
+                        double il = xlo / dq + 1.0, ir = xhi / dq + 1.0;
+                        int l0 = (int)floor(il), r0 = (int)floor(ir);
+                        double yl = (l0 >= 1 && l0 < nq) ? y[l0 - 1] + (il - l0) * (y[l0] - y[l0 - 1]) : y[nq - 1];
+                        double yr = (r0 >= 1 && r0 < nq) ? y[r0 - 1] + (ir - r0) * (y[r0] - y[r0 - 1]) : y[nq - 1];
+                        s_peak[0] = yl > yr ? yl : yr;
+                        s_peak[1] = yl == yr ? (xlo + xhi) / 2 : yl > yr ? xlo : xhi;
+                    }
                 } else {
-                    maximum = y[pmin - 1];
-                    double xi = (double)pmin;
-                    if (y[pmax - 1] > maximum) { maximum = y[pmax - 1]; xi = (double)pmax; }
-                    long long lo = pmin == 1 ? 2 : pmin, hi = pmax == nq ? nq - 1 : pmax;
-                    for (long long i = lo; i <= hi; i++) {
+                    // candidates in Praat's visiting order: y[pmin], y[pmax], then the parabolically refined local maxima
+                    const long long lo = pmin == 1 ? 2 : pmin, hi = pmax == nq ? nq - 1 : pmax;
+                    double bv = -CUDART_INF, bx = 0.0;
+                    int bo = 0x7fffffff;
+                    for (long long i = lo + threadIdx.x; i <= hi; i += blockDim.x) {
                         double yi = y[i - 1], ym = y[i - 2], yp = y[i];
                         if (yi > ym && yi >= yp) {
                             double dy = 0.5 * (yp - ym), d2y = 2 * yi - ym - yp;
                             double loc = yi + 0.5 * dy * dy / d2y;
-                            if (loc > maximum) { maximum = loc; xi = (double)i + dy / d2y; }
+                            int ord = 2 + (int)(i - lo);
+                            if (loc > bv || (loc == bv && ord < bo)) { bv = loc; bx = (double)i + dy / d2y; bo = ord; }
                         }
                     }
-                    x = (xi - 1.0) * dq;
-                    if (x < xlo) x = xlo; else if (x > xhi) x = xhi;
+                    if (threadIdx.x == 0) {
+                        double e0 = y[pmin - 1], e1 = y[pmax - 1];
+                        double ev = e0, ex = (double)pmin;
+                        int eo = 0;
+                        if (e1 > ev) { ev = e1; ex = (double)pmax; eo = 1; }
+                        if (ev > bv || (ev == bv && eo < bo)) { bv = ev; bx = ex; bo = eo; }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(FULL_MASK, bv, o), ox = __shfl_xor_sync(FULL_MASK, bx, o);
+                        int oo = __shfl_xor_sync(FULL_MASK, bo, o);
+                        if (ov > bv || (ov == bv && oo < bo)) { bv = ov; bx = ox; bo = oo; }
+                    }
+                    if ((threadIdx.x & 31) == 0) { s_pv[threadIdx.x >> 5] = bv; s_px[threadIdx.x >> 5] = bx; s_po[threadIdx.x >> 5] = bo; }
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+                            if (s_pv[w] > bv || (s_pv[w] == bv && s_po[w] < bo)) { bv = s_pv[w]; bx = s_px[w]; bo = s_po[w]; }
+                        double x = (bx - 1.0) * dq;
+                        if (x < xlo) x = xlo; else if (x > xhi) x = xhi;
+                        s_peak[0] = bv; s_peak[1] = x;
+                    }
                 }
-                s_peak[0] = maximum; s_peak[1] = x;
             }
             __syncthreads();
             cppv = s_peak[0] - (slope * s_peak[1] + intercept);
         }
         if (threadIdx.x == 0) cpp_frame[f] = cppv;
-        (void)s_red;
     }
 }
 

@@ -46,17 +46,18 @@ struct CandScratch {
     double* pk_s;
     double* pk_key;
     int* pk_lag;
-    unsigned* masks;    // [ceil(maxlag/32)+8]
-    double* cf;         // [maxn+1] 1-based candidate slots
+    unsigned* masks;
+    double* cf;         // [MAXCAND+1] 1-based candidate slots
     double* cs;
     double* ckey;
     int* cimax;
     int* s_int;         // [4]: n maxima, ncand
 };
 
-// Sound_into_PitchFrame, second half: local maxima of r -> candidate slots -> sinc refinement.  Returns ncand (>=1).
-__device__ __forceinline__ int find_and_refine(const PitchCfg& g, double dx, double ceiling, const CandScratch& S, int B,
-                                               bool refine_all) {
+// Sound_into_PitchFrame, first pass: local maxima of r -> parabolic frequency + sinc(30) strength -> candidate slots
+// (Praat's <= maxn slots with its replace-the-weakest rule).  Returns ncand (>= 1, slot 1 = voiceless).
+// Harmonicity pass (maxn = 133 never fills, all path costs zero): only the list of maxima is built; returns their number.
+__device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double thr = 0.5 * g.vt;
     int upper = g.maximumLag < B ? g.maximumLag : B;      // i < maximumLag && i < brent_ixmax
@@ -89,9 +90,9 @@ __device__ __forceinline__ int find_and_refine(const PitchCfg& g, double dx, dou
     }
     __syncthreads();
     const int nmax = S.s_int[0];
+    if (hnr_mode) return nmax;          // harmonicity: every maximum is refined, the caller queues them
     const double* y1 = S.rs0 - 1;                           // 1-based view: y1[j] = r[j - B - 1]
     const int ny = 2 * B + 1;
-    // first pass: parabolic frequency, sinc(30) strength
     for (int m = warp; m < nmax; m += NWARP) {
         int i = S.pk_lag[m];
         double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
@@ -128,22 +129,7 @@ __device__ __forceinline__ int find_and_refine(const PitchCfg& g, double dx, dou
         S.s_int[1] = ncand;
     }
     __syncthreads();
-    const int ncand = S.s_int[1];
-    // second pass: maximise the sinc(70/700) interpolation with Brent.  A candidate whose refined lag cannot fall
-    // below fs/ceiling (lag <= imax+1) is voiceless for the path finder whatever its refined values: skip it.
-    for (int ci = 2 + warp; ci <= ncand; ci += NWARP) {
-        int imax = S.cimax[ci];
-        bool live = refine_all || (1.0 / dx / (double)(imax + 1) < ceiling);
-        if (!live) continue;
-        double xmid;
-        double ymid = improve_extremum_warp(y1, ny, imax + B + 1, S.cf[ci] > 0.3 / dx ? PEAK_SINC700 : PEAK_SINC70, &xmid,
-                                            true, lane);
-        xmid -= (double)(B + 1);
-        if (ymid > 1.0) ymid = 1.0 / ymid;
-        if (lane == 0) { S.cf[ci] = 1.0 / dx / xmid; S.cs[ci] = ymid; }
-    }
-    __syncthreads();
-    return ncand;
+    return S.s_int[1];
 }
 
 struct FrameInfo {
@@ -158,10 +144,13 @@ struct FrameInfo {
 struct FrameSmem {      // byte offsets into dynamic shared memory (computed on the host)
     int a, rs, pkf, pks, pkkey, cf, cs, ckey, red, part, pklag, cimax, masks, sint, fi, total;
     int part_stride;    // CC: doubles per partial-sum row (>= maximumLag)
+    int nchunk_max;
 };
 
+#define CC_TL 4         // lags per thread in the cross-correlation inner loop
+
 template <bool IS_CC>
-__global__ void __launch_bounds__(NTHR) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
+__global__ void __launch_bounds__(NTHR, 2) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)(smem + L.a);            // AC: packed FFT buffer; CC: xs[] doubles
     double* xs = (double*)(smem + L.a);
@@ -243,6 +232,8 @@ __global__ void __launch_bounds__(NTHR) k_pitch_frames(Clips c, PitchPass p, con
         const double intensity = localPeak > globalPeak ? 1.0 : localPeak / globalPeak;
         __syncthreads();
 
+        const int Ls = stored_lags(g);
+        double* rrow = p.rbuf + (size_t)f * p.rstride;
         if (!IS_CC) {
             fft_dif<-1>(a, g.M, tw);
             packed_power_to_inverse_input(a, g.M, g.logM, tw, IdentityF(), (double*)nullptr);
@@ -253,6 +244,7 @@ __global__ void __launch_bounds__(NTHR) k_pitch_frames(Clips c, PitchPass p, con
                 double v = i == 0 ? 1.0 : ac[i] / (ac0 * __ldg(g.windowR + i));
                 S.rs0[B + i] = v;
                 S.rs0[B - i] = v;
+                rrow[i] = v;
             }
         } else {
             // forward cross-correlation
@@ -262,96 +254,128 @@ __global__ void __launch_bounds__(NTHR) k_pitch_frames(Clips c, PitchPass p, con
             long long localSpan = g.maximumLag + W;
             if (localSpan > nx + 1 - startS) localSpan = nx + 1 - startS;
             const int localMaximumLag = (int)(localSpan - W);
-            // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan
-            for (int j = tid; j < (int)localSpan; j += NTHR) xs[j] = samp(pcm, startS - 1 + j) - localMean;
+            const int Lmax = localMaximumLag > 0 ? localMaximumLag : 0;
+            // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan; zero tail so the tiled loop may read ahead
+            const int xs_len = g.maximumLag + W + 8;
+            for (int j = tid; j < xs_len; j += NTHR) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
             for (int i = tid; i < 2 * B + 1; i += NTHR) S.rs0[i] = 0.0;
+            for (int i = tid; i < Ls; i += NTHR) rrow[i] = 0.0;
             __syncthreads();
-            // sumx2 over the first window
-            double sx = 0.0;
-            for (int j = tid; j < W; j += NTHR) sx = fma(xs[j], xs[j], sx);
-            const double sumx2 = block_sum(sx, red);
-            // products: work item = (lag, quarter of the window)
-            const int L = localMaximumLag > 0 ? localMaximumLag : 0;
-            const int q = (W + 3) / 4;
-            for (int wi = tid; wi < 4 * L; wi += NTHR) {
-                int lag = wi % L + 1, ch = wi / L;
-                int j0 = ch * q, j1 = j0 + q < W ? j0 + q : W;
-                double pr = 0.0, sy = 0.0;
+            // prefix sums of squares: sq[k] = sum_{j<k} xs[j]^2  (stored behind the partial products)
+            double* sq = part + (size_t)L.nchunk_max * PS;
+            {
+                const int total_len = (int)localSpan;
+                const int per = (total_len + NTHR - 1) / NTHR;
+                const int b0 = tid * per, b1 = b0 + per < total_len ? b0 + per : total_len;
+                double loc = 0.0;
+                for (int j = b0; j < b1; j++) loc = fma(xs[j], xs[j], loc);
+                // exclusive scan of the per-thread sums
+                const int lane = tid & 31, w = tid >> 5;
+                double incl = loc;
+                for (int o = 1; o < 32; o <<= 1) { double y = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) red[w] = incl;
+                __syncthreads();
+                double woff = 0.0;
+                for (int k = 0; k < w; k++) woff += red[k];
+                double run = woff + incl - loc;
+                for (int j = b0; j < b1; j++) { sq[j] = run; run = fma(xs[j], xs[j], run); }
+                if (b1 == total_len && b0 < total_len) sq[total_len] = run;
+                if (total_len == 0 && tid == 0) sq[0] = 0.0;
+                __syncthreads();
+            }
+            const double sumx2 = sq[W] - sq[0];
+            // products: work item = (group of CC_TL lags, chunk of the window)
+            const int ngroups = (Lmax + CC_TL - 1) / CC_TL;
+            int nchunk = ngroups > 0 ? NTHR / ngroups : 1;
+            if (nchunk < 1) nchunk = 1;
+            if (nchunk > L.nchunk_max) nchunk = L.nchunk_max;
+            const int q = (W + nchunk - 1) / nchunk;
+            for (int wi = tid; wi < ngroups * nchunk; wi += NTHR) {
+                const int grp = wi % ngroups, ch = wi / ngroups;
+                const int lag0 = 1 + CC_TL * grp;
+                const int j0 = ch * q, j1 = j0 + q < W ? j0 + q : W;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 const double* xa = xs + j0;
-                const double* xb = xs + j0 + lag;
+                const double* xb = xs + j0 + lag0;
+                double y0 = xb[0], y1v = xb[1], y2 = xb[2];
                 for (int j = 0; j < j1 - j0; j++) {
-                    double yb = xb[j];
-                    pr = fma(xa[j], yb, pr);
-                    sy = fma(yb, yb, sy);
+                    const double xv = xa[j];
+                    const double y3 = xb[j + 3];
+                    a0 = fma(xv, y0, a0); a1 = fma(xv, y1v, a1); a2 = fma(xv, y2, a2); a3 = fma(xv, y3, a3);
+                    y0 = y1v; y1v = y2; y2 = y3;
                 }
-                part[ch * PS + (lag - 1)] = pr;
-                part[(4 + ch) * PS + (lag - 1)] = sy;
+                double* pr = part + (size_t)ch * PS + (lag0 - 1);
+                pr[0] = a0; pr[1] = a1; pr[2] = a2; pr[3] = a3;
             }
             __syncthreads();
-            for (int lag = 1 + tid; lag <= L; lag += NTHR) {
-                double pr = (part[lag - 1] + part[PS + lag - 1]) + (part[2 * PS + lag - 1] + part[3 * PS + lag - 1]);
-                double sy = (part[4 * PS + lag - 1] + part[5 * PS + lag - 1]) + (part[6 * PS + lag - 1] + part[7 * PS + lag - 1]);
+            for (int lag = 1 + tid; lag <= Lmax; lag += NTHR) {
+                double pr = 0.0;
+                for (int ch = 0; ch < nchunk; ch++) pr += part[(size_t)ch * PS + lag - 1];
+                double sy = sq[lag + W] - sq[lag];
                 double v = pr / sqrt(sumx2 * sy);
                 S.rs0[B + lag] = v;
                 S.rs0[B - lag] = v;
+                if (lag < Ls) rrow[lag] = v;
             }
-            if (tid == 0) S.rs0[B] = 1.0;
+            if (tid == 0) { S.rs0[B] = 1.0; rrow[0] = 1.0; }
         }
         __syncthreads();
 
+        if (p.hnr_mode) {
+            // Sound_to_Harmonicity_cc: the frame value is the best refined strength over ALL maxima of r; queue every one
+            int nmax = 0;
+            if (localPeak != 0.0) nmax = find_candidates(g, dx, S, B, 1);
+            const double* r = S.rs0 + B;
+            for (int m = tid; m < nmax; m += NTHR) {
+                const int i = S.pk_lag[m];
+                double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
+                double freq = 1.0 / dx / (i + dr / d2r);
+                unsigned long long item = ((unsigned long long)(unsigned)f << 32) | ((unsigned long long)i << 8) |
+                                          (freq > 0.3 / dx ? 1ull : 0ull);
+                unsigned long long slot = atomicAdd(p.qcount64, 1ull);
+                if (slot < p.q64_cap) p.queue64[slot] = item;
+                else atomicOr(&c.status[clip], ST_HNR);              // cannot happen: capacity is the worst case
+            }
+            if (tid == 0) { p.inten[f] = intensity; p.best_bits[f] = 0ull; }
+            continue;
+        }
         int ncand = 1;
         if (localPeak != 0.0) {
-            ncand = find_and_refine(g, dx, g.ceiling, S, B, p.hnr_mode != 0);
+            ncand = find_candidates(g, dx, S, B, 0);
         } else if (tid == 0) {
-            S.cf[1] = 0.0; S.cs[1] = 0.0;
+            S.cf[1] = 0.0; S.cs[1] = 0.0; S.cimax[1] = 0;
         }
         __syncthreads();
 
-        // Pitch_pathFinder local scores
-        double unvoicedStrength = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
-        unvoicedStrength = g.vt + (unvoicedStrength > 0 ? unvoicedStrength : 0);
-        if (p.hnr_mode) {
-            // all path costs are zero: the path is the per-frame first maximum of the local scores
-            if (tid == 0) {
-                double best = unvoicedStrength, bestS = DEVNAN, bestF = 0.0;
-                for (int ci = 2; ci <= ncand; ci++) {
-                    double fr = S.cf[ci];
-                    bool voiceless = !(fr > 0.0 && fr < g.ceiling);
-                    double sc = voiceless ? unvoicedStrength : S.cs[ci];
-                    if (sc > best) { best = sc; bestS = voiceless ? DEVNAN : S.cs[ci]; bestF = voiceless ? 0.0 : fr; }
-                }
-                p.sel_f[f] = bestF;
-                p.sel_s[f] = bestS;
+        // candidates leave the SM; the ones that can matter are queued for the refinement kernel
+        if (tid < MAXCAND) {
+            const int ci = tid + 1;
+            double fr = 0.0, st = 0.0;
+            int im = 0;
+            if (ci <= ncand) { fr = S.cf[ci]; st = S.cs[ci]; im = S.cimax[ci]; }
+            const size_t o2 = (size_t)f * MAXCAND + tid;
+            p.cand_f[o2] = fr; p.cand_s[o2] = st; p.cand_imax[o2] = (unsigned short)im;
+            // A candidate whose refined lag cannot fall below fs/ceiling (refined lag <= imax+1) stays voiceless for the
+            // path finder whatever its refined values: it is never refined.
+            bool live = ci >= 2 && ci <= ncand && (1.0 / dx / (double)(im + 1) < g.ceiling);
+            if (live) {
+                int slot = atomicAdd(p.qcount, 1);
+                p.queue[slot] = f * 16 + tid;
             }
-        } else {
-            if (tid < MAXCAND) {
-                int ci = tid + 1;
-                double fr = 0.0, st = 0.0, sc = -1e300, lf = -1.0;
-                if (ci <= ncand) {
-                    fr = S.cf[ci]; st = S.cs[ci];
-                    bool voiceless = !(fr > 0.0 && fr < g.ceiling);
-                    sc = voiceless ? unvoicedStrength : st - g.octave_cost * log2(g.ceiling / fr);
-                    lf = voiceless ? -1.0 : log2(fr);
-                }
-                size_t o2 = (size_t)f * MAXCAND + tid;
-                p.cand_f[o2] = fr; p.cand_s[o2] = st; p.cand_score[o2] = sc; p.cand_lf[o2] = lf;
-            }
-            if (tid == 0) p.ncand[f] = (uint8_t)ncand;
         }
+        if (tid == 0) { p.ncand[f] = (uint8_t)ncand; p.inten[f] = intensity; }
     }
 }
 
 static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
-    int ab = 0, rs = 0, mn = 0, ml = 0;
+    int ab = 0, rs = 0, ml = 0;
     for (int k = 0; k < 3; k++) {
         const PitchCfg& g = p.cfg[k];
-        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 8) : (int)sizeof(double2) * g.M;
+        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 16) : (int)sizeof(double2) * g.M;
         if (need_a > ab) ab = need_a;
         if (2 * g.brent_ixmax + 1 > rs) rs = 2 * g.brent_ixmax + 1;
-        if (g.maxn > mn) mn = g.maxn;
         if (g.maximumLag > ml) ml = g.maximumLag;
     }
-    if (mn < MAXCAND) mn = MAXCAND;
     FrameSmem L;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o = (o + bytes + 15) & ~15; return r; };
@@ -360,14 +384,16 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     L.pkf = take((int)sizeof(double) * MAXPK);
     L.pks = take((int)sizeof(double) * MAXPK);
     L.pkkey = take((int)sizeof(double) * MAXPK);
-    L.cf = take((int)sizeof(double) * (mn + 1));
-    L.cs = take((int)sizeof(double) * (mn + 1));
-    L.ckey = take((int)sizeof(double) * (mn + 1));
+    L.cf = take((int)sizeof(double) * (MAXCAND + 1));
+    L.cs = take((int)sizeof(double) * (MAXCAND + 1));
+    L.ckey = take((int)sizeof(double) * (MAXCAND + 1));
     L.red = take((int)sizeof(double) * 32);
-    L.part_stride = (ml + 8) & ~7;
-    L.part = take(is_cc ? (int)sizeof(double) * 8 * L.part_stride : 16);
+    L.part_stride = (ml + 8 + 7) & ~7;
+    L.nchunk_max = 4;
+    // CC: nchunk_max rows of partial products + the prefix sums of squares (window + maximumLag + 1 entries)
+    L.part = take(is_cc ? (int)sizeof(double) * (L.nchunk_max * L.part_stride + ab / (int)sizeof(double) + 8) : 16);
     L.pklag = take((int)sizeof(int) * MAXPK);
-    L.cimax = take((int)sizeof(int) * (mn + 1));
+    L.cimax = take((int)sizeof(int) * (MAXCAND + 1));
     L.masks = take((int)sizeof(unsigned) * 64);
     L.sint = take((int)sizeof(int) * 4);
     L.fi = take(64);
@@ -383,18 +409,122 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     int blocks_per_sm = (int)(220 * 1024 / (smem + 1024));
-    if (blocks_per_sm > 8) blocks_per_sm = 8;
+    if (blocks_per_sm > 6) blocks_per_sm = 6;
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = nsm * blocks_per_sm;
     if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
     if (grid < 1) grid = 1;
+    cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
+    if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
     if (is_cc) {
         cudaFuncSetAttribute(k_pitch_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pitch_frames<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         k_pitch_frames<true><<<grid, NTHR, smem, s>>>(c, p, tw, L);
     } else {
         cudaFuncSetAttribute(k_pitch_frames<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_pitch_frames<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         k_pitch_frames<false><<<grid, NTHR, smem, s>>>(c, p, tw, L);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ refinement
+// Sound_into_PitchFrame, second pass: NUMimproveMaximum with sinc(70/700) + Brent on the stored correlation row.  A flat,
+// perfectly balanced work list: one warp per queued (frame, candidate).
+__global__ void __launch_bounds__(256, 3) k_pitch_refine(Clips c, PitchPass p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    const int total = *p.qcount;
+    const double dx = c.dx;
+    for (int q = gw; q < total; q += nw) {
+        const int item = p.queue[q];
+        const int f = item >> 4, slot = item & 15;
+        const int clip = find_segment(p.fstart, c.n, f);
+        const PitchCfg& g = p.cfg[c.cls[clip]];
+        const int B = g.brent_ixmax;
+        SymRowY y;
+        y.row = p.rbuf + (size_t)f * p.rstride;
+        y.centre = B + 1;
+        y.len = stored_lags(g);
+        const size_t o2 = (size_t)f * MAXCAND + slot;
+        const int imax = p.cand_imax[o2];
+        const double f0 = p.cand_f[o2];
+        double xmid;
+        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, f0 > 0.3 / dx ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane);
+        xmid -= (double)(B + 1);
+        if (ymid > 1.0) ymid = 1.0 / ymid;
+        if (lane == 0) { p.cand_f[o2] = 1.0 / dx / xmid; p.cand_s[o2] = ymid; }
+    }
+}
+
+// Harmonicity variant: every maximum of every frame is an item (frame, lag, depth flag); the frame keeps the largest
+// refined strength among candidates that stay below the Nyquist "ceiling" (atomicMax on the bits of a positive double).
+__global__ void __launch_bounds__(256, 3) k_hnr_refine(Clips c, PitchPass p) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    unsigned long long total = *p.qcount64;
+    if (total > p.q64_cap) total = p.q64_cap;
+    const double dx = c.dx;
+    for (long long q = gw; q < (long long)total; q += nw) {
+        const unsigned long long item = p.queue64[q];
+        const int f = (int)(item >> 32), imax = (int)((item >> 8) & 0xffffff);
+        const bool deep = (item & 1ull) != 0;
+        const int clip = find_segment(p.fstart, c.n, f);
+        const PitchCfg& g = p.cfg[c.cls[clip]];
+        const int B = g.brent_ixmax;
+        SymRowY y;
+        y.row = p.rbuf + (size_t)f * p.rstride;
+        y.centre = B + 1;
+        y.len = stored_lags(g);
+        double xmid;
+        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, deep ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane);
+        xmid -= (double)(B + 1);
+        if (ymid > 1.0) ymid = 1.0 / ymid;
+        const double fr = 1.0 / dx / xmid;
+        if (lane == 0 && fr > 0.0 && fr < g.ceiling && ymid > 0.0)
+            atomicMax(p.best_bits + f, (unsigned long long)__double_as_longlong(ymid));
+    }
+}
+
+// Pitch_pathFinder local scores (Viterbi passes) / per-frame winner (harmonicity pass)
+__global__ void k_pitch_score(Clips c, PitchPass p) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= p.fstart[c.n]) return;
+    const int clip = find_segment(p.fstart, c.n, f);
+    const PitchCfg& g = p.cfg[c.cls[clip]];
+    const double intensity = p.inten[f];
+    double unvoicedStrength = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
+    unvoicedStrength = g.vt + (unvoicedStrength > 0 ? unvoicedStrength : 0);
+    if (p.hnr_mode) {
+        // all path costs are zero: the path is the per-frame first maximum of the local scores (voiceless comes first)
+        const unsigned long long bits = p.best_bits[f];
+        const double st = __longlong_as_double((long long)bits);
+        const bool voiced = bits != 0ull && st > unvoicedStrength;
+        p.sel_f[f] = voiced ? 1.0 : 0.0;          // only the voiced flag of the winner is used downstream
+        p.sel_s[f] = voiced ? st : DEVNAN;
+        return;
+    }
+    const int ncand = p.ncand[f];
+    for (int ci = 0; ci < MAXCAND; ci++) {
+        double sc = -1e300, lf = -1.0;
+        if (ci < ncand) {
+            double fr = p.cand_f[(size_t)f * MAXCAND + ci], st = p.cand_s[(size_t)f * MAXCAND + ci];
+            bool voiceless = !(fr > 0.0 && fr < g.ceiling);
+            sc = voiceless ? unvoicedStrength : st - g.octave_cost * log2(g.ceiling / fr);
+            lf = voiceless ? -1.0 : log2(fr);
+        }
+        p.cand_score[(size_t)f * MAXCAND + ci] = sc;
+        p.cand_lf[(size_t)f * MAXCAND + ci] = lf;
+    }
+}
+
+void launch_pitch_refine(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s) {
+    if (p.hnr_mode) k_hnr_refine<<<148 * 3, 256, 0, s>>>(c, p);
+    else k_pitch_refine<<<148 * 3, 256, 0, s>>>(c, p);
+    int blocks = (max_frames_hint + 127) / 128;
+    if (blocks < 1) blocks = 1;
+    k_pitch_score<<<blocks, 128, 0, s>>>(c, p);
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include <utility>
+#include <algorithm>
 
 #define CK(call)                                                                                      \
     do {                                                                                              \
@@ -277,7 +278,7 @@ static long long frames_upper_bound(const std::vector<long long>& lens, double d
     return t;
 }
 
-struct CandScratchBuf { double *f, *s, *score, *lf; uint8_t *ncand, *psi; long long cap; };
+struct CandScratchBuf { double *f, *s, *score, *lf, *inten, *rbuf; uint8_t *ncand, *psi; unsigned short* imax; int *queue, *qcount; long long cap; };
 
 static void alloc_pitch_pass(mshds_handle* h, PitchPass* p, int n, long long fub, const CandScratchBuf& cs) {
     p->nF = take<int>(h, n);
@@ -286,6 +287,15 @@ static void alloc_pitch_pass(mshds_handle* h, PitchPass* p, int n, long long fub
     p->sel_f = take<double>(h, fub);
     p->sel_s = take<double>(h, fub);
     p->cand_f = cs.f; p->cand_s = cs.s; p->cand_score = cs.score; p->cand_lf = cs.lf; p->ncand = cs.ncand; p->psi = cs.psi;
+    p->cand_imax = cs.imax; p->inten = cs.inten; p->rbuf = cs.rbuf; p->queue = cs.queue; p->qcount = cs.qcount;
+    int rs = 0;
+    for (int k = 0; k < 3; k++) { int l = stored_lags(p->cfg[k]); if (l > rs) rs = l; }
+    p->rstride = (rs + 7) & ~7;
+}
+static long long rbuf_need(const PitchPass& p, long long fub) {
+    int rs = 0;
+    for (int k = 0; k < 3; k++) { int l = stored_lags(p.cfg[k]); if (l > rs) rs = l; }
+    return fub * (long long)((rs + 7) & ~7);
 }
 
 static void reg_debug(mshds_handle* h, const char* name, const void* base, const int* start, const int* count, int fixed,
@@ -543,11 +553,25 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     cs.f = take<double>(h, fub5 * MAXCAND); cs.s = take<double>(h, fub5 * MAXCAND);
     cs.score = take<double>(h, fub5 * MAXCAND); cs.lf = take<double>(h, fub5 * MAXCAND);
     cs.ncand = take<uint8_t>(h, fub5); cs.psi = take<uint8_t>(h, fub5 * 16);
+    cs.imax = take<unsigned short>(h, fub5 * MAXCAND); cs.inten = take<double>(h, fub5);
+    cs.queue = take<int>(h, fub5 * (MAXCAND - 1)); cs.qcount = take<int>(h, 1);
+    const long long fub20 = frames_upper_bound(lens, dx, 0.02);
+    const long long fub75 = frames_upper_bound(lens, dx, 0.75 / 100.0);
+    {   // correlation rows kept between the frame kernel and the refinement kernel (largest pass decides)
+        long long need = rbuf_need(wide, fub5);
+        need = std::max(need, rbuf_need(mainp, fub5)); need = std::max(need, rbuf_need(hnr, fub5));
+        need = std::max(need, rbuf_need(srp, fub20)); need = std::max(need, rbuf_need(ltp, fub75));
+        need = std::max(need, rbuf_need(ccp, fub5)); need = std::max(need, rbuf_need(cpp_p, fub5));
+        cs.rbuf = take<double>(h, need);
+    }
     alloc_pitch_pass(h, &wide, n, fub5, cs);
     alloc_pitch_pass(h, &mainp, n, fub5, cs);
     alloc_pitch_pass(h, &hnr, n, fub5, cs);
-    const long long fub20 = frames_upper_bound(lens, dx, 0.02);
-    const long long fub75 = frames_upper_bound(lens, dx, 0.75 / 100.0);
+    // harmonicity: worst case one maximum every other lag (maximumLag / 2 per frame)
+    hnr.q64_cap = (unsigned long long)fub5 * 136ull;
+    hnr.queue64 = take<unsigned long long>(h, hnr.q64_cap);
+    hnr.qcount64 = take<unsigned long long>(h, 1);
+    hnr.best_bits = take<unsigned long long>(h, fub5);
     alloc_pitch_pass(h, &srp, n, fub20, cs);
     alloc_pitch_pass(h, &ltp, n, fub75, cs);
     alloc_pitch_pass(h, &ccp, n, fub5, cs);
@@ -673,18 +697,21 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1; PE();
     launch_pitch_grid(c, srp, s); h->launches += 2;
     PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, srp, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, srp, s); h->launches += 1; PE();
     PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, s); h->launches += 1; PE();
 
     // ---- _pitch_values (:127-162): wide AC pass -> speaker class
     launch_pitch_grid(c, wide, s); h->launches += 2;
     PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, wide, fhint, s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, wide, s); h->launches += 1; PE();
     launch_pitch_class(c, wide, s); h->launches += 1;
 
     // ---- _extract_pitch (:164-183)
     launch_pitch_grid(c, mainp, s); h->launches += 2;
     PB("pitch_ac_frames[main]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, mainp, fhint, s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, mainp, s); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, s); h->launches += 1;
 
@@ -696,11 +723,13 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     // ---- _extract_harmonicity (:207-225)
     launch_pitch_grid(c, hnr, s); h->launches += 2;
     PB("pitch_cc_frames[hnr]"); launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, hnr, fhint, s); h->launches += 2; PE();
     launch_hnr_mean(c, hnr, s); h->launches += 1;
 
     // ---- _extract_Slope_Tilt (:227-251)
     launch_pitch_grid(c, ltp, s); h->launches += 2;
     PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, ltp, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, ltp, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, ltp, pl_lt, s); h->launches += 5; PE();
     PB("ltas"); launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5; PE();
@@ -710,6 +739,7 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     PB("formant_burg_frames"); launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3; PE();
     launch_pitch_grid(c, ccp, s); h->launches += 2;
     PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, ccp, fhint, s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, ccp, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, ccp, pl_fm, s); h->launches += 5; PE();
     launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
@@ -717,6 +747,7 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     // ---- _extract_CPP (:253-301)
     launch_pitch_grid(c, cpp_p, s); h->launches += 2;
     PB("pitch_ac_frames[cpp vt=0.3]"); launch_pitch_frames(c, cpp_p, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_refine+score"); launch_pitch_refine(c, cpp_p, fhint, s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5; PE();
     launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;

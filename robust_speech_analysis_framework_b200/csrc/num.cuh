@@ -7,50 +7,76 @@
 #pragma once
 #include "common.cuh"
 
-// y is 1-based: y[1..n] valid.  All 32 lanes must call with identical arguments; all lanes get the result.
-__device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane) {
+// 1-based accessors: a plain pointer, or a symmetric correlation row stored for lags 0..len-1 only
+struct PtrY {
+    const double* y;
+    __device__ __forceinline__ double operator()(int j) const { return y[j]; }
+};
+struct SymRowY {            // y(j) = r[|j - centre|], zero beyond the stored lags
+    const double* __restrict__ row;
+    int centre, len;
+    __device__ __forceinline__ double operator()(int j) const {
+        int l = j - centre;
+        l = l < 0 ? -l : l;
+        return l < len ? row[l] : 0.0;
+    }
+};
+
+// y is 1-based: y(1..n) valid.  All 32 lanes must call with identical arguments; all lanes get the result.
+template <class Y>
+__device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x, int maxDepth, int lane) {
     int midleft = (int)floor(x), midright = midleft + 1;
     if (n < 1) return DEVNAN;
-    if (x > n) return y[n];
-    if (x < 1) return y[1];
-    if (x == midleft) return y[midleft];
+    if (x > n) return y(n);
+    if (x < 1) return y(1);
+    if (x == midleft) return y(midleft);
     if (maxDepth > midright - 1) maxDepth = midright - 1;
     if (maxDepth > n - midleft) maxDepth = n - midleft;
-    if (maxDepth <= 0) return y[(int)floor(x + 0.5)];
-    if (maxDepth == 1) return y[midleft] + (x - midleft) * (y[midright] - y[midleft]);
+    if (maxDepth <= 0) return y((int)floor(x + 0.5));
+    if (maxDepth == 1) return y(midleft) + (x - midleft) * (y(midright) - y(midleft));
     if (maxDepth == 2) {
-        double yl = y[midleft], yr = y[midright];
-        double dyl = 0.5 * (yr - y[midleft - 1]), dyr = 0.5 * (y[midright + 1] - yl);
+        double yl = y(midleft), yr = y(midright);
+        double dyl = 0.5 * (yr - y(midleft - 1)), dyr = 0.5 * (y(midright + 1) - yl);
         double fil = x - midleft, fir = midright - x;
         return yl * fir + yr * fil - fil * fir * (0.5 * (dyr - dyl) + (fil - 0.5) * (dyl + dyr - 2 * (yr - yl)));
     }
     // left side: taps ix = midleft - k, k = 0..maxDepth-1; a_k = pi*(x-midleft) + k*pi; aa_k = a_k / (x-left+1)
     // right side: ix = midright + k;  a_k = pi*(midright-x) + k*pi; aa_k = a_k / (right-x+1)
     double fl = x - midleft, fr = midright - x;
-    double hsl = 0.5 * sinpi(fl), hsr = 0.5 * sinpi(fr);
+    // halfsina / a * (1 + cos(aa)) with a = pi*(f + k): the constant factor 0.5*sin(pi f)/pi is hoisted and the
+    // per-tap division becomes an IEEE reciprocal (one rounding more than Praat's expression: ~1 ulp per tap)
+    double hsl = 0.5 * sinpi(fl) * (1.0 / MSHDS_PI), hsr = 0.5 * sinpi(fr) * (1.0 / MSHDS_PI);
     double invl = 1.0 / (fl + maxDepth), invr = 1.0 / (fr + maxDepth);     // x-left+1 = fl + depth ; right-x+1 = fr + depth
-    double acc = 0.0;
+    double accl = 0.0, accr = 0.0;
     for (int k = lane; k < maxDepth; k += 32) {
-        double sgn = (k & 1) ? -1.0 : 1.0;
         double al = fl + k, ar = fr + k;                                    // in units of pi
-        double dl = sgn * hsl / (MSHDS_PI * al) * (1.0 + cospi(al * invl));
-        double dr = sgn * hsr / (MSHDS_PI * ar) * (1.0 + cospi(ar * invr));
-        acc += y[midleft - k] * dl + y[midright + k] * dr;
+        double dl = __drcp_rn(al) * (1.0 + cospi(al * invl));
+        double dr = __drcp_rn(ar) * (1.0 + cospi(ar * invr));
+        double yl = y(midleft - k), yr = y(midright + k);
+        if (k & 1) { yl = -yl; yr = -yr; }
+        accl = fma(yl, dl, accl);
+        accr = fma(yr, dr, accr);
     }
-    return warp_sum(acc);
+    return warp_sum(accl * hsl + accr * hsr);
+}
+
+__device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane) {
+    PtrY a{y};
+    return sinc_interp_warp_t(a, n, x, maxDepth, lane);
 }
 
 // NUMminimize_brent specialised to f(x) = -/+ sinc_interp(y, x, depth); returns x of the extremum, *fx its value
 // (already sign-corrected: the interpolated y at the extremum).
-__device__ __forceinline__ double brent_sinc_warp(const double* y, int n, double a, double b, int depth, bool isMaximum,
-                                                  double* fx_out, int lane) {
+template <class Y>
+__device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a, double b, int depth, bool isMaximum,
+                                                    double* fx_out, int lane) {
     const double golden = 1.0 - 0.6180339887498948482045868343656381177203;
     const double sqrt_epsilon = 1.4901161193847656e-08;   // sqrt(DBL_EPSILON)
     const double tol = 1e-10;
     const double sg = isMaximum ? -1.0 : 1.0;
     double x, v, fv, w, fw, fx;
     v = a + golden * (b - a);
-    fv = sg * sinc_interp_warp(y, n, v, depth, lane);
+    fv = sg * sinc_interp_warp_t(y, n, v, depth, lane);
     x = v; w = v;
     fx = fv; fw = fv;
     for (int iter = 1; iter <= 60; iter++) {
@@ -73,7 +99,7 @@ __device__ __forceinline__ double brent_sinc_warp(const double* y, int n, double
         if (fabs(new_step) < tol_act) new_step = new_step > 0.0 ? tol_act : -tol_act;
         {
             double t = x + new_step;
-            double ft = sg * sinc_interp_warp(y, n, t, depth, lane);
+            double ft = sg * sinc_interp_warp_t(y, n, t, depth, lane);
             if (ft <= fx) {
                 if (t < x) b = x; else a = x;
                 v = w; w = x; x = t;
@@ -100,21 +126,27 @@ __device__ __forceinline__ double brent_sinc_warp(const double* y, int n, double
 #define PEAK_SINC700 4
 
 // NUMimproveExtremum (warp-cooperative for the sinc modes). y 1-based.
-__device__ __forceinline__ double improve_extremum_warp(const double* y, int n, int ixmid, int interpolation,
-                                                        double* ixmid_real, bool isMaximum, int lane) {
-    if (ixmid <= 1) { *ixmid_real = 1; return y[1]; }
-    if (ixmid >= n) { *ixmid_real = n; return y[n]; }
-    if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y[ixmid]; }
+template <class Y>
+__device__ __forceinline__ double improve_extremum_warp_t(const Y& y, int n, int ixmid, int interpolation,
+                                                          double* ixmid_real, bool isMaximum, int lane) {
+    if (ixmid <= 1) { *ixmid_real = 1; return y(1); }
+    if (ixmid >= n) { *ixmid_real = n; return y(n); }
+    if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y(ixmid); }
     if (interpolation == PEAK_PARABOLIC) {
-        double dy = 0.5 * (y[ixmid + 1] - y[ixmid - 1]);
-        double d2y = 2 * y[ixmid] - y[ixmid - 1] - y[ixmid + 1];
+        double dy = 0.5 * (y(ixmid + 1) - y(ixmid - 1));
+        double d2y = 2 * y(ixmid) - y(ixmid - 1) - y(ixmid + 1);
         *ixmid_real = ixmid + dy / d2y;
-        return y[ixmid] + 0.5 * dy * dy / d2y;
+        return y(ixmid) + 0.5 * dy * dy / d2y;
     }
     double fx;
-    *ixmid_real = brent_sinc_warp(y, n, (double)(ixmid - 1), (double)(ixmid + 1), interpolation == PEAK_SINC70 ? 70 : 700,
-                                  isMaximum, &fx, lane);
+    *ixmid_real = brent_sinc_warp_t(y, n, (double)(ixmid - 1), (double)(ixmid + 1), interpolation == PEAK_SINC70 ? 70 : 700,
+                                    isMaximum, &fx, lane);
     return fx;
+}
+__device__ __forceinline__ double improve_extremum_warp(const double* y, int n, int ixmid, int interpolation,
+                                                        double* ixmid_real, bool isMaximum, int lane) {
+    PtrY a{y};
+    return improve_extremum_warp_t(a, n, ixmid, interpolation, ixmid_real, isMaximum, lane);
 }
 
 // single-thread parabolic / none variant
