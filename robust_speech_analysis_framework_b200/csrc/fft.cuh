@@ -56,33 +56,81 @@ __device__ __forceinline__ void fft_dit_cols(double2* a, int n, int cols, const 
     }
 }
 
-// Single-column versions (the per-frame transforms).
+// Single-column versions (the per-frame transforms).  Two radix-2 stages are fused per pass (4 points in registers, the
+// second pair's first-stage twiddle is the first one rotated by a quarter turn), which halves the shared-memory round
+// trips, the barriers and the twiddle loads while keeping the plain radix-2 bit-reversed ordering.
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+template <int SIGN>
+__device__ __forceinline__ double2 quarter_turn(double2 a) {      // a * exp(SIGN * i * pi / 2)
+    return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
 template <int SIGN>
 __device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __restrict__ tw) {
-    for (int half = n >> 1; half >= 1; half >>= 1) {
+    int half = n >> 1;
+    while (half >= 2) {
+        const int q = half >> 1;
+        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
+            const int pos = t & (q - 1);
+            const int i0 = (t / q) * 2 * half + pos;
+            double2 x0 = a[i0], x1 = a[i0 + q], x2 = a[i0 + half], x3 = a[i0 + half + q];
+            const double2 w1 = twiddle<SIGN>(tw, pos, 2 * half);
+            const double2 w2 = twiddle<SIGN>(tw, pos, half);
+            double2 s0 = cadd(x0, x2), d0 = cmul(csub(x0, x2), w1);
+            double2 s1 = cadd(x1, x3), d1 = cmul(quarter_turn<SIGN>(csub(x1, x3)), w1);
+            a[i0] = cadd(s0, s1);
+            a[i0 + q] = cmul(csub(s0, s1), w2);
+            a[i0 + half] = cadd(d0, d1);
+            a[i0 + half + q] = cmul(csub(d0, d1), w2);
+        }
+        __syncthreads();
+        half >>= 2;
+    }
+    if (half == 1) {
         for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-            int pos = b & (half - 1);
-            int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
-            double2 u = a[i0], v = a[i1];
-            a[i0] = make_double2(u.x + v.x, u.y + v.y);
-            double2 d = make_double2(u.x - v.x, u.y - v.y);
-            a[i1] = half > 1 ? cmul(d, twiddle<SIGN>(tw, pos, 2 * half)) : d;
+            double2 u = a[2 * b], v = a[2 * b + 1];
+            a[2 * b] = cadd(u, v);
+            a[2 * b + 1] = csub(u, v);
         }
         __syncthreads();
     }
 }
 template <int SIGN>
 __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __restrict__ tw) {
-    for (int half = 1; half < n; half <<= 1) {
+    int logn = 0;
+    while ((1 << logn) < n) logn++;
+    int half = 1;
+    if (logn & 1) {
         for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-            int pos = b & (half - 1);
-            int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
-            double2 u = a[i0], v = a[i1];
-            if (half > 1) v = cmul(v, twiddle<SIGN>(tw, pos, 2 * half));
-            a[i0] = make_double2(u.x + v.x, u.y + v.y);
-            a[i1] = make_double2(u.x - v.x, u.y - v.y);
+            double2 u = a[2 * b], v = a[2 * b + 1];
+            a[2 * b] = cadd(u, v);
+            a[2 * b + 1] = csub(u, v);
         }
         __syncthreads();
+        half = 2;
+    }
+    while (half < n) {
+        const int h = half;
+        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
+            const int pos = t & (h - 1);
+            const int i0 = (t / h) * 4 * h + pos;
+            double2 x0 = a[i0], x1 = a[i0 + h], x2 = a[i0 + 2 * h], x3 = a[i0 + 3 * h];
+            if (h > 1) {
+                const double2 wA = twiddle<SIGN>(tw, pos, 2 * h);
+                x1 = cmul(x1, wA);
+                x3 = cmul(x3, wA);
+            }
+            const double2 wB = twiddle<SIGN>(tw, pos, 4 * h);
+            double2 y0 = cadd(x0, x1), y1 = csub(x0, x1), y2 = cadd(x2, x3), y3 = csub(x2, x3);
+            double2 u2 = cmul(y2, wB), u3 = cmul(quarter_turn<SIGN>(y3), wB);
+            a[i0] = cadd(y0, u2);
+            a[i0 + 2 * h] = csub(y0, u2);
+            a[i0 + h] = cadd(y1, u3);
+            a[i0 + 3 * h] = csub(y1, u3);
+        }
+        __syncthreads();
+        half <<= 2;
     }
 }
 

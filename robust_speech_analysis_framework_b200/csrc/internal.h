@@ -102,7 +102,7 @@ void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s
 
 void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
-void launch_pitch_refine(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);   // + local scores
+void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);   // + local scores
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
 void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones
@@ -144,7 +144,7 @@ struct SpeechRateScratch {
     int* pk_i;
 };
 void launch_speechrate(const Clips& c, const IntensityPass& ip, const double* istats, const PitchPass& pp,
-                       const SpeechRateScratch& sc, cudaStream_t s);
+                       const SpeechRateScratch& sc, const double2* tw, cudaStream_t s);
 
 // Sound_resample job: one sound (a whole clip or one voiced segment of it)
 struct ResampleJob {

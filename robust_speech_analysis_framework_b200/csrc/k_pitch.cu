@@ -57,7 +57,8 @@ struct CandScratch {
 // Sound_into_PitchFrame, first pass: local maxima of r -> parabolic frequency + sinc(30) strength -> candidate slots
 // (Praat's <= maxn slots with its replace-the-weakest rule).  Returns ncand (>= 1, slot 1 = voiceless).
 // Harmonicity pass (maxn = 133 never fills, all path costs zero): only the list of maxima is built; returns their number.
-__device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode) {
+__device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode,
+                                               const double2* __restrict__ tw) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double thr = 0.5 * g.vt;
     int upper = g.maximumLag < B ? g.maximumLag : B;      // i < maximumLag && i < brent_ixmax
@@ -98,7 +99,7 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
         double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
         double freq = 1.0 / dx / (i + dr / d2r);
         double x = 1.0 / dx / freq + (double)(B + 1);
-        double strength = sinc_interp_warp(y1, ny, x, 30, lane);
+        double strength = sinc_interp_warp(y1, ny, x, 30, lane, tw);
         if (strength > 1.0) strength = 1.0 / strength;
         if (lane == 0) {
             S.pk_f[m] = freq;
@@ -150,7 +151,7 @@ struct FrameSmem {      // byte offsets into dynamic shared memory (computed on 
 #define CC_TL 4         // lags per thread in the cross-correlation inner loop
 
 template <bool IS_CC>
-__global__ void __launch_bounds__(NTHR, 2) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
+__global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)(smem + L.a);            // AC: packed FFT buffer; CC: xs[] doubles
     double* xs = (double*)(smem + L.a);
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_pitch_frames(Clips c, PitchPass p, 
         if (p.hnr_mode) {
             // Sound_to_Harmonicity_cc: the frame value is the best refined strength over ALL maxima of r; queue every one
             int nmax = 0;
-            if (localPeak != 0.0) nmax = find_candidates(g, dx, S, B, 1);
+            if (localPeak != 0.0) nmax = find_candidates(g, dx, S, B, 1, tw);
             const double* r = S.rs0 + B;
             for (int m = tid; m < nmax; m += NTHR) {
                 const int i = S.pk_lag[m];
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_pitch_frames(Clips c, PitchPass p, 
         }
         int ncand = 1;
         if (localPeak != 0.0) {
-            ncand = find_candidates(g, dx, S, B, 0);
+            ncand = find_candidates(g, dx, S, B, 0, tw);
         } else if (tid == 0) {
             S.cf[1] = 0.0; S.cs[1] = 0.0; S.cimax[1] = 0;
         }
@@ -430,7 +431,7 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
 // ------------------------------------------------------------------------------------------------ refinement
 // Sound_into_PitchFrame, second pass: NUMimproveMaximum with sinc(70/700) + Brent on the stored correlation row.  A flat,
 // perfectly balanced work list: one warp per queued (frame, candidate).
-__global__ void __launch_bounds__(256, 3) k_pitch_refine(Clips c, PitchPass p) {
+__global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nw = gridDim.x * (blockDim.x >> 5);
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(256, 3) k_pitch_refine(Clips c, PitchPass p) {
         const int imax = p.cand_imax[o2];
         const double f0 = p.cand_f[o2];
         double xmid;
-        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, f0 > 0.3 / dx ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane);
+        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, f0 > 0.3 / dx ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane, tw);
         xmid -= (double)(B + 1);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         if (lane == 0) { p.cand_f[o2] = 1.0 / dx / xmid; p.cand_s[o2] = ymid; }
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(256, 3) k_pitch_refine(Clips c, PitchPass p) {
 
 // Harmonicity variant: every maximum of every frame is an item (frame, lag, depth flag); the frame keeps the largest
 // refined strength among candidates that stay below the Nyquist "ceiling" (atomicMax on the bits of a positive double).
-__global__ void __launch_bounds__(256, 3) k_hnr_refine(Clips c, PitchPass p) {
+__global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(256, 3) k_hnr_refine(Clips c, PitchPass p) {
         y.centre = B + 1;
         y.len = stored_lags(g);
         double xmid;
-        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, deep ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane);
+        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, deep ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane, tw);
         xmid -= (double)(B + 1);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         const double fr = 1.0 / dx / xmid;
@@ -519,9 +520,9 @@ __global__ void k_pitch_score(Clips c, PitchPass p) {
     }
 }
 
-void launch_pitch_refine(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s) {
-    if (p.hnr_mode) k_hnr_refine<<<148 * 3, 256, 0, s>>>(c, p);
-    else k_pitch_refine<<<148 * 3, 256, 0, s>>>(c, p);
+void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s) {
+    if (p.hnr_mode) k_hnr_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
+    else k_pitch_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
     int blocks = (max_frames_hint + 127) / 128;
     if (blocks < 1) blocks = 1;
     k_pitch_score<<<blocks, 128, 0, s>>>(c, p);

@@ -58,8 +58,8 @@ __device__ void cut_short(Ivl* v, int* pn, int sounding, double minimumDuration)
 }
 
 __global__ void __launch_bounds__(SRW * 32) k_speechrate(Clips c, IntensityPass ip, const double* __restrict__ istats,
-                                                          PitchPass pp, SpeechRateScratch sc) {
-    __shared__ int s_npk, s_fail;
+                                                          PitchPass pp, SpeechRateScratch sc, const double2* __restrict__ tw) {
+    __shared__ int s_npk;
     const int clip = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = ip.nF[clip];
@@ -94,13 +94,12 @@ __global__ void __launch_bounds__(SRW * 32) k_speechrate(Clips c, IntensityPass 
         for (int i = 2; i <= n - 1; i++)
             if (y1[i] > y1[i - 1] && y1[i] >= y1[i + 1]) pk_i[k++] = i;
         s_npk = k;
-        s_fail = 0;
     }
     __syncthreads();
     const int npk = s_npk;
     for (int k = warp; k < npk; k += SRW) {
         double i_real;
-        (void)improve_extremum_warp(y1, n, pk_i[k], PEAK_SINC70, &i_real, true, lane);
+        (void)improve_extremum_warp(y1, n, pk_i[k], PEAK_SINC70, &i_real, true, lane, tw);
         if (lane == 0) {
             double t = x1 + (i_real - 1.0) * dx;
             pk_t[k] = t;
@@ -198,6 +197,6 @@ __global__ void __launch_bounds__(SRW * 32) k_speechrate(Clips c, IntensityPass 
 }
 
 void launch_speechrate(const Clips& c, const IntensityPass& ip, const double* istats, const PitchPass& pp,
-                       const SpeechRateScratch& sc, cudaStream_t s) {
-    k_speechrate<<<c.n, SRW * 32, 0, s>>>(c, ip, istats, pp, sc);
+                       const SpeechRateScratch& sc, const double2* tw, cudaStream_t s) {
+    k_speechrate<<<c.n, SRW * 32, 0, s>>>(c, ip, istats, pp, sc, tw);
 }

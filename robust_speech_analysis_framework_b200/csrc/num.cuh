@@ -22,9 +22,26 @@ struct SymRowY {            // y(j) = r[|j - centre|], zero beyond the stored la
     }
 };
 
+// cos(pi*u) for u in [0, 1] from the FFT twiddle table (tw[j] = (cos, -sin)(pi*j/4096), j < 4096) plus a 4th-order
+// angle-addition correction: |error| ~ 1e-16, about half the float64 instructions of cospi().
+__device__ __forceinline__ double cospi_tab(double u, const double2* __restrict__ tw) {
+    const double magic = 6755399441055744.0;                 // 2^52 + 2^51: round-to-nearest-integer trick
+    double t = fma(u, 4096.0, magic);
+    int j = __double2loint(t);
+    double jd = t - magic;
+    if (j > 4095) { j = 4095; jd = 4095.0; }
+    double x = (u - jd * (1.0 / 4096.0)) * MSHDS_PI;         // |x| <= pi/8192 (a little more at u = 1)
+    double x2 = x * x;
+    double2 T = __ldg(tw + j);
+    double cx = fma(x2, fma(x2, 1.0 / 24.0, -0.5), 1.0);
+    double sx = x * fma(x2, -1.0 / 6.0, 1.0);
+    return fma(T.x, cx, T.y * sx);
+}
+
 // y is 1-based: y(1..n) valid.  All 32 lanes must call with identical arguments; all lanes get the result.
 template <class Y>
-__device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x, int maxDepth, int lane) {
+__device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x, int maxDepth, int lane,
+                                                     const double2* __restrict__ tw) {
     int midleft = (int)floor(x), midright = midleft + 1;
     if (n < 1) return DEVNAN;
     if (x > n) return y(n);
@@ -45,13 +62,14 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     double fl = x - midleft, fr = midright - x;
     // halfsina / a * (1 + cos(aa)) with a = pi*(f + k): the constant factor 0.5*sin(pi f)/pi is hoisted and the
     // per-tap division becomes an IEEE reciprocal (one rounding more than Praat's expression: ~1 ulp per tap)
-    double hsl = 0.5 * sinpi(fl) * (1.0 / MSHDS_PI), hsr = 0.5 * sinpi(fr) * (1.0 / MSHDS_PI);
-    double invl = 1.0 / (fl + maxDepth), invr = 1.0 / (fr + maxDepth);     // x-left+1 = fl + depth ; right-x+1 = fr + depth
+    // sin(pi*fr) = sin(pi*(1 - fl)) = sin(pi*fl) = cos(pi*|fl - 1/2|): one table look-up serves both sides
+    const double hsl = 0.5 * cospi_tab(fabs(fl - 0.5), tw) * (1.0 / MSHDS_PI), hsr = hsl;
+    double invl = __drcp_rn(fl + maxDepth), invr = __drcp_rn(fr + maxDepth);  // x-left+1 = fl + depth ; right-x+1 = fr + depth
     double accl = 0.0, accr = 0.0;
     for (int k = lane; k < maxDepth; k += 32) {
         double al = fl + k, ar = fr + k;                                    // in units of pi
-        double dl = __drcp_rn(al) * (1.0 + cospi(al * invl));
-        double dr = __drcp_rn(ar) * (1.0 + cospi(ar * invr));
+        double dl = __drcp_rn(al) * (1.0 + cospi_tab(al * invl, tw));
+        double dr = __drcp_rn(ar) * (1.0 + cospi_tab(ar * invr, tw));
         double yl = y(midleft - k), yr = y(midright + k);
         if (k & 1) { yl = -yl; yr = -yr; }
         accl = fma(yl, dl, accl);
@@ -60,23 +78,24 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     return warp_sum(accl * hsl + accr * hsr);
 }
 
-__device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane) {
+__device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane,
+                                                   const double2* __restrict__ tw) {
     PtrY a{y};
-    return sinc_interp_warp_t(a, n, x, maxDepth, lane);
+    return sinc_interp_warp_t(a, n, x, maxDepth, lane, tw);
 }
 
 // NUMminimize_brent specialised to f(x) = -/+ sinc_interp(y, x, depth); returns x of the extremum, *fx its value
 // (already sign-corrected: the interpolated y at the extremum).
 template <class Y>
 __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a, double b, int depth, bool isMaximum,
-                                                    double* fx_out, int lane) {
+                                                    double* fx_out, int lane, const double2* __restrict__ tw) {
     const double golden = 1.0 - 0.6180339887498948482045868343656381177203;
     const double sqrt_epsilon = 1.4901161193847656e-08;   // sqrt(DBL_EPSILON)
     const double tol = 1e-10;
     const double sg = isMaximum ? -1.0 : 1.0;
     double x, v, fv, w, fw, fx;
     v = a + golden * (b - a);
-    fv = sg * sinc_interp_warp_t(y, n, v, depth, lane);
+    fv = sg * sinc_interp_warp_t(y, n, v, depth, lane, tw);
     x = v; w = v;
     fx = fv; fw = fv;
     for (int iter = 1; iter <= 60; iter++) {
@@ -99,7 +118,7 @@ __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a,
         if (fabs(new_step) < tol_act) new_step = new_step > 0.0 ? tol_act : -tol_act;
         {
             double t = x + new_step;
-            double ft = sg * sinc_interp_warp_t(y, n, t, depth, lane);
+            double ft = sg * sinc_interp_warp_t(y, n, t, depth, lane, tw);
             if (ft <= fx) {
                 if (t < x) b = x; else a = x;
                 v = w; w = x; x = t;
@@ -128,7 +147,8 @@ __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a,
 // NUMimproveExtremum (warp-cooperative for the sinc modes). y 1-based.
 template <class Y>
 __device__ __forceinline__ double improve_extremum_warp_t(const Y& y, int n, int ixmid, int interpolation,
-                                                          double* ixmid_real, bool isMaximum, int lane) {
+                                                          double* ixmid_real, bool isMaximum, int lane,
+                                                          const double2* __restrict__ tw) {
     if (ixmid <= 1) { *ixmid_real = 1; return y(1); }
     if (ixmid >= n) { *ixmid_real = n; return y(n); }
     if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y(ixmid); }
@@ -140,13 +160,14 @@ __device__ __forceinline__ double improve_extremum_warp_t(const Y& y, int n, int
     }
     double fx;
     *ixmid_real = brent_sinc_warp_t(y, n, (double)(ixmid - 1), (double)(ixmid + 1), interpolation == PEAK_SINC70 ? 70 : 700,
-                                    isMaximum, &fx, lane);
+                                    isMaximum, &fx, lane, tw);
     return fx;
 }
 __device__ __forceinline__ double improve_extremum_warp(const double* y, int n, int ixmid, int interpolation,
-                                                        double* ixmid_real, bool isMaximum, int lane) {
+                                                        double* ixmid_real, bool isMaximum, int lane,
+                                                        const double2* __restrict__ tw) {
     PtrY a{y};
-    return improve_extremum_warp_t(a, n, ixmid, interpolation, ixmid_real, isMaximum, lane);
+    return improve_extremum_warp_t(a, n, ixmid, interpolation, ixmid_real, isMaximum, lane, tw);
 }
 
 // single-thread parabolic / none variant
