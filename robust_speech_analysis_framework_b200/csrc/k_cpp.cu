@@ -59,7 +59,8 @@ struct LogPowerF {
 __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix, int nsegs,
                                                       const ResampleJob* __restrict__ jobs, const double* __restrict__ sig,
                                                       const double2* __restrict__ tw, double emphasis, double dt,
-                                                      double* __restrict__ cep, int nqmax) {
+                                                      double* __restrict__ cep, int nqmax, const double* __restrict__ wtab,
+                                                      int wtab_n) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)smem;                      // 512 complex
     double* red = (double*)(smem + sizeof(double2) * 512);
@@ -92,8 +93,12 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
         const double mean = block_sum(acc, red) / (double)nwin;                  // Vector_subtractMean
         const double imid = 0.5 * (double)(nwin + 1), edge = exp(-12.0);
         for (int i = threadIdx.x; i < nwin; i += blockDim.x) {
-            double d = (double)(i + 1) - imid;
-            double w = (exp(-48.0 * d * d / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
+            double w;
+            if (nwin == wtab_n) w = __ldg(wtab + i);                 // Sound_createGaussian for the usual 0.1 s window
+            else {
+                double d = (double)(i + 1) - imid;
+                w = (exp(-48.0 * d * d / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
+            }
             ar[i] = (ar[i] - mean) * w;
         }
         __syncthreads();
@@ -219,7 +224,17 @@ __global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ s
                     slope = quantile_sorted(work, numberOfPairs, 0.5);
                     __syncthreads();
                 }
-                {
+                if ((npts & (npts - 2)) == 0 && npts > 2) {
+                    // npts = 2^k + 1 (513 for the 1024-point cepstrum): sort the first 2^k residuals only and place the
+                    // last one by comparison -- the median (element 2^(k-1)+1 of the sorted 2^k+1) is a[h-1], e or a[h]
+                    const int h2 = npts - 1, h = h2 >> 1;
+                    for (int i = threadIdx.x; i < h2; i += blockDim.x) work[i] = yy[i] - slope * ((double)(imin - 1 + i) * dq);
+                    __syncthreads();
+                    block_bitonic_sort(work, h2);
+                    const double e = yy[h2] - slope * ((double)(imin - 1 + h2) * dq);
+                    intercept = e <= work[h - 1] ? work[h - 1] : (e >= work[h] ? work[h] : e);
+                    __syncthreads();
+                } else {
                     int np2 = 1;
                     while (np2 < npts) np2 <<= 1;
                     for (int i = threadIdx.x; i < np2; i += blockDim.x)
@@ -320,11 +335,12 @@ void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, 
     k_vuv_segments<<<(c.n + 63) / 64, 64, 0, s>>>(c, ps, sg, 0.02, 0.1);
 }
 void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
-                        const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames, cudaStream_t s) {
+                        const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames,
+                        const double* wtab, int wtab_n, cudaStream_t s) {
     int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
     if (grid < 1) grid = 1;
     size_t smem = sizeof(double2) * 512 + sizeof(double) * 32;
-    k_cepstrogram<<<grid, 256, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax);
+    k_cepstrogram<<<grid, 256, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax, wtab, wtab_n);
 }
 void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(FW * 32) k_formant_frames(FormantPass p, int n
             if (rad < 0.3) rad = 0.3;
             if (rad > 1.2) rad = 1.2;
             cplx z = {rad * cos(ang), rad * sin(ang)};
-            for (int it = 0; it < 100; it++) {
+            for (int it = 0; it < 60; it++) {
                 cplx pz, dpz;
                 poly_eval(c, NPOLES, z, &pz, &dpz);
                 cplx newton = c_div(pz, dpz);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(FW * 32) k_formant_frames(FormantPass p, int n
                 if (own) { z.re -= step.re; z.im -= step.im; }
                 double sz = own ? c_abs(step) / fmax(c_abs(z), 1e-300) : 0.0;
                 sz = warp_max(sz);
-                if (sz < 1e-15) break;
+                if (sz < 1e-13) break;            // the Newton polish below finishes the last digits
             }
             // Newton polish on the original polynomial (Roots_Polynomial_polish): keep the iterate with the smallest |p|
             {

@@ -324,8 +324,12 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
 
         if (p.hnr_mode) {
             // Sound_to_Harmonicity_cc: the frame value is the best refined strength over ALL maxima of r; queue every one
+            // unvoiced local score: a voiced candidate needs strength > 2 - intensity/sil (vt = 0) and strengths never
+            // exceed 1 (reflection), so a frame with 2 - intensity/sil >= 1 is -200 dB whatever its candidates are
+            double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
+            uvs = g.vt + (uvs > 0 ? uvs : 0);
             int nmax = 0;
-            if (localPeak != 0.0) nmax = find_candidates(g, dx, S, B, 1, tw);
+            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates(g, dx, S, B, 1, tw);
             const double* r = S.rs0 + B;
             for (int m = tid; m < nmax; m += NTHR) {
                 const int i = S.pk_lag[m];
@@ -348,6 +352,16 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         }
         __syncthreads();
 
+        // Pitch_pathFinder: replacing a voiced candidate of frame t by the voiceless one gains at least
+        // (unvoicedStrength - 1) locally (voiced local scores are <= 1) and costs at most two voiced/unvoiced transitions,
+        // so when unvoicedStrength > 1 + 2*vuvCost no voiced candidate of this frame can lie on the best path: their
+        // refined values cannot matter and the refinement is skipped (exact).
+        bool frame_stays_unvoiced;
+        {
+            double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
+            uvs = g.vt + (uvs > 0 ? uvs : 0);
+            frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
+        }
         // candidates leave the SM; the ones that can matter are queued for the refinement kernel
         if (tid < MAXCAND) {
             const int ci = tid + 1;
@@ -358,7 +372,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             p.cand_f[o2] = fr; p.cand_s[o2] = st; p.cand_imax[o2] = (unsigned short)im;
             // A candidate whose refined lag cannot fall below fs/ceiling (refined lag <= imax+1) stays voiceless for the
             // path finder whatever its refined values: it is never refined.
-            bool live = ci >= 2 && ci <= ncand && (1.0 / dx / (double)(im + 1) < g.ceiling);
+            bool live = ci >= 2 && ci <= ncand && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
             if (live) {
                 int slot = atomicAdd(p.qcount, 1);
                 p.queue[slot] = f * 16 + tid;

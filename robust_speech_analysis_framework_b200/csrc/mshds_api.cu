@@ -492,7 +492,9 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     if (nsegs > 0 && totalFrames > 0) {
         PB("resample_segments_10k[fft+sinc50]"); run_resample(h, plan, D, c.pcm, fs, fs10, 50, s); PE();
         const double emphasis = exp(-2.0 * MSHDS_PI * 50.0 * (1.0 / fs10));
-        PB("cepstrogram_frames"); launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, s); h->launches += 1; PE();
+        const double* cep_win = nullptr;                 // same formula as the formant window (Sound_createGaussian)
+        { int rcw = make_formant_window(h, 1000, &cep_win); if (rcw) return rcw; }
+        PB("cepstrogram_frames"); launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, cep_win, 1000, s); h->launches += 1; PE();
         const int nTimeAvg = (int)floor(0.01 / dt);
         PB("cpps_frames"); launch_cpp_frames(d_cseg, d_fprefix, nsegs, d_cep, nqmax, nTimeAvg, 0.001, d_cppf, totalFrames, s); h->launches += 1; PE();
     }
