@@ -119,18 +119,22 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ CPPS per frame
-// ascending bitonic sort of v[0..npow2) in shared memory (npow2 a power of two, padded with +inf by the caller)
+// ascending bitonic sort of v[0..npow2) in shared memory (npow2 a power of two, padded with +inf by the caller).
+// Pair t of a stage with partner distance j touches the 64-element window of its own warp whenever j <= 32, so those
+// stages only need a warp barrier; block barriers remain for the few long-distance stages.
 __device__ void block_bitonic_sort(double* v, int npow2) {
     for (int k = 2; k <= npow2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = threadIdx.x; t < (npow2 >> 1); t += blockDim.x) {
-                int lo = ((t / j) * 2 * j) + (t % j);          // partner pairs (lo, lo + j)
-                int hi = lo + j;
-                bool up = ((lo & k) == 0);
-                double a = v[lo], b = v[hi];
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // partner pairs (lo, lo + j)
+                const int hi = lo + j;
+                const bool up = ((lo & k) == 0);
+                const double a = v[lo], b = v[hi];
                 if ((a > b) == up) { v[lo] = b; v[hi] = a; }
             }
-            __syncthreads();
+            const bool last = (k == npow2 && j == 1);
+            if (j > 32 || last || (j == 1 && k >= 64)) __syncthreads();
+            else __syncwarp();
         }
     }
 }

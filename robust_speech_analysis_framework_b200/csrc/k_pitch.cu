@@ -443,12 +443,41 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
 }
 
 // ------------------------------------------------------------------------------------------------ refinement
+#define RF_HALF 71          // sinc70 evaluated on [c-1, c+1] touches y[c-70 .. c+70]
+#define RF_WIN (2 * RF_HALF + 2)
+
+// NUMimproveMaximum of candidate `imax` on the correlation row of frame f.  The 141 row values a sinc70 search can touch
+// are staged once per item in shared memory (the search evaluates the interpolation ~13 times); sinc700 candidates
+// (f > 0.3 fs, lag < 3.4) read the row directly.
+__device__ __forceinline__ double refine_candidate(const SymRowY& y, int B, int imax, bool deep, double* st, double* xmid_out,
+                                                   int lane, const double2* __restrict__ tw) {
+    const int n = 2 * B + 1, c0 = imax + B + 1;
+    double xmid, ymid;
+    if (deep) {
+        ymid = improve_extremum_warp_t(y, n, c0, PEAK_SINC700, &xmid, true, lane, tw);
+    } else {
+        const int j0 = c0 - RF_HALF;
+        __syncwarp();
+        for (int j = lane; j < RF_WIN; j += 32) {
+            int idx = j0 + j;
+            st[j] = (idx >= 1 && idx <= n) ? y(idx) : 0.0;
+        }
+        __syncwarp();
+        StagedY ys{st, j0};
+        ymid = improve_extremum_warp_t(ys, n, c0, PEAK_SINC70, &xmid, true, lane, tw);
+    }
+    *xmid_out = xmid - (double)(B + 1);
+    return ymid;
+}
+
 // Sound_into_PitchFrame, second pass: NUMimproveMaximum with sinc(70/700) + Brent on the stored correlation row.  A flat,
 // perfectly balanced work list: one warp per queued (frame, candidate).
 __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nw = gridDim.x * (blockDim.x >> 5);
+    __shared__ double s_stage[8][RF_WIN];
+    double* st = s_stage[threadIdx.x >> 5];
     const int total = *p.qcount;
     const double dx = c.dx;
     for (int q = gw; q < total; q += nw) {
@@ -465,8 +494,7 @@ __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, c
         const int imax = p.cand_imax[o2];
         const double f0 = p.cand_f[o2];
         double xmid;
-        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, f0 > 0.3 / dx ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane, tw);
-        xmid -= (double)(B + 1);
+        double ymid = refine_candidate(y, B, imax, f0 > 0.3 / dx, st, &xmid, lane, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         if (lane == 0) { p.cand_f[o2] = 1.0 / dx / xmid; p.cand_s[o2] = ymid; }
     }
@@ -478,6 +506,8 @@ __global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, con
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    __shared__ double s_stage[8][RF_WIN];
+    double* st = s_stage[threadIdx.x >> 5];
     unsigned long long total = *p.qcount64;
     if (total > p.q64_cap) total = p.q64_cap;
     const double dx = c.dx;
@@ -493,8 +523,7 @@ __global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, con
         y.centre = B + 1;
         y.len = stored_lags(g);
         double xmid;
-        double ymid = improve_extremum_warp_t(y, 2 * B + 1, imax + B + 1, deep ? PEAK_SINC700 : PEAK_SINC70, &xmid, true, lane, tw);
-        xmid -= (double)(B + 1);
+        double ymid = refine_candidate(y, B, imax, deep, st, &xmid, lane, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         const double fr = 1.0 / dx / xmid;
         if (lane == 0 && fr > 0.0 && fr < g.ceiling && ymid > 0.0)

@@ -359,17 +359,21 @@ static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleD
     const double dx = 1.0 / fs;
     const double upfactor = fs_new * dx;
     int pos = 0;
+    PB(precision >= 500 ? "  resample500: fft low-pass" : "  resample50: fft low-pass");
     for (auto& g : P.groups) {
         launch_resample_fft_group(D.jobs, D.ids + pos, g.second, g.first, pcm, D.zbuf, D.filt, h->tw, upfactor, s, &h->launches);
         pos += g.second;
     }
+    PE();
     // polyphase period of the rate change (16 kHz -> 10 kHz: 5 phases)
     long long a = (long long)llround(fs), b = (long long)llround(fs_new), gg = a, r = b;
     while (r) { long long t = gg % r; gg = r; r = t; }
     int phases = (int)(b / gg);
     if (phases > 16) phases = 0;
+    PB(precision >= 500 ? "  resample500: sinc interpolation" : "  resample50: sinc interpolation");
     launch_sinc_resample(D.jobs, D.out_prefix, (int)P.jobs.size(), P.ototal, D.table_rep, (int)P.table_rep.size(), D.filt, D.table,
                          D.out, phases, precision, dx, s, &h->launches);
+    PE();
 }
 
 static int upload_plan(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, cudaStream_t s) {

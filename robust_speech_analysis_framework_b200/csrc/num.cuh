@@ -38,6 +38,12 @@ __device__ __forceinline__ double cospi_tab(double u, const double2* __restrict_
     return fma(T.x, cx, T.y * sx);
 }
 
+struct StagedY {            // a window of the 1-based array staged in shared memory: y(j) = st[j - j0]
+    const double* st;
+    int j0;
+    __device__ __forceinline__ double operator()(int j) const { return st[j - j0]; }
+};
+
 // y is 1-based: y(1..n) valid.  All 32 lanes must call with identical arguments; all lanes get the result.
 template <class Y>
 __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x, int maxDepth, int lane,
