@@ -44,6 +44,10 @@ struct PitchPass {
     int rstride;
     int* queue;                // refinement work list: frame*16 + candidate slot
     int* qcount;
+    // dual mode: a second analysis that differs only in its voicing threshold shares frames, correlation and rbuf
+    double dual_vt;
+    double* dual_cand_f; double* dual_cand_s; unsigned short* dual_cand_imax; uint8_t* dual_ncand; double* dual_inten;
+    int* dual_queue; int* dual_qcount;
     // harmonicity pass: every maximum of r is refined; items = frame<<32 | lag<<8 | sinc700 flag
     unsigned long long* queue64;
     unsigned long long* qcount64;

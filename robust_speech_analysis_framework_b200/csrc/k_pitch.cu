@@ -54,13 +54,40 @@ struct CandScratch {
     int* s_int;         // [4]: n maxima, ncand
 };
 
-// Sound_into_PitchFrame, first pass: local maxima of r -> parabolic frequency + sinc(30) strength -> candidate slots
-// (Praat's <= maxn slots with its replace-the-weakest rule).  Returns ncand (>= 1, slot 1 = voiceless).
+// Praat's slot assignment (first free slot, else replace the weakest when stronger), run by ONE thread over the ordered
+// list of maxima; only maxima with r > thr take part.  Returns ncand (>= 1, slot 1 = voiceless).
+__device__ __forceinline__ int insert_candidates(const PitchCfg& g, const CandScratch& S, const double* r, int nmax, double thr,
+                                                 double* cf, double* cs, double* ckey, int* cimax) {
+    int ncand = 1;
+    cf[1] = 0.0; cs[1] = 0.0; cimax[1] = 0;
+    for (int m = 0; m < nmax; m++) {
+        if (!(r[S.pk_lag[m]] > thr)) continue;
+        int place = 0;
+        if (ncand < g.maxn) {
+            place = ++ncand;
+        } else {
+            double weakest = 2;
+            for (int iweak = 2; iweak <= g.maxn; iweak++) {
+                double ls = ckey[iweak];
+                if (ls < weakest) { weakest = ls; place = iweak; }
+            }
+            if (S.pk_key[m] <= weakest) place = 0;
+        }
+        if (place) { cf[place] = S.pk_f[m]; cs[place] = S.pk_s[m]; ckey[place] = S.pk_key[m]; cimax[place] = S.pk_lag[m]; }
+    }
+    return ncand;
+}
+
+// Sound_into_PitchFrame, first pass: local maxima of r -> parabolic frequency + sinc(30) strength -> candidate slots.
+// `vt2 >= 0` additionally builds the slots of a second analysis that differs only in its voicing threshold (the maxima
+// of the lower threshold are a superset, the first-pass values are shared).  Returns ncand | ncand2 << 8.
 // Harmonicity pass (maxn = 133 never fills, all path costs zero): only the list of maxima is built; returns their number.
 __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode,
-                                               const double2* __restrict__ tw) {
+                                               const double2* __restrict__ tw, double vt2, double* cf2, double* cs2,
+                                               double* ckey2, int* cimax2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double thr = 0.5 * g.vt;
+    const double thr1 = 0.5 * g.vt;
+    const double thr = (vt2 >= 0.0 && 0.5 * vt2 < thr1) ? 0.5 * vt2 : thr1;
     int upper = g.maximumLag < B ? g.maximumLag : B;      // i < maximumLag && i < brent_ixmax
     int nlag = upper - 2;                                   // lags 2 .. upper-1
     if (nlag < 0) nlag = 0;
@@ -108,29 +135,10 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int ncand = 1;
-        S.cf[1] = 0.0; S.cs[1] = 0.0; S.cimax[1] = 0;
-        for (int m = 0; m < nmax; m++) {
-            int place = 0;
-            if (ncand < g.maxn) {
-                place = ++ncand;
-            } else {
-                double weakest = 2;
-                for (int iweak = 2; iweak <= g.maxn; iweak++) {
-                    double ls = S.ckey[iweak];
-                    if (ls < weakest) { weakest = ls; place = iweak; }
-                }
-                if (S.pk_key[m] <= weakest) place = 0;
-            }
-            if (place) {
-                S.cf[place] = S.pk_f[m]; S.cs[place] = S.pk_s[m]; S.ckey[place] = S.pk_key[m]; S.cimax[place] = S.pk_lag[m];
-            }
-        }
-        S.s_int[1] = ncand;
-    }
+    if (tid == 0) S.s_int[1] = insert_candidates(g, S, r, nmax, thr1, S.cf, S.cs, S.ckey, S.cimax);
+    if (tid == 32 && vt2 >= 0.0) S.s_int[2] = insert_candidates(g, S, r, nmax, 0.5 * vt2, cf2, cs2, ckey2, cimax2);
     __syncthreads();
-    return S.s_int[1];
+    return S.s_int[1] | ((vt2 >= 0.0 ? S.s_int[2] : 0) << 8);
 }
 
 struct FrameInfo {
@@ -143,7 +151,7 @@ struct FrameInfo {
 // ------------------------------------------------------------------------------------------------ frame kernel
 // IS_CC = false: autocorrelation (AC_HANNING);  true: forward cross-correlation (FCC_NORMAL), optionally HNR mode.
 struct FrameSmem {      // byte offsets into dynamic shared memory (computed on the host)
-    int a, rs, pkf, pks, pkkey, cf, cs, ckey, red, part, pklag, cimax, masks, sint, fi, total;
+    int a, rs, pkf, pks, pkkey, cf, cs, ckey, cf2, cs2, ckey2, cimax2, red, part, pklag, cimax, masks, sint, fi, total;
     int part_stride;    // CC: doubles per partial-sum row (>= maximumLag)
     int nchunk_max;
 };
@@ -163,6 +171,10 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
     S.cf = (double*)(smem + L.cf);
     S.cs = (double*)(smem + L.cs);
     S.ckey = (double*)(smem + L.ckey);
+    double* cf2 = (double*)(smem + L.cf2);
+    double* cs2 = (double*)(smem + L.cs2);
+    double* ckey2 = (double*)(smem + L.ckey2);
+    int* cimax2 = (int*)(smem + L.cimax2);
     double* red = (double*)(smem + L.red);
     double* part = (double*)(smem + L.part);
     S.pk_lag = (int*)(smem + L.pklag);
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
             uvs = g.vt + (uvs > 0 ? uvs : 0);
             int nmax = 0;
-            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates(g, dx, S, B, 1, tw);
+            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates(g, dx, S, B, 1, tw, -1.0, cf2, cs2, ckey2, cimax2);
             const double* r = S.rs0 + B;
             for (int m = tid; m < nmax; m += NTHR) {
                 const int i = S.pk_lag[m];
@@ -344,11 +356,15 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             if (tid == 0) { p.inten[f] = intensity; p.best_bits[f] = 0ull; }
             continue;
         }
-        int ncand = 1;
+        const bool dual = p.dual_cand_f != nullptr;
+        int ncand = 1, ncand2 = 1;
         if (localPeak != 0.0) {
-            ncand = find_candidates(g, dx, S, B, 0, tw);
+            int nn = find_candidates(g, dx, S, B, 0, tw, dual ? p.dual_vt : -1.0, cf2, cs2, ckey2, cimax2);
+            ncand = nn & 0xff;
+            if (dual) ncand2 = nn >> 8;
         } else if (tid == 0) {
             S.cf[1] = 0.0; S.cs[1] = 0.0; S.cimax[1] = 0;
+            cf2[1] = 0.0; cs2[1] = 0.0; cimax2[1] = 0;
         }
         __syncthreads();
 
@@ -356,29 +372,37 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         // (unvoicedStrength - 1) locally (voiced local scores are <= 1) and costs at most two voiced/unvoiced transitions,
         // so when unvoicedStrength > 1 + 2*vuvCost no voiced candidate of this frame can lie on the best path: their
         // refined values cannot matter and the refinement is skipped (exact).
-        bool frame_stays_unvoiced;
-        {
-            double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
-            uvs = g.vt + (uvs > 0 ? uvs : 0);
-            frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
-        }
-        // candidates leave the SM; the ones that can matter are queued for the refinement kernel
-        if (tid < MAXCAND) {
-            const int ci = tid + 1;
+        // Candidates leave the SM; the ones that can matter are queued for the refinement kernel.  Threads 0..14 serve
+        // the analysis itself, threads 32..46 the second analysis that shares this correlation (dual mode).
+        const int set = tid >> 5, ctid = tid & 31;
+        if (ctid < MAXCAND && (set == 0 || (set == 1 && dual))) {
+            const double vt = set == 0 ? g.vt : p.dual_vt;
+            double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + vt));
+            uvs = vt + (uvs > 0 ? uvs : 0);
+            const bool frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
+            const int nc = set == 0 ? ncand : ncand2;
+            const double* scf = set == 0 ? S.cf : cf2;
+            const double* scs = set == 0 ? S.cs : cs2;
+            const int* sci = set == 0 ? S.cimax : cimax2;
+            const int ci = ctid + 1;
             double fr = 0.0, st = 0.0;
             int im = 0;
-            if (ci <= ncand) { fr = S.cf[ci]; st = S.cs[ci]; im = S.cimax[ci]; }
-            const size_t o2 = (size_t)f * MAXCAND + tid;
-            p.cand_f[o2] = fr; p.cand_s[o2] = st; p.cand_imax[o2] = (unsigned short)im;
+            if (ci <= nc) { fr = scf[ci]; st = scs[ci]; im = sci[ci]; }
+            const size_t o2 = (size_t)f * MAXCAND + ctid;
+            if (set == 0) { p.cand_f[o2] = fr; p.cand_s[o2] = st; p.cand_imax[o2] = (unsigned short)im; }
+            else { p.dual_cand_f[o2] = fr; p.dual_cand_s[o2] = st; p.dual_cand_imax[o2] = (unsigned short)im; }
             // A candidate whose refined lag cannot fall below fs/ceiling (refined lag <= imax+1) stays voiceless for the
             // path finder whatever its refined values: it is never refined.
-            bool live = ci >= 2 && ci <= ncand && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
+            bool live = ci >= 2 && ci <= nc && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
             if (live) {
-                int slot = atomicAdd(p.qcount, 1);
-                p.queue[slot] = f * 16 + tid;
+                if (set == 0) { int slot = atomicAdd(p.qcount, 1); p.queue[slot] = f * 16 + ctid; }
+                else { int slot = atomicAdd(p.dual_qcount, 1); p.dual_queue[slot] = f * 16 + ctid; }
             }
         }
-        if (tid == 0) { p.ncand[f] = (uint8_t)ncand; p.inten[f] = intensity; }
+        if (tid == 0) {
+            p.ncand[f] = (uint8_t)ncand; p.inten[f] = intensity;
+            if (dual) { p.dual_ncand[f] = (uint8_t)ncand2; p.dual_inten[f] = intensity; }
+        }
     }
 }
 
@@ -402,6 +426,10 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     L.cf = take((int)sizeof(double) * (MAXCAND + 1));
     L.cs = take((int)sizeof(double) * (MAXCAND + 1));
     L.ckey = take((int)sizeof(double) * (MAXCAND + 1));
+    L.cf2 = take((int)sizeof(double) * (MAXCAND + 1));
+    L.cs2 = take((int)sizeof(double) * (MAXCAND + 1));
+    L.ckey2 = take((int)sizeof(double) * (MAXCAND + 1));
+    L.cimax2 = take((int)sizeof(int) * (MAXCAND + 1));
     L.red = take((int)sizeof(double) * 32);
     L.part_stride = (ml + 8 + 7) & ~7;
     L.nchunk_max = 4;
@@ -430,6 +458,7 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
     if (grid < 1) grid = 1;
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
+    if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
     if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
     if (is_cc) {
         cudaFuncSetAttribute(k_pitch_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -570,6 +570,14 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
         need = std::max(need, rbuf_need(ccp, fub5)); need = std::max(need, rbuf_need(cpp_p, fub5));
         cs.rbuf = take<double>(h, need);
     }
+    // the CPP pitch (:270) differs from the main one (:178) only in voicing_threshold: it shares the main pass's frames
+    // and correlation rows, so its candidates live in a second scratch set
+    CandScratchBuf cs2 = cs;
+    cs2.f = take<double>(h, fub5 * MAXCAND); cs2.s = take<double>(h, fub5 * MAXCAND);
+    cs2.score = take<double>(h, fub5 * MAXCAND); cs2.lf = take<double>(h, fub5 * MAXCAND);
+    cs2.ncand = take<uint8_t>(h, fub5); cs2.psi = take<uint8_t>(h, fub5 * 16);
+    cs2.imax = take<unsigned short>(h, fub5 * MAXCAND); cs2.inten = take<double>(h, fub5);
+    cs2.queue = take<int>(h, fub5 * (MAXCAND - 1)); cs2.qcount = take<int>(h, 1);
     alloc_pitch_pass(h, &wide, n, fub5, cs);
     alloc_pitch_pass(h, &mainp, n, fub5, cs);
     alloc_pitch_pass(h, &hnr, n, fub5, cs);
@@ -581,7 +589,12 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     alloc_pitch_pass(h, &srp, n, fub20, cs);
     alloc_pitch_pass(h, &ltp, n, fub75, cs);
     alloc_pitch_pass(h, &ccp, n, fub5, cs);
-    alloc_pitch_pass(h, &cpp_p, n, fub5, cs);
+    alloc_pitch_pass(h, &cpp_p, n, fub5, cs2);
+    // cpp_p reuses the frame grid of mainp (identical dt, floor, window)
+    cpp_p.nF = mainp.nF; cpp_p.t1 = mainp.t1; cpp_p.fstart = mainp.fstart;
+    mainp.dual_vt = cpp_p.cfg[0].vt;
+    mainp.dual_cand_f = cpp_p.cand_f; mainp.dual_cand_s = cpp_p.cand_s; mainp.dual_cand_imax = cpp_p.cand_imax;
+    mainp.dual_ncand = cpp_p.ncand; mainp.dual_inten = cpp_p.inten; mainp.dual_queue = cpp_p.queue; mainp.dual_qcount = cpp_p.qcount;
 
     // ---- glottal pulses: raw / final capacity per clip (shared raw scratch, one final set per consumer)
     const double cprime = 500.0 / 0.8 * 1.15;
@@ -716,9 +729,12 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
 
     // ---- _extract_pitch (:164-183)
     launch_pitch_grid(c, mainp, s); h->launches += 2;
-    PB("pitch_ac_frames[main]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("pitch_ac_frames[main + cpp vt=0.3]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
     PB("pitch_refine+score"); launch_pitch_refine(c, mainp, h->tw, fhint, s); h->launches += 2; PE();
     PB("viterbi"); launch_pitch_viterbi(c, mainp, s); h->launches += 1; PE();
+    // the CPP pitch pass (:270) rides on the same correlation rows: refine its own candidates now, before rbuf is reused
+    PB("pitch_refine+score"); launch_pitch_refine(c, cpp_p, h->tw, fhint, s); h->launches += 2; PE();
+    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, s); h->launches += 1;
 
     // ---- _extract_intensity (:185-205)
@@ -751,10 +767,6 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
 
     // ---- _extract_CPP (:253-301)
-    launch_pitch_grid(c, cpp_p, s); h->launches += 2;
-    PB("pitch_ac_frames[cpp vt=0.3]"); launch_pitch_frames(c, cpp_p, h->tw, fhint, s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, cpp_p, h->tw, fhint, s); h->launches += 2; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5; PE();
     launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;
     if ((rc = run_cpp_stage(h, c, off_host, lens, sg, scap, seg_prefix, fs, s))) return rc;
