@@ -166,9 +166,11 @@ struct ResampleJob {
 };
 void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, const int16_t* pcm, double2* zbuf,
                                double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches);
+#define SINC_FIR_R 7        // outputs per thread of the polyphase FIR kernel (k_resample.cu FIR_R)
 void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
-                          const int* d_table_rep /*[ntables] representative job per table*/, int ntables, const double* filt,
-                          double* table, double* out, int P, int D, double dx_src, cudaStream_t s, long long* launches);
+                          const int* d_table_rep /*[ntables] representative job per table*/, int ntables,
+                          const int* d_tile_prefix /*[njobs+1] FIR tiles per job*/, int total_tiles, const double* filt,
+                          double* table, double* out, int P, int Q, int D, double dx_src, cudaStream_t s, long long* launches);
 
 // Sound_to_Formant_burg over the resampled clips (job index == clip index)
 struct FormantPass {

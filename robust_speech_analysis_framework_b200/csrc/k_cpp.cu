@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ s
                     slope = quantile_sorted(work, numberOfPairs, 0.5);
                     __syncthreads();
                 }
-                if ((npts & (npts - 2)) == 0 && npts > 2) {
+                if (((npts - 1) & (npts - 2)) == 0 && npts > 2) {
                     // npts = 2^k + 1 (513 for the 1024-point cepstrum): sort the first 2^k residuals only and place the
                     // last one by comparison -- the median (element 2^(k-1)+1 of the sorted 2^k+1) is a[h-1], e or a[h]
                     const int h2 = npts - 1, h = h2 >> 1;

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __rest
 // ------------------------------------------------------------------------------------------------ sinc interpolation
 // Coefficient table of NUM_interpolate_sinc for the P distinct fractional positions of a rational rate change.
 __global__ void k_sinc_table(const ResampleJob* __restrict__ jobs, const int* __restrict__ rep, int ntables,
-                             double* __restrict__ table, double* __restrict__ table_fl, int P, int D, double dx_src) {
+                             double* __restrict__ table, double* __restrict__ table_fl, long long* __restrict__ table_mid,
+                             int P, int D, double dx_src) {
     const int tab = blockIdx.x;
     if (tab >= ntables) return;
     const ResampleJob J = jobs[rep[tab]];
@@ -140,6 +141,7 @@ __global__ void k_sinc_table(const ResampleJob* __restrict__ jobs, const int* __
         double x = J.out_x1 + (double)(j - 1) * J.out_dx;
         double index = (x - J.x1) / dx_src + 1.0;
         table_fl[(size_t)tab * P + threadIdx.x] = index - floor(index);
+        table_mid[(size_t)tab * P + threadIdx.x] = (long long)floor(index);
     }
     for (int e = threadIdx.x; e < P * 2 * D; e += blockDim.x) {
         int ph = e / (2 * D), k = e % (2 * D);
@@ -235,6 +237,139 @@ __global__ void __launch_bounds__(256) k_sinc_apply(const ResampleJob* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------ polyphase FIR
+// Regular outputs of a rational rate change: output j = P*m + ph + 1 has midleft = mid_rep(ph) + Q*(m - m_rep) and one of P
+// fixed coefficient rows, i.e. P FIR filters over Q-decimated input streams.  One warp per phase, one thread computes FIR_R
+// consecutive outputs of its phase with a sliding register window: per tap step 2 shared-memory loads feed FIR_R FMAs.
+// The input tile is staged de-interleaved (Q streams) so lane strides are FIR_R doubles (odd => conflict-free).
+#define FIR_R 7
+__global__ void __launch_bounds__(512) k_sinc_fir(const ResampleJob* __restrict__ jobs, const int* __restrict__ tile_prefix, int njobs,
+                                                   const double* __restrict__ filt, const double* __restrict__ table,
+                                                   const long long* __restrict__ table_mid, double* __restrict__ out, int P, int Q, int D) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* U = (double*)smem_raw;
+    __shared__ int s_job;
+    if (threadIdx.x == 0) s_job = find_segment(tile_prefix, njobs, blockIdx.x);
+    __syncthreads();
+    const int job = s_job;
+    const ResampleJob J = jobs[job];
+    const int tt = blockIdx.x - tile_prefix[job];
+    const long long m_rep = J.nout / 2 / P;
+    const long long m0 = (long long)tt * (32 * FIR_R);
+    const long long* mids = table_mid + (size_t)J.table_id * P;
+    // tile sample range [lo, hi] (1-based indices into the filtered signal)
+    long long mid_min = 0x7fffffffffffffffLL, mid_max = -0x7fffffffffffffffLL;
+    for (int ph = 0; ph < P; ph++) {
+        long long mm = mids[ph] + (long long)Q * (m0 - m_rep);
+        mid_min = mm < mid_min ? mm : mid_min;
+        mid_max = mm > mid_max ? mm : mid_max;
+    }
+    const long long lo = mid_min - (D - 1) - Q;                     // one extra Q of head-room for the sliding window
+    const long long hi = mid_max + (long long)Q * (32 * FIR_R - 1) + D + Q;
+    const int span = (int)(hi - lo + 1);
+    const int NU = ((span + Q - 1) / Q + 2) | 1;                     // odd row length
+    const double* y = filt + J.filt_off - 1;                         // 1-based
+    for (int pos = threadIdx.x; pos < span; pos += blockDim.x) {
+        long long i = lo + pos;
+        U[(pos % Q) * NU + pos / Q] = (i >= 1 && i <= J.nx) ? y[i] : 0.0;
+    }
+    __syncthreads();
+    const int ph = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ph >= P) return;
+    const double* T = table + ((size_t)J.table_id * P + ph) * 2 * D;
+    const long long mid0 = mids[ph] + (long long)Q * (m0 - m_rep);   // midleft of output m0 of this phase
+    const int off = (int)(mid0 - lo);                                // position of that sample in the tile
+    double acc[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) acc[r] = 0.0;
+    // left taps: sample mid - k, k = k0 + Q*s
+    for (int k0 = 0; k0 < Q && k0 < D; k0++) {
+        const int e = off - k0;
+        const double* Us = U + (e % Q) * NU + e / Q + lane * FIR_R;
+        double w[FIR_R];
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) w[r] = Us[r];
+        int sidx = 0;
+        for (int k = k0; k < D; k += Q) {
+            const double cf = __ldg(T + k);
+#pragma unroll
+            for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[r], acc[r]);
+#pragma unroll
+            for (int r = FIR_R - 1; r > 0; r--) w[r] = w[r - 1];
+            sidx++;
+            w[0] = Us[-sidx];
+        }
+    }
+    // right taps: sample mid + 1 + k
+    for (int k0 = 0; k0 < Q && k0 < D; k0++) {
+        const int e = off + 1 + k0;
+        const double* Us = U + (e % Q) * NU + e / Q + lane * FIR_R;
+        double w[FIR_R];
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) w[r] = Us[r];
+        int sidx = 0;
+        for (int k = k0; k < D; k += Q) {
+            const double cf = __ldg(T + D + k);
+#pragma unroll
+            for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[r], acc[r]);
+#pragma unroll
+            for (int r = 0; r < FIR_R - 1; r++) w[r] = w[r + 1];
+            sidx++;
+            w[FIR_R - 1] = Us[FIR_R - 1 + sidx];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) {
+        long long m = m0 + (long long)lane * FIR_R + r;
+        long long j = (long long)P * m + ph + 1;
+        if (j <= J.nout) out[J.out_off + j - 1] = acc[r];
+    }
+}
+
+// Outputs the regular pattern does not describe (depth clipped at the ends of the sound, an index that is an exact
+// integer, a fractional position that fell on the other side of an integer than the table's) are recomputed exactly.
+__global__ void __launch_bounds__(256) k_sinc_fixup(const ResampleJob* __restrict__ jobs, const long long* __restrict__ out_prefix,
+                                                     int njobs, const double* __restrict__ filt, const double* __restrict__ table_fl,
+                                                     const long long* __restrict__ table_mid, double* __restrict__ out, int P,
+                                                     int Q, int D, double dx_src) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long total = out_prefix[njobs];
+    for (long long o0 = gw * 32; o0 < total; o0 += nw * 32) {
+        const long long o = o0 + lane;
+        bool irregular = false;
+        int job = 0;
+        long long j = 0;
+        double index = 0.0;
+        if (o < total) {
+            job = find_segment_ll(out_prefix, njobs, o);
+            const ResampleJob J = jobs[job];
+            j = o - out_prefix[job] + 1;
+            const double x = J.out_x1 + (double)(j - 1) * J.out_dx;
+            index = (x - J.x1) / dx_src + 1.0;
+            const long long midleft = (long long)floor(index);
+            const int ph = (int)((j - 1) % P);
+            const long long m = (j - 1) / P, m_rep = J.nout / 2 / P;
+            const long long pred = table_mid[(size_t)J.table_id * P + ph] + (long long)Q * (m - m_rep);
+            const double tfl = table_fl[(size_t)J.table_id * P + ph];
+            irregular = midleft != pred || midleft < D || midleft + D > J.nx || index == (double)midleft ||
+                        !(fabs((index - (double)midleft) - tfl) < 1e-8);
+        }
+        unsigned mask = __ballot_sync(FULL_MASK, irregular);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int jb = __shfl_sync(FULL_MASK, job, src);
+            const long long jj = __shfl_sync(FULL_MASK, j, src);
+            const double idx = __shfl_sync(FULL_MASK, index, src);
+            const ResampleJob J = jobs[jb];
+            double v = sinc_interp_warp_ll(filt + J.filt_off - 1, J.nx, idx, D, lane);
+            if (lane == 0) out[J.out_off + jj - 1] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host driver
 static void plan_passes(int logn, int* cb, int* npass, int rbits[4]) {
     *cb = logn < 12 ? logn : 12;
@@ -302,13 +437,23 @@ void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int 
 }
 
 void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
-                          const int* d_table_rep, int ntables, const double* filt, double* table, double* out, int P, int D,
-                          double dx_src, cudaStream_t s, long long* launches) {
+                          const int* d_table_rep, int ntables, const int* d_tile_prefix, int total_tiles, const double* filt,
+                          double* table, double* out, int P, int Q, int D, double dx_src, cudaStream_t s, long long* launches) {
     double* table_fl = table + (size_t)ntables * (P > 0 ? P : 1) * 2 * D;      // stored behind the coefficient rows
-    if (P > 0 && ntables > 0) { k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, P, D, dx_src); (*launches)++; }
-    long long blocks = (total_out_hint + 7) / 8;
+    long long* table_mid = (long long*)(table_fl + (size_t)ntables * (P > 0 ? P : 1));
+    long long blocks = (total_out_hint + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    k_sinc_apply<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table, table_fl, out, P, D, dx_src);
-    (*launches)++;
+    if (P > 0 && ntables > 0 && total_tiles > 0) {
+        k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, table_mid, P, D, dx_src);
+        const int span = Q * (32 * FIR_R - 1) + 2 * D + 3 * Q + Q;               // upper bound of the tile span
+        const size_t smem = sizeof(double) * (size_t)Q * ((span + Q - 1) / Q + 4);
+        cudaFuncSetAttribute(k_sinc_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_sinc_fir<<<total_tiles, P * 32, smem, s>>>(d_jobs, d_tile_prefix, njobs, filt, table, table_mid, out, P, Q, D);
+        k_sinc_fixup<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table_fl, table_mid, out, P, Q, D, dx_src);
+        (*launches) += 3;
+    } else {
+        k_sinc_apply<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table, table_fl, out, 0, D, dx_src);
+        (*launches)++;
+    }
 }

@@ -324,14 +324,23 @@ struct ResamplePlan {
     std::vector<std::pair<int, int>> groups;   // (logn, count) in ids order
     std::vector<long long> out_prefix;
     std::vector<int> table_rep;
+    std::vector<int> tile_prefix;         // polyphase FIR tiles per job (exclusive scan)
+    int phases = 0, qstep = 0;
     long long ztotal = 0, ftotal = 0, ototal = 0;
 };
 
-static void finish_plan(ResamplePlan* P, bool share_tables_by_length) {
+static void finish_plan(ResamplePlan* P, bool share_tables_by_length, double fs, double fs_new) {
     const int nj = (int)P->jobs.size();
     std::map<int, std::vector<int>> bylog;
     std::map<long long, int> table_of_len;
     P->out_prefix.assign(nj + 1, 0);
+    P->tile_prefix.assign(nj + 1, 0);
+    {   // polyphase period of the rate change (16 kHz -> 10 kHz: 5 phases, input advances 8 samples per period)
+        long long a = (long long)llround(fs), b = (long long)llround(fs_new), gg = a, r = b;
+        while (r) { long long t = gg % r; gg = r; r = t; }
+        P->phases = (int)(b / gg); P->qstep = (int)(a / gg);
+        if (P->phases > 16 || P->qstep > 64) { P->phases = 0; P->qstep = 0; }
+    }
     for (int j = 0; j < nj; j++) {
         ResampleJob& J = P->jobs[j];
         int logn = ilog2_ceil(J.nx + 2000);
@@ -340,6 +349,10 @@ static void finish_plan(ResamplePlan* P, bool share_tables_by_length) {
         J.filt_off = P->ftotal; P->ftotal += J.nx;
         J.out_off = P->ototal; P->ototal += J.nout;
         P->out_prefix[j + 1] = P->out_prefix[j] + J.nout;
+        if (P->phases > 0) {
+            long long groups = (J.nout + P->phases - 1) / P->phases;
+            P->tile_prefix[j + 1] = P->tile_prefix[j] + (int)((groups + 32 * SINC_FIR_R - 1) / (32 * SINC_FIR_R));
+        }
         if (share_tables_by_length) {
             auto it = table_of_len.find(J.nx);
             if (it == table_of_len.end()) { it = table_of_len.emplace(J.nx, (int)P->table_rep.size()).first; P->table_rep.push_back(j); }
@@ -352,7 +365,7 @@ static void finish_plan(ResamplePlan* P, bool share_tables_by_length) {
     }
 }
 
-struct ResampleDev { ResampleJob* jobs; int* ids; long long* out_prefix; int* table_rep; double2* zbuf; double* filt; double* out; double* table; };
+struct ResampleDev { ResampleJob* jobs; int* ids; long long* out_prefix; int* table_rep; int* tile_prefix; double2* zbuf; double* filt; double* out; double* table; };
 
 static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, const int16_t* pcm, double fs, double fs_new,
                          int precision, cudaStream_t s) {
@@ -365,14 +378,9 @@ static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleD
         pos += g.second;
     }
     PE();
-    // polyphase period of the rate change (16 kHz -> 10 kHz: 5 phases)
-    long long a = (long long)llround(fs), b = (long long)llround(fs_new), gg = a, r = b;
-    while (r) { long long t = gg % r; gg = r; r = t; }
-    int phases = (int)(b / gg);
-    if (phases > 16) phases = 0;
     PB(precision >= 500 ? "  resample500: sinc interpolation" : "  resample50: sinc interpolation");
-    launch_sinc_resample(D.jobs, D.out_prefix, (int)P.jobs.size(), P.ototal, D.table_rep, (int)P.table_rep.size(), D.filt, D.table,
-                         D.out, phases, precision, dx, s, &h->launches);
+    launch_sinc_resample(D.jobs, D.out_prefix, (int)P.jobs.size(), P.ototal, D.table_rep, (int)P.table_rep.size(), D.tile_prefix,
+                         P.tile_prefix.back(), D.filt, D.table, D.out, P.phases, P.qstep, precision, dx, s, &h->launches);
     PE();
 }
 
@@ -383,6 +391,7 @@ static int upload_plan(mshds_handle* h, const ResamplePlan& P, const ResampleDev
     CK(cudaMemcpyAsync(D.ids, P.ids.data(), sizeof(int) * nj, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(D.out_prefix, P.out_prefix.data(), sizeof(long long) * (nj + 1), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(D.table_rep, P.table_rep.data(), sizeof(int) * P.table_rep.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(D.tile_prefix, P.tile_prefix.data(), sizeof(int) * (nj + 1), cudaMemcpyHostToDevice, s));
     return MSHDS_OK;
 }
 
@@ -458,7 +467,7 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
             S.pad = 0;
             fprefix[j + 1] = fprefix[j] + nFrames;
         }
-    finish_plan(&plan, false);
+    finish_plan(&plan, false, fs, fs10);
     const int totalFrames = fprefix[nsegs];
     const int nqmax = 513;
     // carve the CPP scratch
@@ -467,7 +476,8 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     size_t o_jobs = sz(sizeof(ResampleJob) * (nsegs + 1)), o_ids = sz(sizeof(int) * (nsegs + 1));
     size_t o_opre = sz(sizeof(long long) * (nsegs + 2)), o_trep = sz(sizeof(int) * (nsegs + 1));
     size_t o_z = sz(sizeof(double2) * (size_t)(plan.ztotal + 1)), o_filt = sz(sizeof(double) * (size_t)(plan.ftotal + 1));
-    size_t o_out = sz(sizeof(double) * (size_t)(plan.ototal + 1)), o_tab = sz(sizeof(double) * ((size_t)nsegs * (5 * 100 + 16) + 1));
+    size_t o_out = sz(sizeof(double) * (size_t)(plan.ototal + 1)), o_tab = sz(sizeof(double) * ((size_t)nsegs * (5 * 100 + 32) + 1));
+    size_t o_tile = sz(sizeof(int) * (nsegs + 2));
     size_t o_cseg = sz(sizeof(CepSeg) * (nsegs + 1)), o_fpre = sz(sizeof(int) * (nsegs + 2));
     size_t o_cep = sz(sizeof(double) * ((size_t)totalFrames * nqmax + 1)), o_cppf = sz(sizeof(double) * ((size_t)totalFrames + 1));
     if (need > h->cpp_cap) {
@@ -482,7 +492,7 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     ResampleDev D;
     D.jobs = (ResampleJob*)(B + o_jobs); D.ids = (int*)(B + o_ids); D.out_prefix = (long long*)(B + o_opre);
     D.table_rep = (int*)(B + o_trep); D.zbuf = (double2*)(B + o_z); D.filt = (double*)(B + o_filt); D.out = (double*)(B + o_out);
-    D.table = (double*)(B + o_tab);
+    D.table = (double*)(B + o_tab); D.tile_prefix = (int*)(B + o_tile);
     CepSeg* d_cseg = (CepSeg*)(B + o_cseg);
     int* d_fprefix = (int*)(B + o_fpre);
     double* d_cep = (double*)(B + o_cep);
@@ -632,12 +642,12 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     fplan.jobs.resize(n);
     for (int i = 0; i < n; i++)
         fill_resample_job(&fplan.jobs[i], off_host[i], lens[i], 1, lens[i], 0.5 * dx, (double)lens[i] * dx, fs10);
-    finish_plan(&fplan, true);
+    finish_plan(&fplan, true, fs, fs10);
     ResampleDev fdev;
     fdev.jobs = take<ResampleJob>(h, n); fdev.ids = take<int>(h, n); fdev.out_prefix = take<long long>(h, n + 1);
-    fdev.table_rep = take<int>(h, fplan.table_rep.size());
+    fdev.table_rep = take<int>(h, fplan.table_rep.size()); fdev.tile_prefix = take<int>(h, n + 1);
     fdev.zbuf = take<double2>(h, fplan.ztotal); fdev.filt = take<double>(h, fplan.ftotal); fdev.out = take<double>(h, fplan.ototal);
-    fdev.table = take<double>(h, fplan.table_rep.size() * (5 * 1000 + 16));
+    fdev.table = take<double>(h, fplan.table_rep.size() * (5 * 1000 + 32));
     FormantPass fm;
     memset(&fm, 0, sizeof fm);
     fm.jobs = fdev.jobs; fm.dt = 0.005; fm.dt_window = 2.0 * 0.025;
