@@ -478,22 +478,24 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
 // NUMimproveMaximum of candidate `imax` on the correlation row of frame f.  The 141 row values a sinc70 search can touch
 // are staged once per item in shared memory (the search evaluates the interpolation ~13 times); sinc700 candidates
 // (f > 0.3 fs, lag < 3.4) read the row directly.
+#define RF_NL 16            // lanes per refinement item: 70 taps per side = 5 per lane on 16 lanes (87 % slot use vs 73 % on
+                            // 32), and the Brent bookkeeping replicated per lane is issued once per TWO items
 __device__ __forceinline__ double refine_candidate(const SymRowY& y, int B, int imax, bool deep, double* st, double* xmid_out,
-                                                   int lane, const double2* __restrict__ tw) {
+                                                   int lane, unsigned mask, const double2* __restrict__ tw) {
     const int n = 2 * B + 1, c0 = imax + B + 1;
     double xmid, ymid;
     if (deep) {
-        ymid = improve_extremum_warp_t(y, n, c0, PEAK_SINC700, &xmid, true, lane, tw);
+        ymid = improve_extremum_warp_t(y, n, c0, PEAK_SINC700, &xmid, true, lane, tw, mask, RF_NL);
     } else {
         const int j0 = c0 - RF_HALF;
-        __syncwarp();
-        for (int j = lane; j < RF_WIN; j += 32) {
+        __syncwarp(mask);
+        for (int j = lane; j < RF_WIN; j += RF_NL) {
             int idx = j0 + j;
             st[j] = (idx >= 1 && idx <= n) ? y(idx) : 0.0;
         }
-        __syncwarp();
+        __syncwarp(mask);
         StagedY ys{st, j0};
-        ymid = improve_extremum_warp_t(ys, n, c0, PEAK_SINC70, &xmid, true, lane, tw);
+        ymid = improve_extremum_warp_t(ys, n, c0, PEAK_SINC70, &xmid, true, lane, tw, mask, RF_NL);
     }
     *xmid_out = xmid - (double)(B + 1);
     return ymid;
@@ -502,14 +504,16 @@ __device__ __forceinline__ double refine_candidate(const SymRowY& y, int B, int 
 // Sound_into_PitchFrame, second pass: NUMimproveMaximum with sinc(70/700) + Brent on the stored correlation row.  A flat,
 // perfectly balanced work list: one warp per queued (frame, candidate).
 __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
-    const int lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int nw = gridDim.x * (blockDim.x >> 5);
-    __shared__ double s_stage[8][RF_WIN];
-    double* st = s_stage[threadIdx.x >> 5];
+    __shared__ double s_stage[256 / RF_NL][RF_WIN];
+    const int lane = threadIdx.x & (RF_NL - 1);
+    const int grp = threadIdx.x / RF_NL;
+    const unsigned mask = RF_NL == 32 ? FULL_MASK : (((1u << RF_NL) - 1u) << ((threadIdx.x & 31) & ~(RF_NL - 1)));
+    double* st = s_stage[grp];
+    const int gg = blockIdx.x * (blockDim.x / RF_NL) + grp;
+    const int ng = gridDim.x * (blockDim.x / RF_NL);
     const int total = *p.qcount;
     const double dx = c.dx;
-    for (int q = gw; q < total; q += nw) {
+    for (int q = gg; q < total; q += ng) {
         const int item = p.queue[q];
         const int f = item >> 4, slot = item & 15;
         const int clip = find_segment(p.fstart, c.n, f);
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, c
         const int imax = p.cand_imax[o2];
         const double f0 = p.cand_f[o2];
         double xmid;
-        double ymid = refine_candidate(y, B, imax, f0 > 0.3 / dx, st, &xmid, lane, tw);
+        double ymid = refine_candidate(y, B, imax, f0 > 0.3 / dx, st, &xmid, lane, mask, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         if (lane == 0) { p.cand_f[o2] = 1.0 / dx / xmid; p.cand_s[o2] = ymid; }
     }
@@ -532,15 +536,17 @@ __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, c
 // Harmonicity variant: every maximum of every frame is an item (frame, lag, depth flag); the frame keeps the largest
 // refined strength among candidates that stay below the Nyquist "ceiling" (atomicMax on the bits of a positive double).
 __global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
-    const int lane = threadIdx.x & 31;
-    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
-    __shared__ double s_stage[8][RF_WIN];
-    double* st = s_stage[threadIdx.x >> 5];
+    __shared__ double s_stage[256 / RF_NL][RF_WIN];
+    const int lane = threadIdx.x & (RF_NL - 1);
+    const int grp = threadIdx.x / RF_NL;
+    const unsigned mask = RF_NL == 32 ? FULL_MASK : (((1u << RF_NL) - 1u) << ((threadIdx.x & 31) & ~(RF_NL - 1)));
+    double* st = s_stage[grp];
+    const long long gg = (long long)blockIdx.x * (blockDim.x / RF_NL) + grp;
+    const long long ng = (long long)gridDim.x * (blockDim.x / RF_NL);
     unsigned long long total = *p.qcount64;
     if (total > p.q64_cap) total = p.q64_cap;
     const double dx = c.dx;
-    for (long long q = gw; q < (long long)total; q += nw) {
+    for (long long q = gg; q < (long long)total; q += ng) {
         const unsigned long long item = p.queue64[q];
         const int f = (int)(item >> 32), imax = (int)((item >> 8) & 0xffffff);
         const bool deep = (item & 1ull) != 0;
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, con
         y.centre = B + 1;
         y.len = stored_lags(g);
         double xmid;
-        double ymid = refine_candidate(y, B, imax, deep, st, &xmid, lane, tw);
+        double ymid = refine_candidate(y, B, imax, deep, st, &xmid, lane, mask, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         const double fr = 1.0 / dx / xmid;
         if (lane == 0 && fr > 0.0 && fr < g.ceiling && ymid > 0.0)

@@ -45,9 +45,15 @@ struct StagedY {            // a window of the 1-based array staged in shared me
 };
 
 // y is 1-based: y(1..n) valid.  All 32 lanes must call with identical arguments; all lanes get the result.
+// A group of `nl` (32 or 16) adjacent lanes, all named in `mask`, cooperates; groups of one warp may diverge.
+__device__ __forceinline__ double group_sum(double v, unsigned mask, int nl) {
+    for (int o = nl >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
+
 template <class Y>
 __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x, int maxDepth, int lane,
-                                                     const double2* __restrict__ tw) {
+                                                     const double2* __restrict__ tw, unsigned mask = FULL_MASK, int nl = 32) {
     int midleft = (int)floor(x), midright = midleft + 1;
     if (n < 1) return DEVNAN;
     if (x > n) return y(n);
@@ -72,7 +78,7 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     const double hsl = 0.5 * cospi_tab(fabs(fl - 0.5), tw) * (1.0 / MSHDS_PI), hsr = hsl;
     double invl = __drcp_rn(fl + maxDepth), invr = __drcp_rn(fr + maxDepth);  // x-left+1 = fl + depth ; right-x+1 = fr + depth
     double accl = 0.0, accr = 0.0;
-    for (int k = lane; k < maxDepth; k += 32) {
+    for (int k = lane; k < maxDepth; k += nl) {
         double al = fl + k, ar = fr + k;                                    // in units of pi
         double dl = __drcp_rn(al) * (1.0 + cospi_tab(al * invl, tw));
         double dr = __drcp_rn(ar) * (1.0 + cospi_tab(ar * invr, tw));
@@ -81,7 +87,7 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
         accl = fma(yl, dl, accl);
         accr = fma(yr, dr, accr);
     }
-    return warp_sum(accl * hsl + accr * hsr);
+    return group_sum(accl * hsl + accr * hsr, mask, nl);
 }
 
 __device__ __forceinline__ double sinc_interp_warp(const double* y, int n, double x, int maxDepth, int lane,
@@ -94,14 +100,15 @@ __device__ __forceinline__ double sinc_interp_warp(const double* y, int n, doubl
 // (already sign-corrected: the interpolated y at the extremum).
 template <class Y>
 __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a, double b, int depth, bool isMaximum,
-                                                    double* fx_out, int lane, const double2* __restrict__ tw) {
+                                                    double* fx_out, int lane, const double2* __restrict__ tw,
+                                                    unsigned mask = FULL_MASK, int nl = 32) {
     const double golden = 1.0 - 0.6180339887498948482045868343656381177203;
     const double sqrt_epsilon = 1.4901161193847656e-08;   // sqrt(DBL_EPSILON)
     const double tol = 1e-10;
     const double sg = isMaximum ? -1.0 : 1.0;
     double x, v, fv, w, fw, fx;
     v = a + golden * (b - a);
-    fv = sg * sinc_interp_warp_t(y, n, v, depth, lane, tw);
+    fv = sg * sinc_interp_warp_t(y, n, v, depth, lane, tw, mask, nl);
     x = v; w = v;
     fx = fv; fw = fv;
     for (int iter = 1; iter <= 60; iter++) {
@@ -124,7 +131,7 @@ __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a,
         if (fabs(new_step) < tol_act) new_step = new_step > 0.0 ? tol_act : -tol_act;
         {
             double t = x + new_step;
-            double ft = sg * sinc_interp_warp_t(y, n, t, depth, lane, tw);
+            double ft = sg * sinc_interp_warp_t(y, n, t, depth, lane, tw, mask, nl);
             if (ft <= fx) {
                 if (t < x) b = x; else a = x;
                 v = w; w = x; x = t;
@@ -154,7 +161,8 @@ __device__ __forceinline__ double brent_sinc_warp_t(const Y& y, int n, double a,
 template <class Y>
 __device__ __forceinline__ double improve_extremum_warp_t(const Y& y, int n, int ixmid, int interpolation,
                                                           double* ixmid_real, bool isMaximum, int lane,
-                                                          const double2* __restrict__ tw) {
+                                                          const double2* __restrict__ tw, unsigned mask = FULL_MASK,
+                                                          int nl = 32) {
     if (ixmid <= 1) { *ixmid_real = 1; return y(1); }
     if (ixmid >= n) { *ixmid_real = n; return y(n); }
     if (interpolation <= PEAK_NONE) { *ixmid_real = ixmid; return y(ixmid); }
@@ -166,7 +174,7 @@ __device__ __forceinline__ double improve_extremum_warp_t(const Y& y, int n, int
     }
     double fx;
     *ixmid_real = brent_sinc_warp_t(y, n, (double)(ixmid - 1), (double)(ixmid + 1), interpolation == PEAK_SINC70 ? 70 : 700,
-                                    isMaximum, &fx, lane, tw);
+                                    isMaximum, &fx, lane, tw, mask, nl);
     return fx;
 }
 __device__ __forceinline__ double improve_extremum_warp(const double* y, int n, int ixmid, int interpolation,
