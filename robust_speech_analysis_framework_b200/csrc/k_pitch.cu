@@ -156,7 +156,41 @@ struct FrameSmem {      // byte offsets into dynamic shared memory (computed on 
     int nchunk_max;
 };
 
-#define CC_TL 4         // lags per thread in the cross-correlation inner loop
+
+// Forward cross-correlation products sum_j x[j] * x[j + lag] for lag = 1..Lmax over the window j < W.  A thread owns TL
+// consecutive lags and a chunk of the window: per step one new sample enters a sliding register window and feeds TL FMAs
+// (2 shared-memory loads per TL float64 FMAs).  Partial sums go to part[chunk][lag-1]; returns the number of chunks.
+template <int TL>
+__device__ __forceinline__ int cc_products(const double* xs, double* part, int PS, int W, int Lmax, int nchunk_max) {
+    const int tid = threadIdx.x;
+    const int ngroups = (Lmax + TL - 1) / TL;
+    int nchunk = ngroups > 0 ? NTHR / ngroups : 1;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > nchunk_max) nchunk = nchunk_max;
+    const int q = (W + nchunk - 1) / nchunk;
+    for (int wi = tid; wi < ngroups * nchunk; wi += NTHR) {
+        const int grp = wi % ngroups, ch = wi / ngroups;
+        const int lag0 = 1 + TL * grp;
+        const int j0 = ch * q, j1 = j0 + q < W ? j0 + q : W;
+        double acc[TL], yw[TL];
+        const double* xa = xs + j0;
+        const double* xb = xs + j0 + lag0;
+#pragma unroll
+        for (int u = 0; u < TL; u++) { acc[u] = 0.0; yw[u] = xb[u]; }
+        for (int j = 0; j < j1 - j0; j++) {
+            const double xv = xa[j];
+#pragma unroll
+            for (int u = 0; u < TL; u++) acc[u] = fma(xv, yw[u], acc[u]);
+#pragma unroll
+            for (int u = 0; u < TL - 1; u++) yw[u] = yw[u + 1];
+            yw[TL - 1] = xb[j + TL];
+        }
+        double* pr = part + (size_t)ch * PS + (lag0 - 1);
+#pragma unroll
+        for (int u = 0; u < TL; u++) pr[u] = acc[u];
+    }
+    return nchunk;
+}
 
 template <bool IS_CC>
 __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
@@ -269,7 +303,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             const int localMaximumLag = (int)(localSpan - W);
             const int Lmax = localMaximumLag > 0 ? localMaximumLag : 0;
             // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan; zero tail so the tiled loop may read ahead
-            const int xs_len = g.maximumLag + W + 8;
+            const int xs_len = g.maximumLag + W + 16;
             for (int j = tid; j < xs_len; j += NTHR) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
             for (int i = tid; i < 2 * B + 1; i += NTHR) S.rs0[i] = 0.0;
             for (int i = tid; i < Ls; i += NTHR) rrow[i] = 0.0;
@@ -297,29 +331,10 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
                 __syncthreads();
             }
             const double sumx2 = sq[W] - sq[0];
-            // products: work item = (group of CC_TL lags, chunk of the window)
-            const int ngroups = (Lmax + CC_TL - 1) / CC_TL;
-            int nchunk = ngroups > 0 ? NTHR / ngroups : 1;
-            if (nchunk < 1) nchunk = 1;
-            if (nchunk > L.nchunk_max) nchunk = L.nchunk_max;
-            const int q = (W + nchunk - 1) / nchunk;
-            for (int wi = tid; wi < ngroups * nchunk; wi += NTHR) {
-                const int grp = wi % ngroups, ch = wi / ngroups;
-                const int lag0 = 1 + CC_TL * grp;
-                const int j0 = ch * q, j1 = j0 + q < W ? j0 + q : W;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                const double* xa = xs + j0;
-                const double* xb = xs + j0 + lag0;
-                double y0 = xb[0], y1v = xb[1], y2 = xb[2];
-                for (int j = 0; j < j1 - j0; j++) {
-                    const double xv = xa[j];
-                    const double y3 = xb[j + 3];
-                    a0 = fma(xv, y0, a0); a1 = fma(xv, y1v, a1); a2 = fma(xv, y2, a2); a3 = fma(xv, y3, a3);
-                    y0 = y1v; y1v = y2; y2 = y3;
-                }
-                double* pr = part + (size_t)ch * PS + (lag0 - 1);
-                pr[0] = a0; pr[1] = a1; pr[2] = a2; pr[3] = a3;
-            }
+            // products: work item = (group of TL lags, chunk of the window); long windows use 8 lags per thread
+            int nchunk;
+            if (W >= 600) nchunk = cc_products<8>(xs, part, PS, W, Lmax, L.nchunk_max);
+            else nchunk = cc_products<4>(xs, part, PS, W, Lmax, L.nchunk_max);
             __syncthreads();
             for (int lag = 1 + tid; lag <= Lmax; lag += NTHR) {
                 double pr = 0.0;
@@ -410,7 +425,7 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     int ab = 0, rs = 0, ml = 0;
     for (int k = 0; k < 3; k++) {
         const PitchCfg& g = p.cfg[k];
-        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 16) : (int)sizeof(double2) * g.M;
+        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 24) : (int)sizeof(double2) * g.M;
         if (need_a > ab) ab = need_a;
         if (2 * g.brent_ixmax + 1 > rs) rs = 2 * g.brent_ixmax + 1;
         if (g.maximumLag > ml) ml = g.maximumLag;
@@ -431,8 +446,8 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     L.ckey2 = take((int)sizeof(double) * (MAXCAND + 1));
     L.cimax2 = take((int)sizeof(int) * (MAXCAND + 1));
     L.red = take((int)sizeof(double) * 32);
-    L.part_stride = (ml + 8 + 7) & ~7;
-    L.nchunk_max = 4;
+    L.part_stride = (ml + 16 + 7) & ~7;
+    L.nchunk_max = 8;
     // CC: nchunk_max rows of partial products + the prefix sums of squares (window + maximumLag + 1 entries)
     L.part = take(is_cc ? (int)sizeof(double) * (L.nchunk_max * L.part_stride + ab / (int)sizeof(double) + 8) : 16);
     L.pklag = take((int)sizeof(int) * MAXPK);
@@ -621,11 +636,18 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
 
     double delta = -1e300, lf = -1.0;
     int ncPrev = 0;
+    // software pipeline: the candidate row of frame i+1 is in flight while frame i is resolved
+    double nsc = -1e300, nclf = -1.0;
+    int nnc = p.ncand[f0];
+    if (lane < MAXCAND) { nsc = p.cand_score[(size_t)f0 * MAXCAND + lane]; nclf = p.cand_lf[(size_t)f0 * MAXCAND + lane]; }
     for (int i = 0; i < nF; i++) {
         const size_t fo = (size_t)(f0 + i);
-        const int nc = p.ncand[fo];
-        double sc = -1e300, clf = -1.0;
-        if (lane < MAXCAND) { sc = p.cand_score[fo * MAXCAND + lane]; clf = p.cand_lf[fo * MAXCAND + lane]; }
+        const int nc = nnc;
+        const double sc = nsc, clf = nclf;
+        if (i + 1 < nF) {
+            nnc = p.ncand[fo + 1];
+            if (lane < MAXCAND) { nsc = p.cand_score[(fo + 1) * MAXCAND + lane]; nclf = p.cand_lf[(fo + 1) * MAXCAND + lane]; }
+        }
         if (i == 0) {
             delta = sc; lf = clf; ncPrev = nc;
             continue;

@@ -125,19 +125,50 @@ __device__ double find_max_corr_warp(const WarpSound& S, double t1, double windo
     if (staged)
         for (long long i = lo + lane; i <= hi; i += 32) S.stage[i - lo] = (i >= 1 && i <= S.nx) ? samp(S.pcm, i - 1) : 0.0;
     __syncwarp();
+    // norm1 (the energy of the fixed window) is the same serial sum for every offset whose range is not clipped by the
+    // ends of the sound: it is accumulated once per lane (same order, same bits) and reused
+    double n1_full = 0.0;
+    bool have_n1 = false;
     for (int j = lane; j < m; j += 32) {
         const long long ileft2 = ileft2min + j;
         double norm1 = 0.0, norm2 = 0.0, product = 0.0, localPeak = 0.0;
-        for (long long k = 0; k < len; k++) {
-            long long i1 = ileft1 + k, i2 = ileft2 + k;
-            if (i1 < 1 || i1 > S.nx || i2 < 1 || i2 > S.nx) continue;
-            double amp1, amp2;
-            if (staged) { amp1 = S.stage[i1 - lo]; amp2 = S.stage[i2 - lo]; }
-            else { amp1 = samp(S.pcm, i1 - 1); amp2 = samp(S.pcm, i2 - 1); }
-            norm1 += amp1 * amp1;
-            norm2 += amp2 * amp2;
-            product += amp1 * amp2;
-            if (fabs(amp2) > localPeak) localPeak = fabs(amp2);
+        if (staged) {
+            long long kA = 0, kB = len - 1;
+            if (1 - ileft1 > kA) kA = 1 - ileft1;
+            if (1 - ileft2 > kA) kA = 1 - ileft2;
+            if (S.nx - ileft1 < kB) kB = S.nx - ileft1;
+            if (S.nx - ileft2 < kB) kB = S.nx - ileft2;
+            const double* p1 = S.stage + (ileft1 - lo);
+            const double* p2 = S.stage + (ileft2 - lo);
+            const bool full = kA == 0 && kB == len - 1;
+            if (full && have_n1) {
+                norm1 = n1_full;
+                for (long long k = 0; k < len; k++) {
+                    const double amp1 = p1[k], amp2 = p2[k];
+                    norm2 += amp2 * amp2;
+                    product += amp1 * amp2;
+                    localPeak = fmax(localPeak, fabs(amp2));
+                }
+            } else {
+                for (long long k = kA; k <= kB; k++) {
+                    const double amp1 = p1[k], amp2 = p2[k];
+                    norm1 += amp1 * amp1;
+                    norm2 += amp2 * amp2;
+                    product += amp1 * amp2;
+                    localPeak = fmax(localPeak, fabs(amp2));
+                }
+                if (full) { n1_full = norm1; have_n1 = true; }
+            }
+        } else {
+            for (long long k = 0; k < len; k++) {
+                long long i1 = ileft1 + k, i2 = ileft2 + k;
+                if (i1 < 1 || i1 > S.nx || i2 < 1 || i2 > S.nx) continue;
+                double amp1 = samp(S.pcm, i1 - 1), amp2 = samp(S.pcm, i2 - 1);
+                norm1 += amp1 * amp1;
+                norm2 += amp2 * amp2;
+                product += amp1 * amp2;
+                if (fabs(amp2) > localPeak) localPeak = fabs(amp2);
+            }
         }
         S.rbuf[j + 2] = product != 0.0 ? product / (sqrt(norm1 * norm2)) : 0.0;
         S.pbuf[j + 2] = localPeak;
