@@ -193,7 +193,7 @@ __device__ __forceinline__ int cc_products(const double* xs, double* part, int P
 }
 
 template <bool IS_CC>
-__global__ void __launch_bounds__(NTHR, IS_CC ? 3 : 4) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
+__global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)(smem + L.a);            // AC: packed FFT buffer; CC: xs[] doubles
     double* xs = (double*)(smem + L.a);

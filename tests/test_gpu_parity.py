@@ -221,3 +221,27 @@ def test_size_independent_properties_on_a_larger_batch(ex):
     for i in range(16, 64):
         assert np.array_equal(out[i], out[i % 16])
     assert np.all((out[:, 5] > 80) & (out[:, 5] < 260)) and np.all((out[:, 2] > 0.4) & (out[:, 2] <= 1.0))
+
+
+def test_long_clip_exercises_the_multi_pass_fft(ex, orc):
+    """A 70 s clip needs a 2^21-point low-pass FFT (two strided passes around the in-SM block kernel)."""
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    clip = synth_clip(400, 70.0).numpy()
+    got, st = ex.extract_host(clip, np.array([0, len(clip)], np.int64))
+    rs, _ = orc.resample(orc.pcm_to_float(clip), 16000.0, 10000.0, 500)
+    np.testing.assert_allclose(ex.debug_fetch("resampled10k", 0), rs, rtol=0, atol=1e-10)
+    want, wst = orc.extract(clip, np.array([0, len(clip)], np.int64), 16000.0)
+    assert_features_close(got, want, "70 s clip")
+    assert np.array_equal(st, wst)
+
+
+def test_many_short_clips_like_config_4(ex, orc):
+    """BASELINE.json configs[3] in miniature: 2 s clips (launch / packing stress); every row against the oracle."""
+    from robust_speech_analysis_framework_b200.synth import synth_batch
+    pcm, off = synth_batch(192, 2.0, start_index=500)
+    pcm, off = pcm.numpy(), off.numpy()
+    got, st = ex.extract_host(pcm, off)
+    want, wst = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
+    assert_features_close(got, want, "192 x 2 s")
+    assert np.array_equal(st, wst)
+    assert np.array_equal(got[:, SPEECHRATE], want[:, SPEECHRATE], equal_nan=True)
