@@ -106,7 +106,8 @@ void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s
 
 void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
-void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);   // + local scores
+void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
+void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
 void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones

@@ -331,10 +331,11 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
                 __syncthreads();
             }
             const double sumx2 = sq[W] - sq[0];
-            // products: work item = (group of TL lags, chunk of the window); long windows use 8 lags per thread
+            // products: work item = (group of TL lags, chunk of the window).  TL is odd so that the lag windows of adjacent
+            // lanes start TL doubles apart (an even stride would put the whole warp on 2-4 shared-memory banks)
             int nchunk;
-            if (W >= 600) nchunk = cc_products<8>(xs, part, PS, W, Lmax, L.nchunk_max);
-            else nchunk = cc_products<4>(xs, part, PS, W, Lmax, L.nchunk_max);
+            if (W >= 600) nchunk = cc_products<7>(xs, part, PS, W, Lmax, L.nchunk_max);
+            else nchunk = cc_products<5>(xs, part, PS, W, Lmax, L.nchunk_max);
             __syncthreads();
             for (int lag = 1 + tid; lag <= Lmax; lag += NTHR) {
                 double pr = 0.0;
@@ -614,8 +615,11 @@ __global__ void k_pitch_score(Clips c, PitchPass p) {
 }
 
 void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s) {
+    (void)max_frames_hint;
     if (p.hnr_mode) k_hnr_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
     else k_pitch_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
+}
+void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s) {
     int blocks = (max_frames_hint + 127) / 128;
     if (blocks < 1) blocks = 1;
     k_pitch_score<<<blocks, 128, 0, s>>>(c, p);

@@ -726,24 +726,28 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1; PE();
     launch_pitch_grid(c, srp, s); h->launches += 2;
     PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, srp, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, srp, s); h->launches += 1; PE();
     PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, s); h->launches += 1; PE();
 
     // ---- _pitch_values (:127-162): wide AC pass -> speaker class
     launch_pitch_grid(c, wide, s); h->launches += 2;
     PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, wide, h->tw, fhint, s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, wide, h->tw, fhint, s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, wide, fhint, s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, wide, s); h->launches += 1; PE();
     launch_pitch_class(c, wide, s); h->launches += 1;
 
     // ---- _extract_pitch (:164-183)
     launch_pitch_grid(c, mainp, s); h->launches += 2;
     PB("pitch_ac_frames[main + cpp vt=0.3]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, mainp, h->tw, fhint, s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, mainp, fhint, s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, mainp, s); h->launches += 1; PE();
     // the CPP pitch pass (:270) rides on the same correlation rows: refine its own candidates now, before rbuf is reused
-    PB("pitch_refine+score"); launch_pitch_refine(c, cpp_p, h->tw, fhint, s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, cpp_p, h->tw, fhint, s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, cpp_p, fhint, s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, s); h->launches += 1;
 
@@ -755,13 +759,15 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     // ---- _extract_harmonicity (:207-225)
     launch_pitch_grid(c, hnr, s); h->launches += 2;
     PB("pitch_cc_frames[hnr]"); launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, hnr, h->tw, fhint, s); h->launches += 2; PE();
+    PB("k_hnr_refine"); launch_pitch_refine(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, hnr, fhint, s); h->launches += 1; PE();
     launch_hnr_mean(c, hnr, s); h->launches += 1;
 
     // ---- _extract_Slope_Tilt (:227-251)
     launch_pitch_grid(c, ltp, s); h->launches += 2;
     PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, ltp, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, ltp, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, ltp, pl_lt, s); h->launches += 5; PE();
     PB("ltas"); launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5; PE();
@@ -771,7 +777,8 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     PB("formant_burg_frames"); launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3; PE();
     launch_pitch_grid(c, ccp, s); h->launches += 2;
     PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("pitch_refine+score"); launch_pitch_refine(c, ccp, h->tw, fhint, s); h->launches += 2; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, ccp, fhint, s); h->launches += 1; PE();
     PB("viterbi"); launch_pitch_viterbi(c, ccp, s); h->launches += 1; PE();
     PB("pulses"); launch_pulses(c, ccp, pl_fm, s); h->launches += 5; PE();
     launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
