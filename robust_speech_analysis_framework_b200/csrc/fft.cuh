@@ -9,6 +9,12 @@
 
 #define TW_N 8192          // table covers complex FFT sizes up to 8192
 
+// Shared-memory swizzle of the single-column transforms: complex element i lives at i ^ ((i >> 2) & 7).  The fused passes
+// touch elements 4t, 4t+1.. (late DIF / early DIT passes) or t, t+q.. (early passes); with 16-byte elements an unswizzled
+// layout puts a quarter-warp on 2-4 of the 8 bank groups, the XOR spreads every such pattern over all 8.
+#define SWZ(i) ((i) ^ (((i) >> 2) & 7))
+#define SWZD(m) ((SWZ((m) >> 1) << 1) | ((m) & 1))      // same for a flat float64 view of the buffer
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
 }
@@ -74,24 +80,24 @@ __device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __rest
         for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
             const int pos = t & (q - 1);
             const int i0 = (t / q) * 2 * half + pos;
-            double2 x0 = a[i0], x1 = a[i0 + q], x2 = a[i0 + half], x3 = a[i0 + half + q];
+            double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + q)], x2 = a[SWZ(i0 + half)], x3 = a[SWZ(i0 + half + q)];
             const double2 w1 = twiddle<SIGN>(tw, pos, 2 * half);
             const double2 w2 = twiddle<SIGN>(tw, pos, half);
             double2 s0 = cadd(x0, x2), d0 = cmul(csub(x0, x2), w1);
             double2 s1 = cadd(x1, x3), d1 = cmul(quarter_turn<SIGN>(csub(x1, x3)), w1);
-            a[i0] = cadd(s0, s1);
-            a[i0 + q] = cmul(csub(s0, s1), w2);
-            a[i0 + half] = cadd(d0, d1);
-            a[i0 + half + q] = cmul(csub(d0, d1), w2);
+            a[SWZ(i0)] = cadd(s0, s1);
+            a[SWZ(i0 + q)] = cmul(csub(s0, s1), w2);
+            a[SWZ(i0 + half)] = cadd(d0, d1);
+            a[SWZ(i0 + half + q)] = cmul(csub(d0, d1), w2);
         }
         __syncthreads();
         half >>= 2;
     }
     if (half == 1) {
         for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-            double2 u = a[2 * b], v = a[2 * b + 1];
-            a[2 * b] = cadd(u, v);
-            a[2 * b + 1] = csub(u, v);
+            double2 u = a[SWZ(2 * b)], v = a[SWZ(2 * b + 1)];
+            a[SWZ(2 * b)] = cadd(u, v);
+            a[SWZ(2 * b + 1)] = csub(u, v);
         }
         __syncthreads();
     }
@@ -103,9 +109,9 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
     int half = 1;
     if (logn & 1) {
         for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
-            double2 u = a[2 * b], v = a[2 * b + 1];
-            a[2 * b] = cadd(u, v);
-            a[2 * b + 1] = csub(u, v);
+            double2 u = a[SWZ(2 * b)], v = a[SWZ(2 * b + 1)];
+            a[SWZ(2 * b)] = cadd(u, v);
+            a[SWZ(2 * b + 1)] = csub(u, v);
         }
         __syncthreads();
         half = 2;
@@ -115,7 +121,7 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
         for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
             const int pos = t & (h - 1);
             const int i0 = (t / h) * 4 * h + pos;
-            double2 x0 = a[i0], x1 = a[i0 + h], x2 = a[i0 + 2 * h], x3 = a[i0 + 3 * h];
+            double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + h)], x2 = a[SWZ(i0 + 2 * h)], x3 = a[SWZ(i0 + 3 * h)];
             if (h > 1) {
                 const double2 wA = twiddle<SIGN>(tw, pos, 2 * h);
                 x1 = cmul(x1, wA);
@@ -124,10 +130,10 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
             const double2 wB = twiddle<SIGN>(tw, pos, 4 * h);
             double2 y0 = cadd(x0, x1), y1 = csub(x0, x1), y2 = cadd(x2, x3), y3 = csub(x2, x3);
             double2 u2 = cmul(y2, wB), u3 = cmul(quarter_turn<SIGN>(y3), wB);
-            a[i0] = cadd(y0, u2);
-            a[i0 + 2 * h] = csub(y0, u2);
-            a[i0 + h] = cadd(y1, u3);
-            a[i0 + 3 * h] = csub(y1, u3);
+            a[SWZ(i0)] = cadd(y0, u2);
+            a[SWZ(i0 + 2 * h)] = csub(y0, u2);
+            a[SWZ(i0 + h)] = cadd(y1, u3);
+            a[SWZ(i0 + 3 * h)] = csub(y1, u3);
         }
         __syncthreads();
         half <<= 2;
@@ -158,14 +164,14 @@ __device__ __forceinline__ void packed_power_to_inverse_input(double2* a, int M,
     int N = 2 * M;
     for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
         if (k == 0) {
-            double2 z0 = a[0];
+            double2 z0 = a[SWZ(0)];
             double p0 = f((z0.x + z0.y) * (z0.x + z0.y));
             double pM = f((z0.x - z0.y) * (z0.x - z0.y));
-            a[0] = make_double2(p0 + pM, p0 - pM);
+            a[SWZ(0)] = make_double2(p0 + pM, p0 - pM);
             if (pw) { pw[0] = p0; pw[M] = pM; }
         } else {
             int ik = bitrev(k, logM), imk = bitrev(M - k, logM);
-            double2 zk = a[ik], zmk = a[imk];
+            double2 zk = a[SWZ(ik)], zmk = a[SWZ(imk)];
             double2 wk = __ldg(tw + k * (TW_N / N));           // exp(-2 pi i k / N)
             double2 xk, xmk;
             real_bins_from_packed(zk, zmk, wk, &xk, &xmk);
@@ -179,8 +185,8 @@ __device__ __forceinline__ void packed_power_to_inverse_input(double2* a, int M,
             // w'^(M-k) = exp(2 pi i (M-k)/N) = exp(i pi) * conj(w'^k)... = -(wk.x + i wk.y) ; P diff = -d
             // i * (-(wk.x + i wk.y)) * (-d) = i (wk.x + i wk.y) d = (-wk.y d) + i (wk.x d)
             double2 ymk = make_double2(s - wk.y * d, wk.x * d);
-            a[ik] = yk;
-            if (imk != ik) a[imk] = ymk;
+            a[SWZ(ik)] = yk;
+            if (imk != ik) a[SWZ(imk)] = ymk;
         }
     }
     __syncthreads();

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
                 long long j = index + i;                                         // index - 1 + (i+1)
                 if (j >= 1 && j <= J.nout) v = j >= 2 ? y[j] - emphasis * y[j - 1] : y[j];
             }
-            ar[i] = v;
+            ar[SWZD(i)] = v;
             acc += v;
         }
         const double mean = block_sum(acc, red) / (double)nwin;                  // Vector_subtractMean
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
                 double d = (double)(i + 1) - imid;
                 w = (exp(-48.0 * d * d / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
             }
-            ar[i] = (ar[i] - mean) * w;
+            ar[SWZD(i)] = (ar[SWZD(i)] - mean) * w;
         }
         __syncthreads();
         fft_dif<-1>(a, M, tw);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
         double* row = cep + (size_t)f * nqmax;
         for (int i = threadIdx.x; i < nq; i += blockDim.x) {
             // c[i] for i <= M: natural order ar[i]; c[M] = ar[M] exists since M < nfft
-            double cv = ar[i];
+            double cv = ar[SWZD(i)];
             row[i] = cv * cv;
         }
     }

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
         const long long startSample = rightSample - p.halfnsamp_window;
         double* ar = (double*)a;
         for (int m = threadIdx.x; m < p.nsampFFT; m += blockDim.x)
-            ar[m] = m < p.nsamp_window ? samp(pcm, startSample + m - 1) * __ldg(p.window + m) : 0.0;
+            ar[SWZD(m)] = m < p.nsamp_window ? samp(pcm, startSample + m - 1) * __ldg(p.window + m) : 0.0;
         __syncthreads();
         fft_dif<-1>(a, p.M, tw);
         packed_power_to_inverse_input(a, p.M, p.logM, tw, IdentityF(), pw);

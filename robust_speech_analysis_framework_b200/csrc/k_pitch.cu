@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
                     int j = m + 1;
                     if (j >= pk0 && j <= pk1) lp = fmax(lp, fabs(v));
                 }
-                ar[m] = v;
+                ar[SWZD(m)] = v;
             }
         } else {
             for (int m = tid; m < W; m += NTHR) {
@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             packed_power_to_inverse_input(a, g.M, g.logM, tw, IdentityF(), (double*)nullptr);
             fft_dit<+1>(a, g.M, tw);
             const double* ac = (const double*)a;            // ac[i] natural order
-            const double ac0 = ac[0];
+            const double ac0 = ac[SWZD(0)];
             for (int i = tid; i <= B; i += NTHR) {
-                double v = i == 0 ? 1.0 : ac[i] / (ac0 * __ldg(g.windowR + i));
+                double v = i == 0 ? 1.0 : ac[SWZD(i)] / (ac0 * __ldg(g.windowR + i));
                 S.rs0[B + i] = v;
                 S.rs0[B - i] = v;
                 rrow[i] = v;

@@ -108,22 +108,22 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __rest
     const long long chunk = blockIdx.x % chunksPerJob;
     const ResampleJob J = jobs[ids[blockIdx.x / chunksPerJob]];
     double2* z = zbuf + J.zoff + chunk * Cn;
-    for (int e = threadIdx.x; e < Cn; e += RS_NTHR) a[e] = WHOLE ? make_double2(job_src(J, pcm, e), 0.0) : z[e];
+    for (int e = threadIdx.x; e < Cn; e += RS_NTHR) a[SWZ(e)] = WHOLE ? make_double2(job_src(J, pcm, e), 0.0) : z[e];
     __syncthreads();
     fft_dif<-1>(a, Cn, tw);
     const long long i0 = (long long)floor(upfactor * (double)N);
     for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
         long long pos = chunk * Cn + e;
         long long k = (long long)(__brevll((unsigned long long)pos) >> (64 - logn));
-        a[e] = apply_lowpass_mask(a[e], k, N, i0);
+        a[SWZ(e)] = apply_lowpass_mask(a[SWZ(e)], k, N, i0);
     }
     __syncthreads();
     fft_dit<+1>(a, Cn, tw);
     for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
         if (WHOLE) {
             long long i = (long long)e - ANTI_TURN;
-            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = a[e].x * (1.0 / (double)N);
-        } else z[e] = a[e];
+            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = a[SWZ(e)].x * (1.0 / (double)N);
+        } else z[e] = a[SWZ(e)];
     }
 }
 
