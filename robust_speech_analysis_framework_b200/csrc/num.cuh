@@ -78,10 +78,26 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     const double hsl = 0.5 * cospi_tab(fabs(fl - 0.5), tw) * (1.0 / MSHDS_PI), hsr = hsl;
     double invl = __drcp_rn(fl + maxDepth), invr = __drcp_rn(fr + maxDepth);  // x-left+1 = fl + depth ; right-x+1 = fr + depth
     double accl = 0.0, accr = 0.0;
-    for (int k = lane; k < maxDepth; k += nl) {
+    // window 1 + cos(pi*(f + k)/(f + depth)) for this lane's taps k = lane, lane + nl, ...: the angles advance by a constant
+    // step, so after two table look-ups per side the cosines follow the Chebyshev recurrence c[m+1] = 2 cos(step) c[m] - c[m-1]
+    const double stepl = (double)nl * invl, stepr = (double)nl * invr;
+    const bool rec = stepl <= 1.0 && stepr <= 1.0;
+    const double twocl = rec ? 2.0 * cospi_tab(stepl, tw) : 0.0, twocr = rec ? 2.0 * cospi_tab(stepr, tw) : 0.0;
+    double clm = 0.0, cl = 0.0, crm = 0.0, cr = 0.0;
+    int m = 0;
+    for (int k = lane; k < maxDepth; k += nl, m++) {
         double al = fl + k, ar = fr + k;                                    // in units of pi
-        double dl = __drcp_rn(al) * (1.0 + cospi_tab(al * invl, tw));
-        double dr = __drcp_rn(ar) * (1.0 + cospi_tab(ar * invr, tw));
+        double cln, crn;
+        if (!rec || m < 2) {
+            cln = cospi_tab(fmin(al * invl, 1.0), tw);
+            crn = cospi_tab(fmin(ar * invr, 1.0), tw);
+        } else {
+            cln = fma(twocl, cl, -clm);
+            crn = fma(twocr, cr, -crm);
+        }
+        clm = cl; cl = cln; crm = cr; cr = crn;
+        double dl = __drcp_rn(al) * (1.0 + cln);
+        double dr = __drcp_rn(ar) * (1.0 + crn);
         double yl = y(midleft - k), yr = y(midright + k);
         if (k & 1) { yl = -yl; yr = -yr; }
         accl = fma(yl, dl, accl);
