@@ -76,8 +76,10 @@ const char* mshds_last_error(const mshds_handle* h);
  * batch of mono recordings already decoded to 16-bit PCM (sample value = pcm / 32768, as parselmouth.Sound(path)
  * gives at :415).  Clip i is pcm[offsets[i] .. offsets[i+1]).  offsets is a HOST array of n_clips + 1 entries.
  * features: n_clips x 25 float64, row-major, column order as enum mshds_feature; status: n_clips words (may be NULL).
- * sample_rate must be 16000 (the reference resamples everything to 16 kHz first, :418-419; that front-end is the
- * caller's job in this version).  Returns MSHDS_OK or an error code; per-clip analysis failures are NOT errors.
+ * sample_rate is the rate of every clip of the call.  Anything but 16000 is first resampled to 16 kHz on the device exactly
+ * as the reference does (:418-419 snd.resample(16000, 50): FFT brick-wall low-pass when down-sampling, sinc depth 50), and the
+ * analyses then read the float64 result.  8000 Hz is refused with MSHDS_ERR_UNSUPPORTED (Praat switches to Sound_upsample
+ * for an exact doubling).  Returns MSHDS_OK or an error code; per-clip analysis failures are NOT errors.
  */
 int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
                   double* features, uint32_t* status, unsigned flags);

@@ -60,8 +60,10 @@ __host__ __device__ inline long long get_window_samples(double x1, double dx, lo
 }
 
 // ---- sample access: recordings stay int16 in HBM (2 B/sample); s = pcm/32768 exactly ---------------------------
-__device__ __forceinline__ double samp(const int16_t* __restrict__ pcm, long long i0 /*0-based*/) {
-    return (double)__ldg(pcm + i0) * (1.0 / 32768.0);
+// When the caller's audio is not at 16 kHz the front-end (Sound.resample(16000, 50), mshds_extractor.py:418-419) produces
+// float64 samples on the device and the same kernels read those instead (p64 != nullptr; the branch is warp-uniform).
+__device__ __forceinline__ double samp(const SPtr& s, long long i0 /*0-based*/) {
+    return s.p64 ? __ldg(s.p64 + i0) : (double)__ldg(s.p16 + i0) * (1.0 / 32768.0);
 }
 
 // ---- warp / block reductions (fixed order => run-to-run deterministic) ------------------------------------------

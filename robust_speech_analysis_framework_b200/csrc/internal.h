@@ -3,6 +3,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Sample source of the chunk: int16 PCM as delivered, or float64 after the 16 kHz front-end resampler.
+struct SPtr {
+    const int16_t* p16;
+    const double* p64;
+    __host__ __device__ SPtr operator+(long long o) const { return SPtr{p16 ? p16 + o : nullptr, p64 ? p64 + o : nullptr}; }
+    __host__ __device__ SPtr operator-(long long o) const { return SPtr{p16 ? p16 - o : nullptr, p64 ? p64 - o : nullptr}; }
+};
+
 #define MAXCAND 15             // Pitch candidates kept per frame for the Viterbi passes (incl. the voiceless one)
 
 // Per speaker-class configuration of one Sound_to_Pitch_any call (fon/Sound_to_Pitch.cpp set-up section).
@@ -60,9 +68,12 @@ struct PitchPass {
 
 struct Clips {
     int n;
-    const int16_t* pcm;        // packed int16 samples of the chunk
+    SPtr pcm;                  // packed samples of the chunk (int16, or float64 behind the resampling front-end)
     const long long* off;      // [n+1] sample offsets into pcm
     double fs, dx;
+    const double* x1;          // [n] time of the first sample of each clip (dx/2 for a file read as is; shifted behind the
+                               //     resampling front-end, where Praat centres the new samples in the old time domain)
+    const double* xmax;        // [n] end of the clip's time domain (n*dx for a file read as is; the ORIGINAL duration otherwise)
     double* mean;              // [n] mean sample value
     double* gpeak;             // [n] max |s - mean|   (Sound_to_Pitch_any globalPeak)
     double* apeak;             // [n] max |s|          (Sound_Pitch_to_PointProcess_cc globalPeak)
@@ -101,6 +112,7 @@ struct LtasPass {
 void launch_ltas(const Clips& c, const PulseSet& ps, const LtasPass& lt, double* ltas_bands /*[n*50]*/, cudaStream_t s);
 
 // ---- launchers (each in its own .cu) ----------------------------------------------------------------------------
+void launch_finalize_status(const Clips& c, cudaStream_t s);
 void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch /* n*16 bytes */, cudaStream_t s);
 void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s);
 
@@ -165,9 +177,10 @@ struct ResampleJob {
     double out_x1, out_dx;
     int table_id, pad;         // row block of the sinc coefficient table
 };
-void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, const int16_t* pcm, double2* zbuf,
+void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, SPtr pcm, double2* zbuf,
                                double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches);
 #define SINC_FIR_R 7        // outputs per thread of the polyphase FIR kernel (k_resample.cu FIR_R)
+void launch_resample_copy(const ResampleJob* d_jobs, int njobs, long long max_nx, SPtr pcm, double* filt, cudaStream_t s, long long* launches);
 void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
                           const int* d_table_rep /*[ntables] representative job per table*/, int ntables,
                           const int* d_tile_prefix /*[njobs+1] FIR tiles per job*/, int total_tiles, const double* filt,

@@ -18,8 +18,7 @@ __global__ void k_vuv_segments(Clips c, PulseSet ps, CppSegs sg, double maxT, do
     if (clip >= c.n) return;
     const double* t1b = ps.t + ps.cap_start[clip] - 1;           // 1-based pulses
     const int nt = ps.count[clip];
-    const long long nx = c.off[clip + 1] - c.off[clip];
-    const double dx = c.dx, x1 = 0.5 * dx, xmin = 0.0, xmax = (double)nx * dx;
+    const double dx = c.dx, x1 = c.x1[clip], xmin = 0.0, xmax = c.xmax[clip];
     const double halfMeanT = 0.5 * meanT;
     const int base = sg.cap_start[clip];
     const int cap = sg.cap_start[clip + 1] - base;

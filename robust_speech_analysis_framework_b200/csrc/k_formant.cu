@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) k_formant_stats(Clips c, FormantPass p, P
     const int clip = blockIdx.x;
     const double* t = ps.t + ps.cap_start[clip];
     const int np = ps.count[clip];
-    const double xmax = (double)(c.off[clip + 1] - c.off[clip]) * c.dx;
+    const double xmax = c.xmax[clip];
     double* feat = c.feat + (size_t)clip * N_FEAT + 13;
     const bool valid = p.nF[clip] >= 1 && ps.valid[clip];
     for (int q = 0; q < 4; q++) {

@@ -15,7 +15,7 @@ __global__ void k_intensity_grid(Clips c, IntensityPass p) {
     int k = p.class_dep ? c.cls[i] : 0;
     int nf = 0;
     double t1 = 0.0;
-    bool ok = nx > 0 && short_term_analysis(nx, c.dx, 0.5 * c.dx, 6.4 / p.min_pitch[k], p.dt, &nf, &t1) != 0;
+    bool ok = nx > 0 && short_term_analysis(nx, c.dx, c.x1[i], 6.4 / p.min_pitch[k], p.dt, &nf, &t1) != 0;
     p.nF[i] = ok ? nf : 0;
     p.t1[i] = t1;
 }
@@ -26,14 +26,15 @@ __global__ void __launch_bounds__(256) k_intensity_frames(Clips c, IntensityPass
     const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warpsPerBlock;
     const int total = p.fstart[c.n];
-    const double dx = c.dx, x1 = 0.5 * dx;
+    const double dx = c.dx;
     for (int f = gw; f < total; f += nwarps) {
         const int clip = find_segment(p.fstart, c.n, f);
+        const double x1 = c.x1[clip];
         const int kcls = p.class_dep ? c.cls[clip] : 0;
         const int halfN = p.halfN[kcls];
         const double* __restrict__ win = p.win[kcls] + halfN;       // win[i], i in [-halfN, halfN]
         const long long base = c.off[clip], nx = c.off[clip + 1] - base;
-        const int16_t* pcm = c.pcm + base;
+        const SPtr pcm = c.pcm + base;
         const double midTime = p.t1[clip] + (double)(f - p.fstart[clip]) * p.dt;
         const long long midSample = x_to_nearest(x1, dx, midTime);
         long long leftSample = midSample - halfN, rightSample = midSample + halfN;

@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(LW * 32) k_ltas_accum(Clips c, PulseSet ps, Lt
         const double* t1b = ps.t + ps.cap_start[clip] - 1;          // 1-based pulses
         const int nt = ps.count[clip];
         const long long nx = c.off[clip + 1] - c.off[clip];
-        const int16_t* pcm = c.pcm + c.off[clip];
-        const double dx = c.dx, x1 = 0.5 * dx;
+        const SPtr pcm = c.pcm + c.off[clip];
+        const double dx = c.dx, x1 = c.x1[clip];
         for (int b = lane; b < 2 * NBAND; b += 32) band[b] = 0.0;
         __syncwarp();
         int ip0 = 2 + part * LTAS_PART, ip1 = ip0 + LTAS_PART - 1;
@@ -155,7 +155,7 @@ __global__ void k_ltas_final(Clips c, PulseSet ps, LtasPass lt, double* ltas_ban
     double totalNumberOfEnergies = 0.0;
     for (int b = 0; b < NBAND; b++) totalNumberOfEnergies += cnt[b];
     if (totalNumberOfEnergies == 0.0) fail = true;          // no valid period / no energy in any bin
-    const double duration = (double)(c.off[clip + 1] - c.off[clip]) * c.dx;
+    const double duration = c.xmax[clip];                     // sound -> xmax - sound -> xmin
     if (!fail) {
         for (int b = 0; b < NBAND; b++) {
             if (cnt[b] == 0.0) z[b] = DEVNAN;

@@ -18,7 +18,7 @@ __global__ void k_spec_grid(Clips c, SpecPass p) {
     double t1 = 0.0;
     if (nx > 0 && !(p.physicalAnalysisWidth > duration)) {
         nf = 1 + (int)floor((duration - p.physicalAnalysisWidth) / p.timeStep);
-        t1 = 0.5 * c.dx + 0.5 * ((double)(nx - 1) * c.dx - (double)(nf - 1) * p.timeStep);
+        t1 = c.x1[i] + 0.5 * ((double)(nx - 1) * c.dx - (double)(nf - 1) * p.timeStep);
     }
     p.nF[i] = nf;
     p.t1[i] = t1;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
     double* red = pw + p.M + 8;
     __shared__ int s_clip, s_voiced;
     const int total = p.fstart[c.n];
-    const double dx = c.dx, x1 = 0.5 * dx;
+    const double dx = c.dx;
     for (int f = blockIdx.x; f < total; f += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
             PitchView pv;
             pv.f = pp.sel_f + pp.fstart[clip]; pv.nx = pp.nF[clip]; pv.x1 = pp.t1[clip];
             pv.dx = pp.cfg[c.cls[clip]].dt; pv.ceiling = pp.cfg[c.cls[clip]].ceiling;
-            pv.xmin = 0.0; pv.xmax = (double)(c.off[clip + 1] - c.off[clip]) * dx;
+            pv.xmin = 0.0; pv.xmax = c.xmax[clip];
             s_voiced = pv.nx >= 1 && !is_undef(pitch_value_at(pv, t));
         }
         __syncthreads();
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
             continue;
         }
         const int clip = s_clip;
-        const int16_t* pcm = c.pcm + c.off[clip];
+        const SPtr pcm = c.pcm + c.off[clip];
         const double t = p.t1[clip] + (double)(f - p.fstart[clip]) * p.timeStep;
-        const long long leftSample = x_to_low(x1, dx, t), rightSample = leftSample + 1;
+        const long long leftSample = x_to_low(c.x1[clip], dx, t), rightSample = leftSample + 1;
         const long long startSample = rightSample - p.halfnsamp_window;
         double* ar = (double*)a;
         for (int m = threadIdx.x; m < p.nsampFFT; m += blockDim.x)

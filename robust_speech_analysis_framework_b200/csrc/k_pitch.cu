@@ -28,7 +28,7 @@ __global__ void k_pitch_grid(Clips c, PitchPass p) {
     double t1 = 0.0;
     double duration = c.dx * (double)nx;
     bool ok = nx > 0 && !(g.floor_hz < g.ppw / duration) && g.halfnsamp_window >= 2;
-    if (ok) ok = short_term_analysis(nx, c.dx, 0.5 * c.dx, g.grid_window, g.dt, &nf, &t1) != 0;
+    if (ok) ok = short_term_analysis(nx, c.dx, c.x1[i], g.grid_window, g.dt, &nf, &t1) != 0;
     if (!ok) nf = 0;
     p.nF[i] = nf;
     p.t1[i] = t1;
@@ -221,7 +221,6 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
     const int tid = threadIdx.x;
     const int total = p.fstart[c.n];
     const double dx = c.dx;
-    const double x1 = 0.5 * dx;
 
     for (int f = blockIdx.x; f < total; f += gridDim.x) {
         __syncthreads();
@@ -235,8 +234,9 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         }
         __syncthreads();
         const int clip = fi->clip;
+        const double x1 = c.x1[clip];
         const PitchCfg& g = p.cfg[fi->cls];
-        const int16_t* pcm = c.pcm + fi->base;            // pcm[i-1] is 1-based sample i
+        const SPtr pcm = c.pcm + fi->base;                // pcm[i-1] is 1-based sample i
         const long long nx = fi->nx;
         const double t = p.t1[clip] + (double)fi->k * g.dt;
         const long long leftSample = x_to_low(x1, dx, t), rightSample = leftSample + 1;

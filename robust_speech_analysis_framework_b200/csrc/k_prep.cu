@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) k_stats_accum(Clips c, long long* sum, in
     const long long s0 = (long long)blockIdx.y * STAT_CHUNK;
     if (s0 >= nx) return;
     long long s1 = s0 + STAT_CHUNK < nx ? s0 + STAT_CHUNK : nx;
-    const int16_t* __restrict__ pcm = c.pcm + base;
+    const int16_t* __restrict__ pcm = c.pcm.p16 + base;
     long long acc = 0;
     int lo = INT_MAX, hi = INT_MIN;
     // 4-byte vector body when the clip start is 4-byte aligned, scalar otherwise
@@ -59,7 +59,29 @@ __global__ void k_stats_final(Clips c, const long long* sum, const int* mn, cons
 }
 
 
+// float64 samples (behind the resampling front-end): one CTA per clip, fixed-order reductions (deterministic)
+__global__ void __launch_bounds__(256) k_stats_f64(Clips c) {
+    __shared__ double red[32];
+    const int clip = blockIdx.x;
+    const long long base = c.off[clip], nx = c.off[clip + 1] - base;
+    const double* __restrict__ x = c.pcm.p64 + base;
+    if (threadIdx.x == 0) {
+        c.cls[clip] = 0; c.status[clip] = nx > 0 ? 0u : ST_FILE;
+        for (int k = 0; k < N_FEAT; k++) c.feat[(size_t)clip * N_FEAT + k] = DEVNAN;
+    }
+    double s = 0.0, ap = 0.0;
+    for (long long i = threadIdx.x; i < nx; i += blockDim.x) { double v = x[i]; s += v; ap = fmax(ap, fabs(v)); }
+    s = block_sum(s, red);
+    ap = block_max(ap, red);
+    const double mean = nx > 0 ? s / (double)nx : 0.0;
+    double gp = 0.0;
+    for (long long i = threadIdx.x; i < nx; i += blockDim.x) gp = fmax(gp, fabs(x[i] - mean));
+    gp = block_max(gp, red);
+    if (threadIdx.x == 0) { c.mean[clip] = mean; c.gpeak[clip] = nx > 0 ? gp : 0.0; c.apeak[clip] = nx > 0 ? ap : 0.0; }
+}
+
 void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch, cudaStream_t s) {
+    if (c.pcm.p64) { k_stats_f64<<<c.n, 256, 0, s>>>(c); return; }
     // scratch: n * (8 + 4 + 4) bytes
     long long* sum = (long long*)scratch;
     int* mn = (int*)(sum + c.n);
@@ -112,3 +134,11 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const int* __restrict__
 void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s) {
     k_exclusive_scan<<<1, 1024, 0, s>>>(counts, prefix, n);
 }
+
+// A recording that could not be loaded (empty, or too short to give one 16 kHz sample) is the reference's whole-file failure
+// (:450-457): its row is all NaN and no helper ran, so only MSHDS_ST_FILE is reported for it.
+__global__ void k_finalize_status(Clips c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.n && (c.status[i] & ST_FILE)) c.status[i] = ST_FILE;
+}
+void launch_finalize_status(const Clips& c, cudaStream_t s) { k_finalize_status<<<(c.n + 255) / 256, 256, 0, s>>>(c); }

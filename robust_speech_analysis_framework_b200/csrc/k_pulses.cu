@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) k_stretch_list(Clips c, PitchPass p, Puls
 
 // ------------------------------------------------------------------------------------------------ helpers
 struct WarpSound {
-    const int16_t* pcm;     // clip samples, pcm[i-1] = sample i
+    SPtr pcm;               // clip samples, pcm[i-1] = sample i
     long long nx;
     double x1, dx;
     double* stage;          // per-warp shared staging buffer [SPAN_MAX]
@@ -66,7 +66,7 @@ __device__ double find_extremum_warp(const WarpSound& S, double tmin, double tma
     if (imax > S.nx) imax = S.nx;
     long long n = imax - imin + 1;
     double iextremum;
-    const int16_t* ch = S.pcm + (imin - 1) - 1;           // ch[i], i = 1..n  -> sample imin-1+i
+    const SPtr ch = S.pcm + ((imin - 1) - 1);             // ch[i], i = 1..n  -> sample imin-1+i
     if (n < 3) {
         if (n <= 0) iextremum = 0.0;
         else if (n == 1) iextremum = 1.0;
@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(PW * 32) k_pulses_stretch(Clips c, PitchPass p
         WarpSound S;
         S.nx = c.off[clip + 1] - c.off[clip];
         S.pcm = c.pcm + c.off[clip];
-        S.dx = c.dx; S.x1 = 0.5 * c.dx;
+        S.dx = c.dx; S.x1 = c.x1[clip];
         S.stage = s_stage[wib]; S.rbuf = s_r[wib]; S.pbuf = s_p[wib];
-        pv.xmax = (double)S.nx * c.dx;
+        pv.xmax = c.xmax[clip];
         const double globalPeak = c.apeak[clip];
 
         double tleft = pv.x1 + (double)(ileft - 1) * pv.dx - 0.5 * pv.dx;

@@ -18,7 +18,7 @@
 #define TB 16                      // columns per CTA in the strided passes
 #define ANTI_TURN 1000             // Praat's antiTurnAround
 
-__device__ __forceinline__ double job_src(const ResampleJob& J, const int16_t* __restrict__ pcm, long long pos /*0-based in data*/) {
+__device__ __forceinline__ double job_src(const ResampleJob& J, const SPtr& pcm, long long pos /*0-based in data*/) {
     long long i = pos - (ANTI_TURN - 1);                 // data[antiTurnAround + i] = z[i], i = 1..nx
     if (i < 1 || i > J.nx) return 0.0;
     long long ic = J.ix1 + i - 1;                        // sample index within the clip (1-based); outside -> virtual zero
@@ -29,7 +29,7 @@ __device__ __forceinline__ double job_src(const ResampleJob& J, const int16_t* _
 // One strided DIF / DIT pass over blocks of length Nl = 2^nl: R = 2^rb point transforms at stride M = Nl / R.
 template <bool INVERSE, bool FIRST_FROM_SRC, bool LAST_TO_REAL>
 __global__ void __launch_bounds__(RS_NTHR) k_fft_strided(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
-                                                          const int16_t* __restrict__ pcm, double2* __restrict__ zbuf,
+                                                          SPtr pcm, double2* __restrict__ zbuf,
                                                           double* __restrict__ filt, const double2* __restrict__ tw,
                                                           int logn, int nl, int rb) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -97,7 +97,7 @@ __device__ __forceinline__ double2 apply_lowpass_mask(double2 v, long long k, lo
 // Innermost kernel: contiguous blocks of Cn = 2^cb points: forward DIF, mask, inverse DIT, all in shared memory.
 template <bool WHOLE>     // WHOLE: logn == cb (load from the source, write filtered reals)
 __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
-                                                        const int16_t* __restrict__ pcm, double2* __restrict__ zbuf,
+                                                        SPtr pcm, double2* __restrict__ zbuf,
                                                         double* __restrict__ filt, const double2* __restrict__ tw, int logn,
                                                         int cb, double upfactor) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -127,6 +127,23 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __rest
     }
 }
 
+// Up-sampling (upfactor >= 1) skips the low-pass: the interpolation reads the source samples themselves.
+__global__ void __launch_bounds__(256) k_copy_src(const ResampleJob* __restrict__ jobs, int njobs, SPtr pcm, double* __restrict__ filt) {
+    for (int jb = blockIdx.y; jb < njobs; jb += gridDim.y) {
+        const ResampleJob J = jobs[jb];
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < J.nx; i += (long long)gridDim.x * blockDim.x)
+            filt[J.filt_off + i] = job_src(J, pcm, i + ANTI_TURN);
+    }
+}
+void launch_resample_copy(const ResampleJob* d_jobs, int njobs, long long max_nx, SPtr pcm, double* filt, cudaStream_t s, long long* launches) {
+    if (njobs < 1) return;
+    long long bx = (max_nx + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    if (bx < 1) bx = 1;
+    k_copy_src<<<dim3((unsigned)bx, (unsigned)(njobs < 65535 ? njobs : 65535)), 256, 0, s>>>(d_jobs, njobs, pcm, filt);
+    (*launches)++;
+}
+
 // ------------------------------------------------------------------------------------------------ sinc interpolation
 // Coefficient table of NUM_interpolate_sinc for the P distinct fractional positions of a rational rate change.
 __global__ void k_sinc_table(const ResampleJob* __restrict__ jobs, const int* __restrict__ rep, int ntables,
@@ -136,12 +153,12 @@ __global__ void k_sinc_table(const ResampleJob* __restrict__ jobs, const int* __
     if (tab >= ntables) return;
     const ResampleJob J = jobs[rep[tab]];
     double* T = table + (size_t)tab * P * 2 * D;
-    if (threadIdx.x < P) {
-        long long j = (long long)(J.nout / 2 / P) * P + threadIdx.x + 1;
+    for (int ph = threadIdx.x; ph < P; ph += blockDim.x) {
+        long long j = (long long)(J.nout / 2 / P) * P + ph + 1;
         double x = J.out_x1 + (double)(j - 1) * J.out_dx;
         double index = (x - J.x1) / dx_src + 1.0;
-        table_fl[(size_t)tab * P + threadIdx.x] = index - floor(index);
-        table_mid[(size_t)tab * P + threadIdx.x] = (long long)floor(index);
+        table_fl[(size_t)tab * P + ph] = index - floor(index);
+        table_mid[(size_t)tab * P + ph] = (long long)floor(index);
     }
     for (int e = threadIdx.x; e < P * 2 * D; e += blockDim.x) {
         int ph = e / (2 * D), k = e % (2 * D);
@@ -382,7 +399,7 @@ static void plan_passes(int logn, int* cb, int* npass, int rbits[4]) {
 }
 
 // jobs of one FFT size: d_ids lists the job indices, cnt of them
-void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, const int16_t* pcm, double2* zbuf,
+void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, SPtr pcm, double2* zbuf,
                                double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches) {
     int cb, npass, rbits[4];
     plan_passes(logn, &cb, &npass, rbits);
@@ -439,12 +456,15 @@ void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int 
 void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,
                           const int* d_table_rep, int ntables, const int* d_tile_prefix, int total_tiles, const double* filt,
                           double* table, double* out, int P, int Q, int D, double dx_src, cudaStream_t s, long long* launches) {
+    // P <= 16 phases with Q <= 64: polyphase FIR kernel; more phases (44.1 kHz -> 16 kHz has 160): coefficient rows per phase
+    // but one warp per output sample; P == 0 (no short rational period): every sample evaluates the window itself.
+    const bool fir = P > 0 && P <= 16 && Q <= 64;
     double* table_fl = table + (size_t)ntables * (P > 0 ? P : 1) * 2 * D;      // stored behind the coefficient rows
     long long* table_mid = (long long*)(table_fl + (size_t)ntables * (P > 0 ? P : 1));
     long long blocks = (total_out_hint + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    if (P > 0 && ntables > 0 && total_tiles > 0) {
+    if (fir && ntables > 0 && total_tiles > 0) {
         k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, table_mid, P, D, dx_src);
         const int span = Q * (32 * FIR_R - 1) + 2 * D + 3 * Q + Q;               // upper bound of the tile span
         const size_t smem = sizeof(double) * (size_t)Q * ((span + Q - 1) / Q + 4);
@@ -453,7 +473,11 @@ void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_pref
         k_sinc_fixup<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table_fl, table_mid, out, P, Q, D, dx_src);
         (*launches) += 3;
     } else {
-        k_sinc_apply<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table, table_fl, out, 0, D, dx_src);
+        if (P > 0 && ntables > 0) {
+            k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, table_mid, P, D, dx_src);
+            (*launches)++;
+        }
+        k_sinc_apply<<<(unsigned)blocks, 256, 0, s>>>(d_jobs, d_out_prefix, njobs, filt, table, table_fl, out, ntables > 0 ? P : 0, D, dx_src);
         (*launches)++;
     }
 }

@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(SRW * 32) k_speechrate(Clips c, IntensityPass 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = ip.nF[clip];
     const long long nx = c.off[clip + 1] - c.off[clip];
-    const double xmin = 0.0, xmax = (double)nx * c.dx;
+    const double xmin = 0.0, xmax = c.xmax[clip], dur_nx = (double)nx * c.dx;
     double* feat = c.feat + (size_t)clip * N_FEAT;
     // Praat throws (-> five NaNs, :124-125) when: the default to_harmonicity_cc() at :36 cannot run (FCC, 75 Hz, ppw 1:
     // needs a sound of at least 2/75 s), the intensity analysis cannot run (6.4/50 s), or the pitch analysis cannot.
-    bool ok = n >= 1 && pp.nF[clip] >= 1 && !(2.0 / 75.0 > xmax) && !(75.0 < 1.0 / xmax);
+    bool ok = n >= 1 && pp.nF[clip] >= 1 && !(2.0 / 75.0 > dur_nx) && !(75.0 < 1.0 / dur_nx);
     if (!ok) {
         if (threadIdx.x == 0) atomicOr(&c.status[clip], ST_SPEECHRATE);
         return;

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 #include <utility>
@@ -50,6 +51,9 @@ struct mshds_handle {
     // growable scratch for the CPP stage (sized after the voiced-segment list is known)
     char* cpp_buf = nullptr;
     size_t cpp_cap = 0;
+    // scratch of the resample-to-16-kHz front-end
+    char* front_buf = nullptr;
+    size_t front_cap = 0;
     // arena
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -332,14 +336,14 @@ struct ResamplePlan {
 static void finish_plan(ResamplePlan* P, bool share_tables_by_length, double fs, double fs_new) {
     const int nj = (int)P->jobs.size();
     std::map<int, std::vector<int>> bylog;
-    std::map<long long, int> table_of_len;
+    std::map<std::tuple<long long, long long, double, double>, int> table_of_len;   // same geometry -> same coefficient rows
     P->out_prefix.assign(nj + 1, 0);
     P->tile_prefix.assign(nj + 1, 0);
     {   // polyphase period of the rate change (16 kHz -> 10 kHz: 5 phases, input advances 8 samples per period)
         long long a = (long long)llround(fs), b = (long long)llround(fs_new), gg = a, r = b;
         while (r) { long long t = gg % r; gg = r; r = t; }
         P->phases = (int)(b / gg); P->qstep = (int)(a / gg);
-        if (P->phases > 16 || P->qstep > 64) { P->phases = 0; P->qstep = 0; }
+        if (P->phases > 640) { P->phases = 0; P->qstep = 0; }     // no useful period: every output evaluates its own window
     }
     for (int j = 0; j < nj; j++) {
         ResampleJob& J = P->jobs[j];
@@ -349,13 +353,14 @@ static void finish_plan(ResamplePlan* P, bool share_tables_by_length, double fs,
         J.filt_off = P->ftotal; P->ftotal += J.nx;
         J.out_off = P->ototal; P->ototal += J.nout;
         P->out_prefix[j + 1] = P->out_prefix[j] + J.nout;
-        if (P->phases > 0) {
+        if (P->phases > 0 && P->phases <= 16 && P->qstep <= 64) {
             long long groups = (J.nout + P->phases - 1) / P->phases;
             P->tile_prefix[j + 1] = P->tile_prefix[j] + (int)((groups + 32 * SINC_FIR_R - 1) / (32 * SINC_FIR_R));
         }
         if (share_tables_by_length) {
-            auto it = table_of_len.find(J.nx);
-            if (it == table_of_len.end()) { it = table_of_len.emplace(J.nx, (int)P->table_rep.size()).first; P->table_rep.push_back(j); }
+            auto key = std::make_tuple(J.nx, J.nout, J.x1, J.out_x1);
+            auto it = table_of_len.find(key);
+            if (it == table_of_len.end()) { it = table_of_len.emplace(key, (int)P->table_rep.size()).first; P->table_rep.push_back(j); }
             J.table_id = it->second;
         } else { J.table_id = (int)P->table_rep.size(); P->table_rep.push_back(j); }
     }
@@ -367,13 +372,17 @@ static void finish_plan(ResamplePlan* P, bool share_tables_by_length, double fs,
 
 struct ResampleDev { ResampleJob* jobs; int* ids; long long* out_prefix; int* table_rep; int* tile_prefix; double2* zbuf; double* filt; double* out; double* table; };
 
-static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, const int16_t* pcm, double fs, double fs_new,
+static void run_resample(mshds_handle* h, const ResamplePlan& P, const ResampleDev& D, SPtr pcm, double fs, double fs_new,
                          int precision, cudaStream_t s) {
     const double dx = 1.0 / fs;
     const double upfactor = fs_new * dx;
     int pos = 0;
     PB(precision >= 500 ? "  resample500: fft low-pass" : "  resample50: fft low-pass");
-    for (auto& g : P.groups) {
+    if (upfactor >= 1.0) {
+        long long mx = 0;
+        for (auto& J : P.jobs) mx = J.nx > mx ? J.nx : mx;
+        launch_resample_copy(D.jobs, (int)P.jobs.size(), mx, pcm, D.filt, s, &h->launches);
+    } else for (auto& g : P.groups) {
         launch_resample_fft_group(D.jobs, D.ids + pos, g.second, g.first, pcm, D.zbuf, D.filt, h->tw, upfactor, s, &h->launches);
         pos += g.second;
     }
@@ -414,7 +423,7 @@ static int make_formant_window(mshds_handle* h, int nsw, const double** win) {
 // ------------------------------------------------------------------------------------------------ CPP stage
 // The voiced-segment list only exists on the device; one small read-back per chunk sizes the per-segment FFTs.
 static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long long>& off_host, const std::vector<long long>& lens,
-                         const CppSegs& sg, const std::vector<int>& scap, int* d_seg_prefix, double fs, cudaStream_t s) {
+                         const std::vector<double>& x1_host, const CppSegs& sg, const std::vector<int>& scap, int* d_seg_prefix, double fs, cudaStream_t s) {
     const int n = c.n;
     const double dx = 1.0 / fs, fs10 = 10000.0;
     std::vector<int> cnt(n);
@@ -444,7 +453,7 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
             const int src = scap[i] + k, j = sprefix[i] + k;
             // Sound_extractPart: xmin = 0, xmax = t2 - t1, x1 = my x1 + (ix1 - 1) dx - t1
             const double xmax = tmax[src] - tmin[src];
-            const double x1 = (0.5 * dx + (double)(ix1[src] - 1) * dx) - tmin[src];
+            const double x1 = (x1_host[i] + (double)(ix1[src] - 1) * dx) - tmin[src];
             fill_resample_job(&plan.jobs[j], off_host[i], lens[i], ix1[src], nseg[src], x1, xmax, fs10);
             // Sound_to_PowerCepstrogram set-up
             CepSeg& S = cseg[j];
@@ -518,7 +527,8 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
 }
 
 // ------------------------------------------------------------------------------------------------ one chunk
-static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vector<long long>& off_host, double fs,
+static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long long>& off_host, double fs,
+                         const std::vector<double>& x1_host, const std::vector<double>& xmax_host,
                          double* d_feat, uint32_t* d_status, bool dry_run) {
     cudaStream_t s = h->stream;
     const int n = (int)off_host.size() - 1;
@@ -536,6 +546,8 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     long long* d_off = take<long long>(h, n + 1);
     c.off = d_off;
     c.mean = take<double>(h, n); c.gpeak = take<double>(h, n); c.apeak = take<double>(h, n);
+    double* d_x1 = take<double>(h, n); double* d_xmax = take<double>(h, n);
+    c.x1 = d_x1; c.xmax = d_xmax;
     c.cls = take<int>(h, n);
     c.status = d_status; c.feat = d_feat;
     void* stat_scratch = arena_take(h, (size_t)n * 16);
@@ -641,7 +653,7 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     ResamplePlan fplan;
     fplan.jobs.resize(n);
     for (int i = 0; i < n; i++)
-        fill_resample_job(&fplan.jobs[i], off_host[i], lens[i], 1, lens[i], 0.5 * dx, (double)lens[i] * dx, fs10);
+        fill_resample_job(&fplan.jobs[i], off_host[i], lens[i], 1, lens[i], x1_host[i], xmax_host[i], fs10);
     finish_plan(&fplan, true, fs, fs10);
     ResampleDev fdev;
     fdev.jobs = take<ResampleJob>(h, n); fdev.ids = take<int>(h, n); fdev.out_prefix = take<long long>(h, n + 1);
@@ -713,6 +725,8 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     if (h->arena_overflow) { h->err = "internal: arena overflow after sizing"; return MSHDS_ERR_CUDA; }
 
     CK(cudaMemcpyAsync(d_off, off_host.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_x1, x1_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_xmax, xmax_host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_pcap, pcap.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(sg.cap_start, scap.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, s));
     if ((rc = upload_plan(h, fplan, fdev, s))) return rc;
@@ -786,11 +800,12 @@ static int process_chunk(mshds_handle* h, const int16_t* d_pcm, const std::vecto
     // ---- _extract_CPP (:253-301)
     PB("pulses"); launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5; PE();
     launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;
-    if ((rc = run_cpp_stage(h, c, off_host, lens, sg, scap, seg_prefix, fs, s))) return rc;
+    if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, s))) return rc;
 
     // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
     PB("spectrogram_moments"); launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4; PE();
 
+    launch_finalize_status(c, s); h->launches += 1;
     CK(cudaGetLastError());
 
     reg_debug(h, "pitch_wide_f", wide.sel_f, wide.fstart, wide.nF, 0, 8);
@@ -858,6 +873,7 @@ void mshds_destroy(mshds_handle* h) {
     for (auto& kv : h->gauss_spec) cudaFree(kv.second);
     for (auto& kv : h->gauss_formant) cudaFree(kv.second);
     cudaFree(h->cpp_buf);
+    cudaFree(h->front_buf);
     cudaFree(h->tw);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -884,14 +900,21 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     if (!h) return MSHDS_ERR_ARG;
     h->err.clear();
     if (n_clips < 0 || (n_clips > 0 && (!pcm || !offsets || !features))) { h->err = "null pointer argument"; return MSHDS_ERR_ARG; }
-    if (sample_rate != 16000) { h->err = "sample_rate must be 16000 (resample(16000, 50) front-end not built yet)"; return MSHDS_ERR_UNSUPPORTED; }
+    if (sample_rate < 4000 || sample_rate > 384000) { h->err = "sample_rate out of range"; return MSHDS_ERR_ARG; }
+    if (sample_rate == 8000) {
+        // Sound_resample switches to Sound_upsample (a different algorithm) when the rate exactly doubles
+        h->err = "8 kHz input (exact 2x up-sampling goes through Praat's Sound_upsample) is not supported yet";
+        return MSHDS_ERR_UNSUPPORTED;
+    }
     if (n_clips == 0) return MSHDS_OK;
     for (int i = 0; i < n_clips; i++)
         if (offsets[i + 1] < offsets[i]) { h->err = "offsets must be non-decreasing"; return MSHDS_ERR_ARG; }
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     const bool pcm_dev = flags & MSHDS_PCM_ON_DEVICE, out_dev = flags & MSHDS_OUT_ON_DEVICE;
-    const double fs = (double)sample_rate;
+    const double fs_in = (double)sample_rate;
+    const bool front = sample_rate != 16000;          // mshds_extractor.py:418-419  snd.resample(16000, 50)
+    const double fs = 16000.0;
 
     int c0 = 0;
     while (c0 < n_clips) {
@@ -903,14 +926,34 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             c1++;
         }
         const int n = c1 - c0;
-        std::vector<long long> off(n + 1);
-        for (int i = 0; i <= n; i++) off[i] = offsets[c0 + i] - offsets[c0];
+        std::vector<long long> off_in(n + 1);
+        for (int i = 0; i <= n; i++) off_in[i] = offsets[c0 + i] - offsets[c0];
+
+        // time domain of every clip as the analyses see it, and (front-end) the resample plan to 16 kHz
+        std::vector<long long> off(n + 1, 0);
+        std::vector<double> x1v(n), xmaxv(n);
+        ResamplePlan fe;
+        if (!front) {
+            off = off_in;
+            for (int i = 0; i < n; i++) { x1v[i] = 0.5 * (1.0 / fs); xmaxv[i] = (double)(off[i + 1] - off[i]) * (1.0 / fs); }
+        } else {
+            const double dx_in = 1.0 / fs_in;
+            fe.jobs.resize(n);
+            for (int i = 0; i < n; i++) {
+                const long long len = off_in[i + 1] - off_in[i];
+                fill_resample_job(&fe.jobs[i], off_in[i], len, 1, len, 0.5 * dx_in, (double)len * dx_in, fs);
+                if (len <= 0 || fe.jobs[i].nout < 1) fe.jobs[i].nout = 0;    // empty clip (or too short to give one sample): whole row NaN
+                x1v[i] = fe.jobs[i].out_x1; xmaxv[i] = (double)len * dx_in;
+            }
+            finish_plan(&fe, true, fs_in, fs);
+            for (int i = 0; i < n; i++) off[i + 1] = off[i] + fe.jobs[i].nout;
+        }
 
         // sizing pass, then (re)allocate the arena
         char* saved = h->arena;
         size_t saved_cap = h->arena_cap;
         h->arena = nullptr; h->arena_cap = 0;
-        int rc = process_chunk(h, nullptr, off, fs, nullptr, nullptr, true);
+        int rc = process_chunk(h, SPtr{nullptr, nullptr}, off, fs, x1v, xmaxv, nullptr, nullptr, true);
         h->arena = saved; h->arena_cap = saved_cap;
         if (rc) return rc;
         size_t need = h->arena_off + (pcm_dev ? 0 : (size_t)tot * 2 + 512) + (out_dev ? 0 : (size_t)n * (25 * 8 + 4) + 512) + 4096;
@@ -944,11 +987,47 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             tail = (tail - (size_t)n * 4 - 256) & ~(size_t)255;
             d_status = (uint32_t*)(h->arena + tail);
         }
+
+        SPtr src{d_pcm, nullptr};
+        const double* d_front_out = nullptr;
+        if (front) {
+            // ---- front-end: every clip -> 16 kHz float64 (FFT low-pass when down-sampling, sinc depth 50), own scratch
+            size_t fneed = 0;
+            auto sz = [&](size_t bytes) { size_t o = (fneed + 255) & ~(size_t)255; fneed = o + bytes; return o; };
+            size_t o_jobs = sz(sizeof(ResampleJob) * (n + 1)), o_ids = sz(sizeof(int) * (n + 1));
+            size_t o_opre = sz(sizeof(long long) * (n + 2)), o_trep = sz(sizeof(int) * (n + 1)), o_tile = sz(sizeof(int) * (n + 2));
+            size_t o_z = sz(sizeof(double2) * (size_t)(fe.ztotal + 1)), o_filt = sz(sizeof(double) * (size_t)(fe.ftotal + 1));
+            size_t o_out = sz(sizeof(double) * (size_t)(fe.ototal + 1));
+            size_t o_tab = sz(sizeof(double) * (fe.table_rep.size() * (size_t)((fe.phases > 0 ? fe.phases : 1) * 102 + 8) + 8));
+            if (fneed > h->front_cap) {
+                CK(cudaStreamSynchronize(s));
+                if (h->front_buf) CK(cudaFree(h->front_buf));
+                h->front_buf = nullptr; h->front_cap = 0;
+                CK(cudaMalloc((void**)&h->front_buf, fneed + (fneed >> 3)));
+                h->front_cap = fneed + (fneed >> 3);
+            }
+            char* B = h->front_buf;
+            ResampleDev D;
+            D.jobs = (ResampleJob*)(B + o_jobs); D.ids = (int*)(B + o_ids); D.out_prefix = (long long*)(B + o_opre);
+            D.table_rep = (int*)(B + o_trep); D.tile_prefix = (int*)(B + o_tile); D.zbuf = (double2*)(B + o_z);
+            D.filt = (double*)(B + o_filt); D.out = (double*)(B + o_out); D.table = (double*)(B + o_tab);
+            if ((rc = upload_plan(h, fe, D, s))) return rc;
+            PB("frontend_resample_to_16k[fft+sinc50]");
+            run_resample(h, fe, D, src, fs_in, fs, 50, s);
+            PE();
+            src = SPtr{nullptr, D.out};
+            d_front_out = D.out;
+        }
+
         size_t cap_saved = h->arena_cap;
         h->arena_cap = tail;                       // scratch may not run into the staging area
-        rc = process_chunk(h, d_pcm, off, fs, d_feat, d_status, false);
+        rc = process_chunk(h, src, off, fs, x1v, xmaxv, d_feat, d_status, false);
         h->arena_cap = cap_saved;
         if (rc) return rc;
+        if (front) {
+            reg_debug(h, "resampled16k", d_front_out, nullptr, nullptr, 0, 8);
+            h->debug["resampled16k"].host_prefix = fe.out_prefix;
+        }
         if (!out_dev) {
             CK(cudaMemcpyAsync(features + (size_t)c0 * 25, d_feat, (size_t)n * 25 * 8, cudaMemcpyDeviceToHost, s));
             if (status) CK(cudaMemcpyAsync(status + c0, d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, s));

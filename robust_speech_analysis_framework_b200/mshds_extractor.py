@@ -85,22 +85,23 @@ def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True,
     n = len(paths)
     feats = np.full((n, len(FEATURE_NAMES)), np.nan, dtype=np.float64)
 
-    batch_idx, batch_pcm, batch_samples = [], [], 0
+    # one open batch per sampling frequency: a device call takes clips of one rate (the library resamples to 16 kHz itself,
+    # the reference's snd.resample(16000, 50) of :418-419)
+    batches = {}
 
-    def flush():
-        nonlocal batch_idx, batch_pcm, batch_samples
+    def flush(fs):
+        batch_idx, batch_pcm, _ = batches.pop(fs, ([], [], 0))
         if not batch_idx:
             return
         offs = np.cumsum([0] + [len(p) for p in batch_pcm]).astype(np.int64)
         pcm = np.concatenate(batch_pcm) if batch_pcm else np.zeros(0, np.int16)
         try:
-            out, _status = ex.extract_host(pcm, offs, TARGET_RATE)
+            out, _status = ex.extract_host(pcm, offs, fs)
             feats[np.asarray(batch_idx)] = out
         except Exception as e:  # mirrors the whole-file handler at :450-457
             if verbose:
                 for i in batch_idx:
                     print(f"ERROR processing file '{filenames[i]}': {e}. Appending NaNs.")
-        batch_idx, batch_pcm, batch_samples = [], [], 0
 
     iterator = range(n)
     if verbose:
@@ -112,21 +113,20 @@ def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True,
     for i in iterator:
         try:
             pcm, fs = read_wav_mono_int16(paths[i])
-            if fs != TARGET_RATE:
-                # :418-419 snd.resample(16000, 50): front-end row of SURVEY 8f-2, not built in this round
-                raise AudioLoadError(f"sampling frequency {fs} Hz: only 16 kHz input is supported by the device path yet")
             if len(pcm) == 0:
                 raise AudioLoadError("empty sound")
         except Exception as e:
             if verbose:
                 print(f"ERROR processing file '{filenames[i]}': {e}. Appending NaNs.")
             continue
-        batch_idx.append(i)
-        batch_pcm.append(pcm)
-        batch_samples += len(pcm)
-        if batch_samples >= max_batch_seconds * TARGET_RATE:
-            flush()
-    flush()
+        b = batches.setdefault(fs, ([], [], 0))
+        b[0].append(i)
+        b[1].append(pcm)
+        batches[fs] = (b[0], b[1], b[2] + len(pcm))
+        if batches[fs][2] >= max_batch_seconds * fs:
+            flush(fs)
+    for fs in list(batches):
+        flush(fs)
 
     rows = []
     for i in range(n):

@@ -93,8 +93,14 @@ def test_wav_reader(tmp_path):
 
 class _FakeExtractor:
     """Stands in for the CUDA handle so the DataFrame / error-convention logic can be tested without a GPU."""
+    def __init__(self):
+        self.calls = []
+
     def extract_host(self, pcm, offsets, sample_rate=16000):
         n = len(offsets) - 1
+        self.calls.append((int(sample_rate), n))
+        if sample_rate == 8000:
+            raise RuntimeError("8 kHz input is not supported yet")      # what the library answers (MSHDS_ERR_UNSUPPORTED)
         out = np.zeros((n, 25))
         for i in range(n):
             seg = pcm[offsets[i]:offsets[i + 1]].astype(np.float64)
@@ -105,23 +111,30 @@ class _FakeExtractor:
 def test_dataframe_contract_matches_reference(tmp_path, monkeypatch, capsys):
     import pandas as pd
     from robust_speech_analysis_framework_b200 import mshds_extractor as mx
-    monkeypatch.setattr(mx, "get_extractor", lambda device=0: _FakeExtractor())
+    fake = _FakeExtractor()
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: fake)
     a, b = np.full(4000, 3, np.int16), np.full(2000, -5, np.int16)
     pa, pb = str(tmp_path / "s1" / "a.wav"), str(tmp_path / "b.wav")
     os.makedirs(os.path.dirname(pa))
     _write_wav(pa, a)
     _write_wav(pb, b)
     _write_wav(str(tmp_path / "c44.wav"), a, fs=44100)
-    df = pd.DataFrame({"other": [1, 2, 3, 4], "filepath": [pa, str(tmp_path / "nope.wav"), pb, str(tmp_path / "c44.wav")]})
+    _write_wav(str(tmp_path / "d8.wav"), b, fs=8000)
+    df = pd.DataFrame({"other": [1, 2, 3, 4, 5], "filepath": [pa, str(tmp_path / "nope.wav"), pb, str(tmp_path / "c44.wav"),
+                                                             str(tmp_path / "d8.wav")]})
     out = mx.extract_mshds_features(df, verbose=True)
     # mshds_extractor.py:240 smoke check shape (n, 26); column order :397-404; filename = basename (:410)
-    assert list(out.columns) == ["filename"] + mx.FEATURE_NAMES and out.shape == (4, 26)
-    assert list(out["filename"]) == ["a.wav", "nope.wav", "b.wav", "c44.wav"]
+    assert list(out.columns) == ["filename"] + mx.FEATURE_NAMES and out.shape == (5, 26)
+    assert list(out["filename"]) == ["a.wav", "nope.wav", "b.wav", "c44.wav", "d8.wav"]
     assert out.iloc[0]["Speaking_Rate"] == 12000.0 and out.iloc[2]["Spectral_Kurtosis"] == -10000.0 + 24
-    assert out.iloc[1][mx.FEATURE_NAMES].isna().all() and out.iloc[3][mx.FEATURE_NAMES].isna().all()
-    assert "ERROR processing file 'nope.wav'" in capsys.readouterr().out      # :452-453
+    # one device call per sampling frequency, each told its rate (the library does resample(16000, 50), :418-419)
+    assert sorted(fake.calls) == [(8000, 1), (16000, 2), (44100, 1)]
+    assert out.iloc[3]["Speaking_Rate"] == 12000.0
+    assert out.iloc[1][mx.FEATURE_NAMES].isna().all() and out.iloc[4][mx.FEATURE_NAMES].isna().all()
+    printed = capsys.readouterr().out
+    assert "ERROR processing file 'nope.wav'" in printed and "ERROR processing file 'd8.wav'" in printed     # :452-453
     quiet = mx.extract_mshds_features(df, verbose=False)
-    assert capsys.readouterr().out == "" and quiet.shape == (4, 26)
+    assert capsys.readouterr().out == "" and quiet.shape == (5, 26)
     assert out[mx.FEATURE_NAMES].dtypes.map(lambda d: d == np.float64).all()
     # custom column name (:379 audio_file_column)
     out2 = mx.extract_mshds_features(df.rename(columns={"filepath": "p"}), audio_file_column="p", verbose=False)
