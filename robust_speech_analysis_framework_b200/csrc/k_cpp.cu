@@ -8,6 +8,7 @@
 // One CTA per cepstrogram frame: mean removal, Gaussian window, packed real FFT-1024, log power and the inverse
 // transform stay in shared memory; a second kernel does the 5-frame / 10-bin box smoothing, the dB conversion, the
 // robust tilt line (medians by rank counting, no sort) and the parabolic peak per frame.
+#include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
 #include "fft.cuh"
@@ -307,6 +308,217 @@ __global__ void __launch_bounds__(256) k_cpp_frames(const CepSeg* __restrict__ s
     }
 }
 
+// ---- warp-per-frame variant (the usual 1024-point cepstrum: 513 quefrency bins) -----------------------------------------
+// The two medians of the robust line fit dominate the frame: 256 pair slopes and 513 residuals.  Here one warp owns a frame
+// and sorts in REGISTERS (8 / 16 values per lane, bitonic network: exchanges at distance < E stay inside a lane, the others
+// are one shuffle per value), so no block barrier is ever taken and eight frames advance independently per CTA.
+template <int E>
+__device__ __forceinline__ void warp_bitonic_sort(double (&v)[E], int lane) {
+    constexpr int LOGN = E == 8 ? 8 : 9;
+    static_assert(E == 8 || E == 16, "8 or 16 values per lane");
+#pragma unroll
+    for (int lk = 1; lk <= LOGN; lk++) {
+        const int k = 1 << lk;
+#pragma unroll
+        for (int lj = lk - 1; lj >= 0; lj--) {
+            const int j = 1 << lj;
+            if (j >= E) {
+                const int pl = j / E;
+                const bool up = ((lane * E) & k) == 0;
+                const bool keep_min = ((lane & pl) == 0) == up;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const double o = __shfl_xor_sync(FULL_MASK, v[e], pl);
+                    v[e] = ((o < v[e]) == keep_min) ? o : v[e];          // no NaNs here; on a tie either copy will do
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if ((e & j) == 0) {
+                        const bool up = (((lane * E) | e) & k) == 0;
+                        const double a = v[e], b = v[e | j];
+                        const bool sw = (a > b) == up;
+                        v[e] = sw ? b : a;
+                        v[e | j] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+}
+
+#define CPW 8                       // frames (warps) per CTA
+#define CPW_STRIDE 1048             // doubles of shared memory per warp: col[524] + y[524]
+__global__ void __launch_bounds__(32 * CPW, 2) k_cpp_frames_warp(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix,
+                                                                  int nsegs, const double* __restrict__ cep, int nqmax, int nTimeAvg,
+                                                                  double qAvgWindow, double peakLo, double peakHi, double qstartFit,
+                                                                  double qendFit, double* __restrict__ cpp_frame) {
+    extern __shared__ __align__(16) unsigned char cpw_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double* col = (double*)cpw_smem + (size_t)wid * CPW_STRIDE;       // time-averaged column, later the sorted values
+    double* y = col + CPW_STRIDE / 2;
+    const int total = fprefix[nsegs];
+    for (int f = blockIdx.x * CPW + wid; f < total; f += gridDim.x * CPW) {
+        __syncwarp();
+        const int sgi = find_segment(fprefix, nsegs, f);
+        const CepSeg S = segs[sgi];
+        const int f0 = fprefix[sgi], nFrames = fprefix[sgi + 1] - f0;
+        const int i1 = f - f0 + 1;                                               // 1-based frame
+        const int nq = S.nfft / 2 + 1;
+        const double dq = S.dq;
+        int jfrom = i1, jto = i1;
+        if (nTimeAvg > 1) {
+            jfrom = i1 - nTimeAvg / 2; jto = i1 + nTimeAvg / 2;
+            if ((nTimeAvg % 2) == 0) jto--;
+            if (jfrom < 1) jfrom = 1;
+            if (jto > nFrames) jto = nFrames;
+        }
+        if (jto - jfrom < 5) {
+            // up to five rows (the 0.01 s window at 2 ms steps): all loads of a bin are issued before the first addition;
+            // a row beyond jto contributes an exact 0.0 to the same left-to-right sum
+            const double* r0 = cep + (size_t)(f0 + jfrom - 1) * nqmax;
+            const int nrow = jto - jfrom + 1;
+#pragma unroll 2
+            for (int iq = lane; iq < nq; iq += 32) {
+                double r[5];
+#pragma unroll
+                for (int t = 0; t < 5; t++) r[t] = t < nrow ? __ldg(r0 + (size_t)t * nqmax + iq) : 0.0;
+                double s = 0.0;
+#pragma unroll
+                for (int t = 0; t < 5; t++) s += r[t];
+                col[iq] = nTimeAvg > 1 ? s / (double)nrow : s;
+            }
+        } else {
+            for (int iq = lane; iq < nq; iq += 32) {
+                double s = 0.0;
+                for (int j = jfrom; j <= jto; j++) s += __ldg(cep + (size_t)(f0 + j - 1) * nqmax + iq);
+                col[iq] = nTimeAvg > 1 ? s / (double)(jto - jfrom + 1) : s;
+            }
+        }
+        __syncwarp();
+        const int nQ = (int)floor(qAvgWindow / dq);
+        for (int iq = lane; iq < nq; iq += 32) {
+            double v;
+            if (nQ > 1) {
+                int i = iq + 1;
+                int qf = i - nQ / 2, qt = i + nQ / 2;
+                if ((nQ % 2) == 0) qt--;
+                if (qf < 1) qf = 1;
+                if (qt > nq) qt = nq;
+                double s = 0.0;
+                for (int j = qf; j <= qt; j++) s += col[j - 1];
+                v = s / (double)(qt - qf + 1);
+            } else v = col[iq];
+            y[iq] = 10.0 * log10(v + 1e-30);
+        }
+        __syncwarp();
+        double qlo = qstartFit, qhi = qendFit;
+        const double qmaxDom = dq * (double)(nq - 1);
+        if (qhi <= qlo) { qlo = 0.0; qhi = qmaxDom; }
+        long long imin, imax;
+        double cppv = DEVNAN;
+        if (get_window_samples(0.0, dq, nq, qlo, qhi, &imin, &imax) && imax - imin + 1 >= 2) {
+            const int npts = (int)(imax - imin + 1);
+            const double* yy = y + (imin - 1);
+            double slope, intercept;
+            if (npts == 2) {
+                slope = (yy[1] - yy[0]) / dq;
+                intercept = yy[0] - slope * ((double)(imin - 1) * dq);
+            } else {
+                const int numberOfPairs = npts / 2;
+                const int n2 = (npts % 2 == 1) ? numberOfPairs + 1 : numberOfPairs;
+                {   // median of the pair slopes (the order in which the values enter the network is irrelevant)
+                    double v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int i = e * 32 + lane;
+                        double xa = (double)(imin - 1 + i) * dq, xb = (double)(imin - 1 + n2 + i) * dq;
+                        v[e] = i < numberOfPairs ? (yy[n2 + i] - yy[i]) / (xb - xa) : CUDART_INF;
+                    }
+                    warp_bitonic_sort<8>(v, lane);
+                    if (numberOfPairs == 256) {
+                        const double a127 = __shfl_sync(FULL_MASK, v[7], 15), a128 = __shfl_sync(FULL_MASK, v[0], 16);
+                        slope = a128 == a127 ? a127 : a127 + 0.5 * (a128 - a127);     // NUMquantile (0.5): place 128.5
+                    } else {
+                        __syncwarp();
+#pragma unroll
+                        for (int e = 0; e < 8; e++) col[lane * 8 + e] = v[e];
+                        __syncwarp();
+                        slope = quantile_sorted(col, numberOfPairs, 0.5);
+                    }
+                }
+                {   // median of the residuals
+                    const bool pow2p1 = npts == 513;
+                    const int nsort = pow2p1 ? 512 : npts;
+                    double v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const int i = e * 32 + lane;
+                        v[e] = i < nsort ? yy[i] - slope * ((double)(imin - 1 + i) * dq) : CUDART_INF;
+                    }
+                    warp_bitonic_sort<16>(v, lane);
+                    if (pow2p1) {
+                        // 513 values: sort the first 512 and place the last one by comparison -- the median is a[255], e or a[256]
+                        const double lo = __shfl_sync(FULL_MASK, v[15], 15), hi = __shfl_sync(FULL_MASK, v[0], 16);
+                        const double e = yy[512] - slope * ((double)(imin - 1 + 512) * dq);
+                        intercept = e <= lo ? lo : (e >= hi ? hi : e);
+                    } else {
+                        __syncwarp();
+#pragma unroll
+                        for (int e = 0; e < 16; e++) col[lane * 16 + e] = v[e];
+                        __syncwarp();
+                        intercept = quantile_sorted(col, npts, 0.5);
+                    }
+                }
+            }
+            // PowerCepstrum_getMaximumAndQuefrency: Vector_getMaximumAndX (1/ceiling, 1/floor, parabolic)
+            double pk_v, pk_x;
+            {
+                long long pmin, pmax;
+                const double xlo = peakLo, xhi = peakHi;
+                if (!get_window_samples(0.0, dq, nq, xlo, xhi, &pmin, &pmax)) {
+                    double il = xlo / dq + 1.0, ir = xhi / dq + 1.0;
+                    int l0 = (int)floor(il), r0 = (int)floor(ir);
+                    double yl = (l0 >= 1 && l0 < nq) ? y[l0 - 1] + (il - l0) * (y[l0] - y[l0 - 1]) : y[nq - 1];
+                    double yr = (r0 >= 1 && r0 < nq) ? y[r0 - 1] + (ir - r0) * (y[r0] - y[r0 - 1]) : y[nq - 1];
+                    pk_v = yl > yr ? yl : yr;
+                    pk_x = yl == yr ? (xlo + xhi) / 2 : yl > yr ? xlo : xhi;
+                } else {
+                    const long long lo = pmin == 1 ? 2 : pmin, hi = pmax == nq ? nq - 1 : pmax;
+                    double bv = -CUDART_INF, bx = 0.0;
+                    int bo = 0x7fffffff;
+                    for (long long i = lo + lane; i <= hi; i += 32) {
+                        double yi = y[i - 1], ym = y[i - 2], yp = y[i];
+                        if (yi > ym && yi >= yp) {
+                            double dy = 0.5 * (yp - ym), d2y = 2 * yi - ym - yp;
+                            double loc = yi + 0.5 * dy * dy / d2y;
+                            int ord = 2 + (int)(i - lo);
+                            if (loc > bv || (loc == bv && ord < bo)) { bv = loc; bx = (double)i + dy / d2y; bo = ord; }
+                        }
+                    }
+                    if (lane == 0) {
+                        double e0 = y[pmin - 1], e1 = y[pmax - 1];
+                        double ev = e0, ex = (double)pmin;
+                        int eo = 0;
+                        if (e1 > ev) { ev = e1; ex = (double)pmax; eo = 1; }
+                        if (ev > bv || (ev == bv && eo < bo)) { bv = ev; bx = ex; bo = eo; }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(FULL_MASK, bv, o), ox = __shfl_xor_sync(FULL_MASK, bx, o);
+                        int oo = __shfl_xor_sync(FULL_MASK, bo, o);
+                        if (ov > bv || (ov == bv && oo < bo)) { bv = ov; bx = ox; bo = oo; }
+                    }
+                    double x = (bx - 1.0) * dq;
+                    if (x < xlo) x = xlo; else if (x > xhi) x = xhi;
+                    pk_v = bv; pk_x = x;
+                }
+            }
+            cppv = pk_v - (slope * pk_x + intercept);
+        }
+        if (lane == 0) cpp_frame[f] = cppv;
+    }
+}
+
 // CPPS per segment = mean over frames; clip value = mean of the segments with CPPS > 4 (mshds_extractor.py:293,298)
 __global__ void __launch_bounds__(128) k_cpp_reduce(Clips c, CppSegs sg, const int* __restrict__ seg_prefix,
                                                      const int* __restrict__ fprefix, const double* __restrict__ cpp_frame) {
@@ -349,6 +561,18 @@ void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const 
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {
     int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
     if (grid < 1) grid = 1;
+    static int use_block = -1;
+    if (use_block < 0) { const char* e = getenv("MSHDS_CPP_BLOCK"); use_block = e && atoi(e) ? 1 : 0; }    // development switch
+    if (nqmax <= 513 && !use_block) {
+        const size_t smem = sizeof(double) * CPW_STRIDE * CPW;
+        int g = (total_frames + CPW - 1) / CPW;
+        if (g > 148 * 2) g = 148 * 2;
+        if (g < 1) g = 1;
+        cudaFuncSetAttribute(k_cpp_frames_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_cpp_frames_warp<<<g, 32 * CPW, smem, s>>>(segs, fprefix, nsegs, cep, nqmax, nTimeAvg, qAvgWindow, 1.0 / 330.0, 1.0 / 60.0,
+                                                   0.001, 0.0, cpp_frame);
+        return;
+    }
     k_cpp_frames<<<grid, 256, 0, s>>>(segs, fprefix, nsegs, cep, nqmax, nTimeAvg, qAvgWindow, 1.0 / 330.0, 1.0 / 60.0, 0.001, 0.0,
                                       cpp_frame);
 }

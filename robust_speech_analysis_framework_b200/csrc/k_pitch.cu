@@ -9,6 +9,7 @@
 // One CTA per frame (persistent grid-stride loop over the flattened frame list of all clips): the frame is staged in
 // shared memory, transformed with the packed real FFT of fft.cuh (AC) or correlated directly (FCC), candidates are
 // refined warp-per-candidate, and only the <=15 candidates leave the SM.
+#include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
 #include "fft.cuh"
@@ -494,39 +495,43 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
 // NUMimproveMaximum of candidate `imax` on the correlation row of frame f.  The 141 row values a sinc70 search can touch
 // are staged once per item in shared memory (the search evaluates the interpolation ~13 times); sinc700 candidates
 // (f > 0.3 fs, lag < 3.4) read the row directly.
-#define RF_NL 16            // lanes per refinement item: 70 taps per side = 5 per lane on 16 lanes (87 % slot use vs 73 % on
-                            // 32), and the Brent bookkeeping replicated per lane is issued once per TWO items
+// Lanes per refinement item (template parameter NL).  70 taps per side: 18 per lane on 4 lanes, 9 on 8 (97 % slot use; the
+// per-evaluation table look-ups are amortised over the taps and the Brent bookkeeping replicated per lane is issued once per
+// 8 / 4 items), 5 per lane on 16 (87 %).
+template <int NL>
 __device__ __forceinline__ double refine_candidate(const SymRowY& y, int B, int imax, bool deep, double* st, double* xmid_out,
                                                    int lane, unsigned mask, const double2* __restrict__ tw) {
     const int n = 2 * B + 1, c0 = imax + B + 1;
     double xmid, ymid;
     if (deep) {
-        ymid = improve_extremum_warp_t(y, n, c0, PEAK_SINC700, &xmid, true, lane, tw, mask, RF_NL);
+        ymid = improve_extremum_warp_t(y, n, c0, PEAK_SINC700, &xmid, true, lane, tw, mask, NL);
     } else {
         const int j0 = c0 - RF_HALF;
         __syncwarp(mask);
-        for (int j = lane; j < RF_WIN; j += RF_NL) {
+        for (int j = lane; j < RF_WIN; j += NL) {
             int idx = j0 + j;
             st[j] = (idx >= 1 && idx <= n) ? y(idx) : 0.0;
         }
         __syncwarp(mask);
         StagedY ys{st, j0};
-        ymid = improve_extremum_warp_t(ys, n, c0, PEAK_SINC70, &xmid, true, lane, tw, mask, RF_NL);
+        ymid = improve_extremum_warp_t(ys, n, c0, PEAK_SINC70, &xmid, true, lane, tw, mask, NL);
     }
     *xmid_out = xmid - (double)(B + 1);
     return ymid;
 }
 
 // Sound_into_PitchFrame, second pass: NUMimproveMaximum with sinc(70/700) + Brent on the stored correlation row.  A flat,
-// perfectly balanced work list: one warp per queued (frame, candidate).
-__global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
-    __shared__ double s_stage[256 / RF_NL][RF_WIN];
-    const int lane = threadIdx.x & (RF_NL - 1);
-    const int grp = threadIdx.x / RF_NL;
-    const unsigned mask = RF_NL == 32 ? FULL_MASK : (((1u << RF_NL) - 1u) << ((threadIdx.x & 31) & ~(RF_NL - 1)));
+// perfectly balanced work list: one lane group per queued (frame, candidate).
+template <int NL>
+__global__ void __launch_bounds__(256, 3) k_pitch_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    double (*s_stage)[RF_WIN] = (double (*)[RF_WIN])rf_smem;
+    const int lane = threadIdx.x & (NL - 1);
+    const int grp = threadIdx.x / NL;
+    const unsigned mask = NL == 32 ? FULL_MASK : (((1u << NL) - 1u) << ((threadIdx.x & 31) & ~(NL - 1)));
     double* st = s_stage[grp];
-    const int gg = blockIdx.x * (blockDim.x / RF_NL) + grp;
-    const int ng = gridDim.x * (blockDim.x / RF_NL);
+    const int gg = blockIdx.x * (blockDim.x / NL) + grp;
+    const int ng = gridDim.x * (blockDim.x / NL);
     const int total = *p.qcount;
     const double dx = c.dx;
     for (int q = gg; q < total; q += ng) {
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, c
         const int imax = p.cand_imax[o2];
         const double f0 = p.cand_f[o2];
         double xmid;
-        double ymid = refine_candidate(y, B, imax, f0 > 0.3 / dx, st, &xmid, lane, mask, tw);
+        double ymid = refine_candidate<NL>(y, B, imax, f0 > 0.3 / dx, st, &xmid, lane, mask, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         if (lane == 0) { p.cand_f[o2] = 1.0 / dx / xmid; p.cand_s[o2] = ymid; }
     }
@@ -551,14 +556,16 @@ __global__ void __launch_bounds__(256, 4) k_pitch_refine(Clips c, PitchPass p, c
 
 // Harmonicity variant: every maximum of every frame is an item (frame, lag, depth flag); the frame keeps the largest
 // refined strength among candidates that stay below the Nyquist "ceiling" (atomicMax on the bits of a positive double).
-__global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
-    __shared__ double s_stage[256 / RF_NL][RF_WIN];
-    const int lane = threadIdx.x & (RF_NL - 1);
-    const int grp = threadIdx.x / RF_NL;
-    const unsigned mask = RF_NL == 32 ? FULL_MASK : (((1u << RF_NL) - 1u) << ((threadIdx.x & 31) & ~(RF_NL - 1)));
+template <int NL>
+__global__ void __launch_bounds__(256, 3) k_hnr_refine(Clips c, PitchPass p, const double2* __restrict__ tw) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    double (*s_stage)[RF_WIN] = (double (*)[RF_WIN])rf_smem;
+    const int lane = threadIdx.x & (NL - 1);
+    const int grp = threadIdx.x / NL;
+    const unsigned mask = NL == 32 ? FULL_MASK : (((1u << NL) - 1u) << ((threadIdx.x & 31) & ~(NL - 1)));
     double* st = s_stage[grp];
-    const long long gg = (long long)blockIdx.x * (blockDim.x / RF_NL) + grp;
-    const long long ng = (long long)gridDim.x * (blockDim.x / RF_NL);
+    const long long gg = (long long)blockIdx.x * (blockDim.x / NL) + grp;
+    const long long ng = (long long)gridDim.x * (blockDim.x / NL);
     unsigned long long total = *p.qcount64;
     if (total > p.q64_cap) total = p.q64_cap;
     const double dx = c.dx;
@@ -574,7 +581,7 @@ __global__ void __launch_bounds__(256, 4) k_hnr_refine(Clips c, PitchPass p, con
         y.centre = B + 1;
         y.len = stored_lags(g);
         double xmid;
-        double ymid = refine_candidate(y, B, imax, deep, st, &xmid, lane, mask, tw);
+        double ymid = refine_candidate<NL>(y, B, imax, deep, st, &xmid, lane, mask, tw);
         if (ymid > 1.0) ymid = 1.0 / ymid;
         const double fr = 1.0 / dx / xmid;
         if (lane == 0 && fr > 0.0 && fr < g.ceiling && ymid > 0.0)
@@ -616,8 +623,28 @@ __global__ void k_pitch_score(Clips c, PitchPass p) {
 
 void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s) {
     (void)max_frames_hint;
-    if (p.hnr_mode) k_hnr_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
-    else k_pitch_refine<<<148 * 4, 256, 0, s>>>(c, p, tw);
+    static int nl_env = -1;
+    if (nl_env < 0) {   // development switch; the defaults are what the committed measurements use
+        const char* e = getenv("MSHDS_RF_NL");
+        nl_env = e ? atoi(e) : 0;
+        if (nl_env != 4 && nl_env != 8 && nl_env != 16) nl_env = 0;
+    }
+    // measured on B200 (96 x 30 s): Viterbi passes 4 lanes 16.3 ms / 8 lanes 20.5 ms / 16 lanes 29.3 ms; harmonicity pass
+    // (a third of its items are 700-tap ones) 34.4 / 31.9 / 39.5 ms
+    const int nl = nl_env ? nl_env : (p.hnr_mode ? 8 : 4);
+    const int grid = 148 * 3;
+    const size_t smem = (size_t)(256 / nl) * RF_WIN * sizeof(double);
+#define RF_LAUNCH(K, N) \
+    do { \
+        cudaFuncSetAttribute(K<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        K<N><<<grid, 256, smem, s>>>(c, p, tw); \
+    } while (0)
+    if (p.hnr_mode) {
+        if (nl == 4) RF_LAUNCH(k_hnr_refine, 4); else if (nl == 8) RF_LAUNCH(k_hnr_refine, 8); else RF_LAUNCH(k_hnr_refine, 16);
+    } else {
+        if (nl == 4) RF_LAUNCH(k_pitch_refine, 4); else if (nl == 8) RF_LAUNCH(k_pitch_refine, 8); else RF_LAUNCH(k_pitch_refine, 16);
+    }
+#undef RF_LAUNCH
 }
 void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s) {
     int blocks = (max_frames_hint + 127) / 128;

@@ -39,6 +39,11 @@ struct DebugEntry {
 struct mshds_handle {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // latency-bound single-warp-per-clip kernels (Viterbi, pulse walks, interval logic) are issued on a side stream so that
+    // they run underneath the frame kernels of the next analysis; `cur` is the stream work is being issued on right now
+    cudaStream_t side = nullptr, cur = nullptr;
+    cudaEvent_t ev[12] = {};
+    bool overlap = true;
     std::string err;
     long long launches = 0;
     long long chunk_samples = 1LL << 27;
@@ -62,7 +67,7 @@ struct mshds_handle {
     int last_n = 0;
     // optional per-stage timing with CUDA events on the handle's stream
     bool prof_on = false;
-    struct ProfSpan { std::string name; cudaEvent_t a, b; };
+    struct ProfSpan { std::string name; cudaEvent_t a, b; cudaStream_t st; };
     std::vector<ProfSpan> prof_open;
     std::vector<std::string> prof_order;
     std::map<std::string, std::pair<double, long long>> prof_acc;    // name -> (ms, spans)
@@ -73,15 +78,16 @@ static void prof_begin(mshds_handle* h, const char* name) {
     mshds_handle::ProfSpan sp;
     sp.name = name;
     cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
-    cudaEventRecord(sp.a, h->stream);
+    cudaEventRecord(sp.a, h->cur);
+    sp.st = h->cur;
     h->prof_open.push_back(sp);
 }
 static void prof_end(mshds_handle* h) {
     if (!h->prof_on || h->prof_open.empty()) return;
     // close the most recent span that has not been closed yet
     for (size_t i = h->prof_open.size(); i-- > 0;) {
-        if (h->prof_open[i].name.empty() || h->prof_open[i].name[0] != '\x01') {
-            cudaEventRecord(h->prof_open[i].b, h->stream);
+        if ((h->prof_open[i].name.empty() || h->prof_open[i].name[0] != '\x01') && h->prof_open[i].st == h->cur) {
+            cudaEventRecord(h->prof_open[i].b, h->prof_open[i].st);
             h->prof_open[i].name.insert(h->prof_open[i].name.begin(), '\x01');
             return;
         }
@@ -600,17 +606,27 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     cs2.ncand = take<uint8_t>(h, fub5); cs2.psi = take<uint8_t>(h, fub5 * 16);
     cs2.imax = take<unsigned short>(h, fub5 * MAXCAND); cs2.inten = take<double>(h, fub5);
     cs2.queue = take<int>(h, fub5 * (MAXCAND - 1)); cs2.qcount = take<int>(h, 1);
-    alloc_pitch_pass(h, &wide, n, fub5, cs);
+    // A pass whose Viterbi runs on the side stream while the main stream already fills the next pass's candidates owns the
+    // arrays the path finder reads (f, s, score, lf, ncand, psi); the frame -> refine -> score scratch stays shared.
+    auto own_set = [&](long long fub) {
+        CandScratchBuf o = cs;
+        o.f = take<double>(h, fub * MAXCAND); o.s = take<double>(h, fub * MAXCAND);
+        o.score = take<double>(h, fub * MAXCAND); o.lf = take<double>(h, fub * MAXCAND);
+        o.ncand = take<uint8_t>(h, fub); o.psi = take<uint8_t>(h, fub * 16);
+        return o;
+    };
+    const CandScratchBuf cs_wide = own_set(fub5), cs_sr = own_set(fub20), cs_lt = own_set(fub75), cs_cc = own_set(fub5);
+    alloc_pitch_pass(h, &wide, n, fub5, cs_wide);
     alloc_pitch_pass(h, &mainp, n, fub5, cs);
-    alloc_pitch_pass(h, &hnr, n, fub5, cs);
+    alloc_pitch_pass(h, &hnr, n, fub5, cs_wide);          // no path finder; the wide pass is long finished by then
     // harmonicity: worst case one maximum every other lag (maximumLag / 2 per frame)
     hnr.q64_cap = (unsigned long long)fub5 * 136ull;
     hnr.queue64 = take<unsigned long long>(h, hnr.q64_cap);
     hnr.qcount64 = take<unsigned long long>(h, 1);
     hnr.best_bits = take<unsigned long long>(h, fub5);
-    alloc_pitch_pass(h, &srp, n, fub20, cs);
-    alloc_pitch_pass(h, &ltp, n, fub75, cs);
-    alloc_pitch_pass(h, &ccp, n, fub5, cs);
+    alloc_pitch_pass(h, &srp, n, fub20, cs_sr);
+    alloc_pitch_pass(h, &ltp, n, fub75, cs_lt);
+    alloc_pitch_pass(h, &ccp, n, fub5, cs_cc);
     alloc_pitch_pass(h, &cpp_p, n, fub5, cs2);
     // cpp_p reuses the frame grid of mainp (identical dt, floor, window)
     cpp_p.nF = mainp.nF; cpp_p.t1 = mainp.t1; cpp_p.fstart = mainp.fstart;
@@ -732,78 +748,115 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     if ((rc = upload_plan(h, fplan, fdev, s))) return rc;
     const int fhint = (int)(fub5 > 0x3fffffff ? 0x3fffffff : fub5);
 
-    // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
-    PB("clip_stats"); launch_clip_stats(c, maxlen, stat_scratch, s); h->launches += 3; PE();
+    // Two streams.  `s` carries everything that fills the GPU; `side` carries the kernels that are one warp (or thread) per
+    // clip and therefore latency-bound: Viterbi, glottal-pulse walks, interval logic.  SIDE(ev) makes the side stream wait for
+    // what `s` has issued so far and switches issue to it; MAIN() switches back; MARK(ev) records a point on the side stream
+    // that `s` can later WAIT(ev) for.  With MSHDS_NO_OVERLAP=1 everything is issued on `s` in the same order.
+    cudaStream_t side = h->overlap ? h->side : s;
+    cudaStream_t q = s;                          // stream the next launch goes to
+    h->cur = s;
+    int evn = 0;
+    auto SIDE = [&]() { if (side != s) { cudaEvent_t e = h->ev[evn++]; cudaEventRecord(e, s); cudaStreamWaitEvent(side, e, 0); } q = side; h->cur = side; };
+    auto MAIN = [&]() { q = s; h->cur = s; };
+    auto MARK = [&]() { cudaEvent_t e = h->ev[evn++]; if (side != s) cudaEventRecord(e, side); return e; };
+    auto WAIT = [&](cudaEvent_t e) { if (side != s) cudaStreamWaitEvent(s, e, 0); };
+    const int fhint20 = (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), fhint75 = (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75);
 
-    // ---- _speechrate (:11-125)
-    PB("intensity_sr"); launch_intensity(c, isr, (int)(fub16 > 0x3fffffff ? 0x3fffffff : fub16), s); h->launches += 3;
-    launch_contour_stats(c, isr, isr_stats, 1, s); h->launches += 1; PE();
-    launch_pitch_grid(c, srp, s); h->launches += 2;
-    PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
-    PB("k_pitch_refine"); launch_pitch_refine(c, srp, h->tw, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, srp, (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, srp, s); h->launches += 1; PE();
-    PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, s); h->launches += 1; PE();
+    // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
+    PB("clip_stats"); launch_clip_stats(c, maxlen, stat_scratch, q); h->launches += 3; PE();
 
     // ---- _pitch_values (:127-162): wide AC pass -> speaker class
-    launch_pitch_grid(c, wide, s); h->launches += 2;
-    PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_refine"); launch_pitch_refine(c, wide, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, wide, fhint, s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, wide, s); h->launches += 1; PE();
-    launch_pitch_class(c, wide, s); h->launches += 1;
+    launch_pitch_grid(c, wide, q); h->launches += 2;
+    PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, wide, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, wide, fhint, q); h->launches += 1; PE();
+    SIDE();
+    PB("viterbi"); launch_pitch_viterbi(c, wide, q); h->launches += 1; PE();
+    const cudaEvent_t ev_wide = MARK();
+    MAIN();
 
-    // ---- _extract_pitch (:164-183)
-    launch_pitch_grid(c, mainp, s); h->launches += 2;
-    PB("pitch_ac_frames[main + cpp vt=0.3]"); launch_pitch_frames(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_refine"); launch_pitch_refine(c, mainp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, mainp, fhint, s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, mainp, s); h->launches += 1; PE();
-    // the CPP pitch pass (:270) rides on the same correlation rows: refine its own candidates now, before rbuf is reused
-    PB("k_pitch_refine"); launch_pitch_refine(c, cpp_p, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, cpp_p, fhint, s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, s); h->launches += 1; PE();
-    launch_pitch_stats(c, mainp, s); h->launches += 1;
+    // ---- _speechrate (:11-125)
+    PB("intensity_sr"); launch_intensity(c, isr, (int)(fub16 > 0x3fffffff ? 0x3fffffff : fub16), q); h->launches += 3;
+    launch_contour_stats(c, isr, isr_stats, 1, q); h->launches += 1; PE();
+    launch_pitch_grid(c, srp, q); h->launches += 2;
+    PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, fhint20, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, srp, h->tw, fhint20, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, srp, fhint20, q); h->launches += 1; PE();
+    SIDE();
+    PB("viterbi"); launch_pitch_viterbi(c, srp, q); h->launches += 1; PE();
+    PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, q); h->launches += 1; PE();
+    MAIN();
+
+    WAIT(ev_wide);
+    launch_pitch_class(c, wide, q); h->launches += 1;
+
+    // ---- _extract_pitch (:164-183); the CPP pitch pass (:270) rides on the same frames and correlation rows
+    launch_pitch_grid(c, mainp, q); h->launches += 2;
+    PB("pitch_ac_frames[main + cpp vt=0.3]"); launch_pitch_frames(c, mainp, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, mainp, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, mainp, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, cpp_p, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, cpp_p, fhint, q); h->launches += 1; PE();
+    SIDE();
+    PB("viterbi"); launch_pitch_viterbi(c, mainp, q); h->launches += 1; PE();
+    launch_pitch_stats(c, mainp, q); h->launches += 1;
+    const cudaEvent_t ev_mainpitch = MARK();
+    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, q); h->launches += 1; PE();
+    // ---- _extract_CPP (:253-301), first half: pulses of the vt=0.3 pitch and the voiced intervals
+    PB("pulses"); launch_pulses(c, cpp_p, pl_cp, q); h->launches += 5; PE();
+    launch_vuv_segments(c, pl_cp, sg, q); h->launches += 1;
+    const cudaEvent_t ev_vuv = MARK();
+    MAIN();
 
     // ---- _extract_intensity (:185-205)
-    PB("intensity_main"); launch_intensity(c, imain, fhint, s); h->launches += 3;
-    launch_contour_stats(c, imain, imain_stats, 0, s); h->launches += 1; PE();
-    launch_intensity_features(c, imain, imain_stats, s); h->launches += 1;
+    PB("intensity_main"); launch_intensity(c, imain, fhint, q); h->launches += 3;
+    launch_contour_stats(c, imain, imain_stats, 0, q); h->launches += 1; PE();
+    launch_intensity_features(c, imain, imain_stats, q); h->launches += 1;
 
     // ---- _extract_harmonicity (:207-225)
-    launch_pitch_grid(c, hnr, s); h->launches += 2;
-    PB("pitch_cc_frames[hnr]"); launch_pitch_frames(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_hnr_refine"); launch_pitch_refine(c, hnr, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, hnr, fhint, s); h->launches += 1; PE();
-    launch_hnr_mean(c, hnr, s); h->launches += 1;
+    launch_pitch_grid(c, hnr, q); h->launches += 2;
+    PB("pitch_cc_frames[hnr]"); launch_pitch_frames(c, hnr, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_hnr_refine"); launch_pitch_refine(c, hnr, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, hnr, fhint, q); h->launches += 1; PE();
+    launch_hnr_mean(c, hnr, q); h->launches += 1;
 
     // ---- _extract_Slope_Tilt (:227-251)
-    launch_pitch_grid(c, ltp, s); h->launches += 2;
-    PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
-    PB("k_pitch_refine"); launch_pitch_refine(c, ltp, h->tw, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, ltp, (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75), s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, ltp, s); h->launches += 1; PE();
-    PB("pulses"); launch_pulses(c, ltp, pl_lt, s); h->launches += 5; PE();
-    PB("ltas"); launch_ltas(c, pl_lt, lt, ltas_bands, s); h->launches += 5; PE();
+    launch_pitch_grid(c, ltp, q); h->launches += 2;
+    PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, fhint75, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, ltp, h->tw, fhint75, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, ltp, fhint75, q); h->launches += 1; PE();
+    SIDE();
+    PB("viterbi"); launch_pitch_viterbi(c, ltp, q); h->launches += 1; PE();
+    PB("pulses"); launch_pulses(c, ltp, pl_lt, q); h->launches += 5; PE();
+    const cudaEvent_t ev_ltas = MARK();
+    MAIN();
 
     // ---- _measureFormants (:303-338)
-    PB("resample_clip_10k[fft+sinc500]"); run_resample(h, fplan, fdev, d_pcm, fs, fs10, 500, s); PE();
-    PB("formant_burg_frames"); launch_formants(c, fm, n, fdev.out, fhint, s); h->launches += 3; PE();
-    launch_pitch_grid(c, ccp, s); h->launches += 2;
-    PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_refine"); launch_pitch_refine(c, ccp, h->tw, fhint, s); h->launches += 1; PE();
-    PB("k_pitch_score"); launch_pitch_score(c, ccp, fhint, s); h->launches += 1; PE();
-    PB("viterbi"); launch_pitch_viterbi(c, ccp, s); h->launches += 1; PE();
-    PB("pulses"); launch_pulses(c, ccp, pl_fm, s); h->launches += 5; PE();
-    launch_formant_stats(c, fm, pl_fm, s); h->launches += 1;
-
-    // ---- _extract_CPP (:253-301)
-    PB("pulses"); launch_pulses(c, cpp_p, pl_cp, s); h->launches += 5; PE();
-    launch_vuv_segments(c, pl_cp, sg, s); h->launches += 1;
-    if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, s))) return rc;
+    PB("resample_clip_10k[fft+sinc500]"); run_resample(h, fplan, fdev, d_pcm, fs, fs10, 500, q); PE();
+    PB("formant_burg_frames"); launch_formants(c, fm, n, fdev.out, fhint, q); h->launches += 3; PE();
+    launch_pitch_grid(c, ccp, q); h->launches += 2;
+    PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_refine"); launch_pitch_refine(c, ccp, h->tw, fhint, q); h->launches += 1; PE();
+    PB("k_pitch_score"); launch_pitch_score(c, ccp, fhint, q); h->launches += 1; PE();
+    SIDE();
+    PB("viterbi"); launch_pitch_viterbi(c, ccp, q); h->launches += 1; PE();
+    PB("pulses"); launch_pulses(c, ccp, pl_fm, q); h->launches += 5; PE();
+    const cudaEvent_t ev_fmt = MARK();
+    MAIN();
 
     // ---- _extract_Spectral_Moments (:340-376); its pitch object is identical to _extract_pitch's
-    PB("spectrogram_moments"); launch_moments(c, spec, mainp, h->tw, fhint, s); h->launches += 4; PE();
+    WAIT(ev_mainpitch);
+    PB("spectrogram_moments"); launch_moments(c, spec, mainp, h->tw, fhint, q); h->launches += 4; PE();
+
+    WAIT(ev_ltas);
+    PB("ltas"); launch_ltas(c, pl_lt, lt, ltas_bands, q); h->launches += 5; PE();
+
+    // ---- _extract_CPP, second half (one small read-back, then resample / cepstrogram / CPPS of every voiced interval)
+    WAIT(ev_vuv);
+    if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, q))) return rc;
+
+    WAIT(ev_fmt);
+    launch_formant_stats(c, fm, pl_fm, q); h->launches += 1;
 
     launch_finalize_status(c, s); h->launches += 1;
     CK(cudaGetLastError());
@@ -848,6 +901,9 @@ int mshds_create(int device, mshds_handle** out) {
         return MSHDS_ERR_CUDA;
     }
     h->stream = h->own_stream;
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    for (auto& e : h->ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    { const char* e = getenv("MSHDS_NO_OVERLAP"); h->overlap = !(e && atoi(e)); }     // development switch
     // twiddle table exp(-2 pi i j / TW_N), j < TW_N/2
     const int TWN = 8192;
     std::vector<double> tw(TWN);
@@ -877,6 +933,8 @@ void mshds_destroy(mshds_handle* h) {
     cudaFree(h->tw);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side) cudaStreamDestroy(h->side);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
 }
 
@@ -911,6 +969,7 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
         if (offsets[i + 1] < offsets[i]) { h->err = "offsets must be non-decreasing"; return MSHDS_ERR_ARG; }
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
+    h->cur = s;
     const bool pcm_dev = flags & MSHDS_PCM_ON_DEVICE, out_dev = flags & MSHDS_OUT_ON_DEVICE;
     const double fs_in = (double)sample_rate;
     const bool front = sample_rate != 16000;          // mshds_extractor.py:418-419  snd.resample(16000, 50)

@@ -84,24 +84,39 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     const bool rec = stepl <= 1.0 && stepr <= 1.0;
     const double twocl = rec ? 2.0 * cospi_tab(stepl, tw) : 0.0, twocr = rec ? 2.0 * cospi_tab(stepr, tw) : 0.0;
     double clm = 0.0, cl = 0.0, crm = 0.0, cr = 0.0;
-    int m = 0;
-    for (int k = lane; k < maxDepth; k += nl, m++) {
-        double al = fl + k, ar = fr + k;                                    // in units of pi
-        double cln, crn;
+    // two taps per side and trip: the four divisions 1/(f + k) share ONE reciprocal (of the product of the four
+    // denominators, <= 71^4), the individual ones are recovered with multiplications
+    for (int k = lane, m = 0; k < maxDepth; k += 2 * nl, m += 2) {
+        const int k2 = k + nl;
+        const bool has2 = k2 < maxDepth;
+        const double al = fl + k, ar = fr + k;                              // in units of pi
+        const double al2 = has2 ? fl + k2 : 1.0, ar2 = has2 ? fr + k2 : 1.0;
+        double cl0, cr0, cl1, cr1;
         if (!rec || m < 2) {
-            cln = cospi_tab(fmin(al * invl, 1.0), tw);
-            crn = cospi_tab(fmin(ar * invr, 1.0), tw);
+            cl0 = cospi_tab(fmin(al * invl, 1.0), tw);
+            cr0 = cospi_tab(fmin(ar * invr, 1.0), tw);
+            cl1 = cospi_tab(fmin(al2 * invl, 1.0), tw);
+            cr1 = cospi_tab(fmin(ar2 * invr, 1.0), tw);
         } else {
-            cln = fma(twocl, cl, -clm);
-            crn = fma(twocr, cr, -crm);
+            cl0 = fma(twocl, cl, -clm);
+            cr0 = fma(twocr, cr, -crm);
+            cl1 = fma(twocl, cl0, -cl);
+            cr1 = fma(twocr, cr0, -cr);
         }
-        clm = cl; cl = cln; crm = cr; cr = crn;
-        double dl = __drcp_rn(al) * (1.0 + cln);
-        double dr = __drcp_rn(ar) * (1.0 + crn);
+        clm = cl0; cl = cl1; crm = cr0; cr = cr1;
+        const double p = al * ar, q = al2 * ar2;
+        const double r = __drcp_rn(p * q);
+        const double ip = q * r, iq = p * r;
+        const double dl = (ar * ip) * (1.0 + cl0), dr = (al * ip) * (1.0 + cr0);
+        const double dl2 = (ar2 * iq) * (1.0 + cl1), dr2 = (al2 * iq) * (1.0 + cr1);
         double yl = y(midleft - k), yr = y(midright + k);
+        double yl2 = has2 ? y(midleft - k2) : 0.0, yr2 = has2 ? y(midright + k2) : 0.0;
         if (k & 1) { yl = -yl; yr = -yr; }
+        if (k2 & 1) { yl2 = -yl2; yr2 = -yr2; }
         accl = fma(yl, dl, accl);
         accr = fma(yr, dr, accr);
+        accl = fma(yl2, dl2, accl);
+        accr = fma(yr2, dr2, accr);
     }
     return group_sum(accl * hsl + accr * hsr, mask, nl);
 }

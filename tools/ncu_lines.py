@@ -51,6 +51,8 @@ for r in rows[2:]:
 src = {}
 csrc = os.path.join(root, "robust_speech_analysis_framework_b200", "csrc")
 for fn in os.listdir(csrc):
+    if not os.path.isfile(os.path.join(csrc, fn)):
+        continue
     src[fn] = open(os.path.join(csrc, fn)).read().split("\n")
 print("total samples", tot, "total warp instructions", sum(inst.values()))
 for (fn, ln), n in agg.most_common(int(sys.argv[6]) if len(sys.argv) > 6 else 28):
