@@ -82,7 +82,7 @@ __device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __rest
             const int i0 = (t / q) * 2 * half + pos;
             double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + q)], x2 = a[SWZ(i0 + half)], x3 = a[SWZ(i0 + half + q)];
             const double2 w1 = twiddle<SIGN>(tw, pos, 2 * half);
-            const double2 w2 = twiddle<SIGN>(tw, pos, half);
+            const double2 w2 = cmul(w1, w1);                  // exp(i a)^2 instead of a second table look-up
             double2 s0 = cadd(x0, x2), d0 = cmul(csub(x0, x2), w1);
             double2 s1 = cadd(x1, x3), d1 = cmul(quarter_turn<SIGN>(csub(x1, x3)), w1);
             a[SWZ(i0)] = cadd(s0, s1);
@@ -122,12 +122,12 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
             const int pos = t & (h - 1);
             const int i0 = (t / h) * 4 * h + pos;
             double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + h)], x2 = a[SWZ(i0 + 2 * h)], x3 = a[SWZ(i0 + 3 * h)];
+            const double2 wB = twiddle<SIGN>(tw, pos, 4 * h);
             if (h > 1) {
-                const double2 wA = twiddle<SIGN>(tw, pos, 2 * h);
+                const double2 wA = cmul(wB, wB);
                 x1 = cmul(x1, wA);
                 x3 = cmul(x3, wA);
             }
-            const double2 wB = twiddle<SIGN>(tw, pos, 4 * h);
             double2 y0 = cadd(x0, x1), y1 = csub(x0, x1), y2 = cadd(x2, x3), y3 = csub(x2, x3);
             double2 u2 = cmul(y2, wB), u3 = cmul(quarter_turn<SIGN>(y3), wB);
             a[SWZ(i0)] = cadd(y0, u2);

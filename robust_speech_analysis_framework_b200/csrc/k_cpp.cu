@@ -10,6 +10,7 @@
 // robust tilt line (medians by rank counting, no sort) and the parabolic peak per frame.
 #include <cstdlib>
 #include "internal.h"
+#define NT_CEP_DEFAULT 128
 #include "common.cuh"
 #include "fft.cuh"
 
@@ -552,10 +553,13 @@ void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, 
 void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
                         const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames,
                         const double* wtab, int wtab_n, cudaStream_t s) {
-    int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
+    static int nt = 0;
+    if (!nt) { const char* e = getenv("MSHDS_NT_CEP"); nt = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : NT_CEP_DEFAULT); }   // development switch
+    const int cap = nt == 128 ? 148 * 12 : 148 * 8;
+    int grid = total_frames < cap ? total_frames : cap;
     if (grid < 1) grid = 1;
     size_t smem = sizeof(double2) * 512 + sizeof(double) * 32;
-    k_cepstrogram<<<grid, 256, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax, wtab, wtab_n);
+    k_cepstrogram<<<grid, nt, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax, wtab, wtab_n);
 }
 void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {

@@ -4,7 +4,9 @@
 // Serves _extract_Spectral_Moments (mshds_extractor.py:355-374).  The reference materialises a 320-bin spectrogram and
 // walks it frame by frame from Python; here one CTA owns one spectrogram frame: window, packed real FFT-1024, 320 power
 // bins and the four moments never leave shared memory, and only 4 doubles per voiced frame are written.
+#include <cstdlib>
 #include "internal.h"
+#define NT_SPEC_DEFAULT 128
 #include "common.cuh"
 #include "fft.cuh"
 #include "pitchq.cuh"
@@ -124,6 +126,9 @@ void launch_moments(const Clips& c, const SpecPass& p, const PitchPass& pp, cons
     if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
     if (grid < 1) grid = 1;
     cudaFuncSetAttribute(k_spec_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_spec_frames<<<grid, 256, smem, s>>>(c, p, pp, tw);
+    static int nt = 0;
+    if (!nt) { const char* e = getenv("MSHDS_NT_SPEC"); nt = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : NT_SPEC_DEFAULT); }   // development switch
+    if (nt == 128) { grid = 148 * 12; if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint; if (grid < 1) grid = 1; }
+    k_spec_frames<<<grid, nt, smem, s>>>(c, p, pp, tw);
     k_spec_reduce<<<c.n, 256, 0, s>>>(c, p, pp);
 }

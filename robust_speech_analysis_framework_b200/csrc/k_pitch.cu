@@ -15,9 +15,8 @@
 #include "fft.cuh"
 #include "num.cuh"
 
-#define NTHR 256
-#define NWARP (NTHR / 32)
 #define MAXPK 320
+#define FRAMES_PER_TURN 8
 
 // ------------------------------------------------------------------------------------------------ frame grid
 __global__ void k_pitch_grid(Clips c, PitchPass p) {
@@ -53,6 +52,7 @@ struct CandScratch {
     double* ckey;
     int* cimax;
     int* s_int;         // [4]: n maxima, ncand
+    int pkcap;
 };
 
 // Praat's slot assignment (first free slot, else replace the weakest when stronger), run by ONE thread over the ordered
@@ -83,6 +83,7 @@ __device__ __forceinline__ int insert_candidates(const PitchCfg& g, const CandSc
 // `vt2 >= 0` additionally builds the slots of a second analysis that differs only in its voicing threshold (the maxima
 // of the lower threshold are a superset, the first-pass values are shared).  Returns ncand | ncand2 << 8.
 // Harmonicity pass (maxn = 133 never fills, all path costs zero): only the list of maxima is built; returns their number.
+template <int NT>
 __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode,
                                                const double2* __restrict__ tw, double vt2, double* cf2, double* cs2,
                                                double* ckey2, int* cimax2) {
@@ -92,27 +93,27 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
     int upper = g.maximumLag < B ? g.maximumLag : B;      // i < maximumLag && i < brent_ixmax
     int nlag = upper - 2;                                   // lags 2 .. upper-1
     if (nlag < 0) nlag = 0;
-    int nrounds = (nlag + NTHR - 1) / NTHR;
+    int nrounds = (nlag + NT - 1) / NT;
     const double* r = S.rs0 + B;                            // r[i], i in [-B, B]
     for (int round = 0; round < nrounds; round++) {
-        int i = 2 + round * NTHR + tid;
+        int i = 2 + round * NT + tid;
         bool flag = false;
         if (i < 2 + nlag) {
             double ri = r[i];
             flag = ri > thr && ri > r[i - 1] && ri >= r[i + 1];
         }
         unsigned m = __ballot_sync(FULL_MASK, flag);
-        if (lane == 0) S.masks[round * NWARP + warp] = m;
+        if (lane == 0) S.masks[round * (NT / 32) + warp] = m;
     }
     __syncthreads();
     if (tid == 0) {
         int n = 0;
-        for (int w = 0; w < nrounds * NWARP; w++) {
+        for (int w = 0; w < nrounds * (NT / 32); w++) {
             unsigned m = S.masks[w];
             while (m) {
                 int b = __ffs(m) - 1;
                 m &= m - 1;
-                if (n < MAXPK) S.pk_lag[n++] = 2 + w * 32 + b;
+                if (n < S.pkcap) S.pk_lag[n++] = 2 + w * 32 + b;
             }
         }
         S.s_int[0] = n;
@@ -122,7 +123,7 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
     if (hnr_mode) return nmax;          // harmonicity: every maximum is refined, the caller queues them
     const double* y1 = S.rs0 - 1;                           // 1-based view: y1[j] = r[j - B - 1]
     const int ny = 2 * B + 1;
-    for (int m = warp; m < nmax; m += NWARP) {
+    for (int m = warp; m < nmax; m += (NT / 32)) {
         int i = S.pk_lag[m];
         double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
         double freq = 1.0 / dx / (i + dr / d2r);
@@ -153,6 +154,7 @@ struct FrameInfo {
 // IS_CC = false: autocorrelation (AC_HANNING);  true: forward cross-correlation (FCC_NORMAL), optionally HNR mode.
 struct FrameSmem {      // byte offsets into dynamic shared memory (computed on the host)
     int a, rs, pkf, pks, pkkey, cf, cs, ckey, cf2, cs2, ckey2, cimax2, red, part, pklag, cimax, masks, sint, fi, total;
+    int pkcap;          // capacity of the list of maxima
     int part_stride;    // CC: doubles per partial-sum row (>= maximumLag)
     int nchunk_max;
 };
@@ -161,15 +163,15 @@ struct FrameSmem {      // byte offsets into dynamic shared memory (computed on 
 // Forward cross-correlation products sum_j x[j] * x[j + lag] for lag = 1..Lmax over the window j < W.  A thread owns TL
 // consecutive lags and a chunk of the window: per step one new sample enters a sliding register window and feeds TL FMAs
 // (2 shared-memory loads per TL float64 FMAs).  Partial sums go to part[chunk][lag-1]; returns the number of chunks.
-template <int TL>
+template <int TL, int NT>
 __device__ __forceinline__ int cc_products(const double* xs, double* part, int PS, int W, int Lmax, int nchunk_max) {
     const int tid = threadIdx.x;
     const int ngroups = (Lmax + TL - 1) / TL;
-    int nchunk = ngroups > 0 ? NTHR / ngroups : 1;
+    int nchunk = ngroups > 0 ? NT / ngroups : 1;
     if (nchunk < 1) nchunk = 1;
     if (nchunk > nchunk_max) nchunk = nchunk_max;
     const int q = (W + nchunk - 1) / nchunk;
-    for (int wi = tid; wi < ngroups * nchunk; wi += NTHR) {
+    for (int wi = tid; wi < ngroups * nchunk; wi += NT) {
         const int grp = wi % ngroups, ch = wi / ngroups;
         const int lag0 = 1 + TL * grp;
         const int j0 = ch * q, j1 = j0 + q < W ? j0 + q : W;
@@ -193,8 +195,8 @@ __device__ __forceinline__ int cc_products(const double* xs, double* part, int P
     return nchunk;
 }
 
-template <bool IS_CC>
-__global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
+template <bool IS_CC, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)(smem + L.a);            // AC: packed FFT buffer; CC: xs[] doubles
     double* xs = (double*)(smem + L.a);
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
     S.cimax = (int*)(smem + L.cimax);
     S.masks = (unsigned*)(smem + L.masks);
     S.s_int = (int*)(smem + L.sint);
+    S.pkcap = L.pkcap;
     FrameInfo* fi = (FrameInfo*)(smem + L.fi);
     const int PS = L.part_stride;
 
@@ -223,7 +226,10 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
     const int total = p.fstart[c.n];
     const double dx = c.dx;
 
-    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    // a CTA takes FRAMES_PER_TURN consecutive frames per turn: neighbouring frames share ~90 % of their samples (L1 hits)
+    const int nturn = (total + FRAMES_PER_TURN - 1) / FRAMES_PER_TURN;
+    for (int turn = blockIdx.x; turn < nturn; turn += gridDim.x)
+    for (int f = turn * FRAMES_PER_TURN; f < total && f < (turn + 1) * FRAMES_PER_TURN; f++) {
         __syncthreads();
         if (tid == 0) {
             int clip = find_segment(p.fstart, c.n, f);
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         double acc = 0.0;
         {
             long long s0 = rightSample - g.nsamp_period, s1 = leftSample + g.nsamp_period;
-            for (long long i = s0 + tid; i <= s1; i += NTHR) acc += samp(pcm, i - 1);
+            for (long long i = s0 + tid; i <= s1; i += NT) acc += samp(pcm, i - 1);
         }
         const double localMean = block_sum(acc, red) / (double)(2 * g.nsamp_period);
 
@@ -261,7 +267,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         if (!IS_CC) {
             double* ar = (double*)a;                         // packed: ar[m] = frame[m+1]
             const int Nfft = g.nsampFFT;
-            for (int m = tid; m < Nfft; m += NTHR) {
+            for (int m = tid; m < Nfft; m += NT) {
                 double v = 0.0;
                 if (m < W) {
                     v = (samp(pcm, startSample + m - 1) - localMean) * __ldg(g.window + m);
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
                 ar[SWZD(m)] = v;
             }
         } else {
-            for (int m = tid; m < W; m += NTHR) {
+            for (int m = tid; m < W; m += NT) {
                 int j = m + 1;
                 if (j >= pk0 && j <= pk1) lp = fmax(lp, fabs(samp(pcm, startSample + m - 1) - localMean));
             }
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             fft_dit<+1>(a, g.M, tw);
             const double* ac = (const double*)a;            // ac[i] natural order
             const double ac0 = ac[SWZD(0)];
-            for (int i = tid; i <= B; i += NTHR) {
+            for (int i = tid; i <= B; i += NT) {
                 double v = i == 0 ? 1.0 : ac[SWZD(i)] / (ac0 * __ldg(g.windowR + i));
                 S.rs0[B + i] = v;
                 S.rs0[B - i] = v;
@@ -305,15 +311,15 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             const int Lmax = localMaximumLag > 0 ? localMaximumLag : 0;
             // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan; zero tail so the tiled loop may read ahead
             const int xs_len = g.maximumLag + W + 16;
-            for (int j = tid; j < xs_len; j += NTHR) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
-            for (int i = tid; i < 2 * B + 1; i += NTHR) S.rs0[i] = 0.0;
-            for (int i = tid; i < Ls; i += NTHR) rrow[i] = 0.0;
+            for (int j = tid; j < xs_len; j += NT) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
+            for (int i = tid; i < 2 * B + 1; i += NT) S.rs0[i] = 0.0;
+            for (int i = tid; i < Ls; i += NT) rrow[i] = 0.0;
             __syncthreads();
             // prefix sums of squares: sq[k] = sum_{j<k} xs[j]^2  (stored behind the partial products)
             double* sq = part + (size_t)L.nchunk_max * PS;
             {
                 const int total_len = (int)localSpan;
-                const int per = (total_len + NTHR - 1) / NTHR;
+                const int per = (total_len + NT - 1) / NT;
                 const int b0 = tid * per, b1 = b0 + per < total_len ? b0 + per : total_len;
                 double loc = 0.0;
                 for (int j = b0; j < b1; j++) loc = fma(xs[j], xs[j], loc);
@@ -335,10 +341,10 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             // products: work item = (group of TL lags, chunk of the window).  TL is odd so that the lag windows of adjacent
             // lanes start TL doubles apart (an even stride would put the whole warp on 2-4 shared-memory banks)
             int nchunk;
-            if (W >= 600) nchunk = cc_products<7>(xs, part, PS, W, Lmax, L.nchunk_max);
-            else nchunk = cc_products<5>(xs, part, PS, W, Lmax, L.nchunk_max);
+            if (W >= 600) nchunk = cc_products<7, NT>(xs, part, PS, W, Lmax, L.nchunk_max);
+            else nchunk = cc_products<5, NT>(xs, part, PS, W, Lmax, L.nchunk_max);
             __syncthreads();
-            for (int lag = 1 + tid; lag <= Lmax; lag += NTHR) {
+            for (int lag = 1 + tid; lag <= Lmax; lag += NT) {
                 double pr = 0.0;
                 for (int ch = 0; ch < nchunk; ch++) pr += part[(size_t)ch * PS + lag - 1];
                 double sy = sq[lag + W] - sq[lag];
@@ -358,9 +364,9 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
             double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
             uvs = g.vt + (uvs > 0 ? uvs : 0);
             int nmax = 0;
-            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates(g, dx, S, B, 1, tw, -1.0, cf2, cs2, ckey2, cimax2);
+            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates<NT>(g, dx, S, B, 1, tw, -1.0, cf2, cs2, ckey2, cimax2);
             const double* r = S.rs0 + B;
-            for (int m = tid; m < nmax; m += NTHR) {
+            for (int m = tid; m < nmax; m += NT) {
                 const int i = S.pk_lag[m];
                 double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
                 double freq = 1.0 / dx / (i + dr / d2r);
@@ -376,7 +382,7 @@ __global__ void __launch_bounds__(NTHR, 4) k_pitch_frames(Clips c, PitchPass p, 
         const bool dual = p.dual_cand_f != nullptr;
         int ncand = 1, ncand2 = 1;
         if (localPeak != 0.0) {
-            int nn = find_candidates(g, dx, S, B, 0, tw, dual ? p.dual_vt : -1.0, cf2, cs2, ckey2, cimax2);
+            int nn = find_candidates<NT>(g, dx, S, B, 0, tw, dual ? p.dual_vt : -1.0, cf2, cs2, ckey2, cimax2);
             ncand = nn & 0xff;
             if (dual) ncand2 = nn >> 8;
         } else if (tid == 0) {
@@ -435,11 +441,15 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     FrameSmem L;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o = (o + bytes + 15) & ~15; return r; };
+    // the list of maxima (at most one every other lag) is built after the transform buffer / sample window is dead: it lives there
+    int pkcap = ml / 2 + 2;
+    if (pkcap > MAXPK) pkcap = MAXPK;
+    L.pkcap = pkcap;
+    const int pkbytes = ((int)sizeof(double) * pkcap + 15) & ~15;
+    if (ab < 3 * pkbytes + (((int)sizeof(int) * pkcap + 15) & ~15)) ab = 3 * pkbytes + (((int)sizeof(int) * pkcap + 15) & ~15);
     L.a = take(ab);
+    L.pkf = L.a; L.pks = L.a + pkbytes; L.pkkey = L.a + 2 * pkbytes; L.pklag = L.a + 3 * pkbytes;
     L.rs = take((int)sizeof(double) * (rs + 1));
-    L.pkf = take((int)sizeof(double) * MAXPK);
-    L.pks = take((int)sizeof(double) * MAXPK);
-    L.pkkey = take((int)sizeof(double) * MAXPK);
     L.cf = take((int)sizeof(double) * (MAXCAND + 1));
     L.cs = take((int)sizeof(double) * (MAXCAND + 1));
     L.ckey = take((int)sizeof(double) * (MAXCAND + 1));
@@ -452,7 +462,6 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     L.nchunk_max = 8;
     // CC: nchunk_max rows of partial products + the prefix sums of squares (window + maximumLag + 1 entries)
     L.part = take(is_cc ? (int)sizeof(double) * (L.nchunk_max * L.part_stride + ab / (int)sizeof(double) + 8) : 16);
-    L.pklag = take((int)sizeof(int) * MAXPK);
     L.cimax = take((int)sizeof(int) * (MAXCAND + 1));
     L.masks = take((int)sizeof(unsigned) * 64);
     L.sint = take((int)sizeof(int) * 4);
@@ -477,15 +486,33 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
     if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
     if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
-    if (is_cc) {
-        cudaFuncSetAttribute(k_pitch_frames<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pitch_frames<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        k_pitch_frames<true><<<grid, NTHR, smem, s>>>(c, p, tw, L);
-    } else {
-        cudaFuncSetAttribute(k_pitch_frames<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_pitch_frames<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        k_pitch_frames<false><<<grid, NTHR, smem, s>>>(c, p, tw, L);
+    static int nt_ac = -1, nt_cc = -1;
+    if (nt_ac < 0) {   // development switches (128 / 256 threads per frame); 0 = the rule below
+        const char* e = getenv("MSHDS_NT_AC");
+        nt_ac = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : 0);
+        e = getenv("MSHDS_NT_CC");
+        nt_cc = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : 0);
     }
+    // 128 threads per frame keep every thread busy in the radix-4 passes of the 512/1024-point transforms and make the ~20
+    // barriers per frame cheaper (measured: wide AC pass 28.2 -> 25.5 ms, formant CC pass 17.3 -> 12.4 ms on 96 x 30 s);
+    // the 2048-point transform of the 30 Hz speech-rate pass is better off with 256 (13.0 vs 15.0 ms)
+    int maxM = 0;
+    for (int k = 0; k < 3; k++) if (p.cfg[k].M > maxM) maxM = p.cfg[k].M;
+    const int nt = is_cc ? (nt_cc ? nt_cc : 128) : (nt_ac ? nt_ac : (maxM >= 2048 ? 256 : 128));
+    if (nt == 128) {
+        grid = nsm * (blocks_per_sm * 2 > 8 ? 8 : blocks_per_sm * 2);
+        if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
+        if (grid < 1) grid = 1;
+    }
+#define PF_LAUNCH(CC, N) \
+    do { \
+        cudaFuncSetAttribute(k_pitch_frames<CC, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaFuncSetAttribute(k_pitch_frames<CC, N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        k_pitch_frames<CC, N><<<grid, N, smem, s>>>(c, p, tw, L); \
+    } while (0)
+    if (is_cc) { if (nt == 128) PF_LAUNCH(true, 128); else PF_LAUNCH(true, 256); }
+    else { if (nt == 128) PF_LAUNCH(false, 128); else PF_LAUNCH(false, 256); }
+#undef PF_LAUNCH
 }
 
 // ------------------------------------------------------------------------------------------------ refinement

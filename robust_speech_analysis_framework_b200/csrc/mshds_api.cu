@@ -751,7 +751,8 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     // Two streams.  `s` carries everything that fills the GPU; `side` carries the kernels that are one warp (or thread) per
     // clip and therefore latency-bound: Viterbi, glottal-pulse walks, interval logic.  SIDE(ev) makes the side stream wait for
     // what `s` has issued so far and switches issue to it; MAIN() switches back; MARK(ev) records a point on the side stream
-    // that `s` can later WAIT(ev) for.  With MSHDS_NO_OVERLAP=1 everything is issued on `s` in the same order.
+    // that `s` can later WAIT(ev) for.  With MSHDS_NO_OVERLAP=1 everything is issued on `s` in the same order.  Profiling spans
+    // of side-stream work are named "~...": their durations include time spent sharing the SMs with the main stream.
     cudaStream_t side = h->overlap ? h->side : s;
     cudaStream_t q = s;                          // stream the next launch goes to
     h->cur = s;
@@ -771,7 +772,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_refine"); launch_pitch_refine(c, wide, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, wide, fhint, q); h->launches += 1; PE();
     SIDE();
-    PB("viterbi"); launch_pitch_viterbi(c, wide, q); h->launches += 1; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, wide, q); h->launches += 1; PE();
     const cudaEvent_t ev_wide = MARK();
     MAIN();
 
@@ -783,8 +784,8 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_refine"); launch_pitch_refine(c, srp, h->tw, fhint20, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, srp, fhint20, q); h->launches += 1; PE();
     SIDE();
-    PB("viterbi"); launch_pitch_viterbi(c, srp, q); h->launches += 1; PE();
-    PB("speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, q); h->launches += 1; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, srp, q); h->launches += 1; PE();
+    PB("~speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, q); h->launches += 1; PE();
     MAIN();
 
     WAIT(ev_wide);
@@ -798,12 +799,12 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_refine"); launch_pitch_refine(c, cpp_p, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, cpp_p, fhint, q); h->launches += 1; PE();
     SIDE();
-    PB("viterbi"); launch_pitch_viterbi(c, mainp, q); h->launches += 1; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, mainp, q); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, q); h->launches += 1;
     const cudaEvent_t ev_mainpitch = MARK();
-    PB("viterbi"); launch_pitch_viterbi(c, cpp_p, q); h->launches += 1; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, cpp_p, q); h->launches += 1; PE();
     // ---- _extract_CPP (:253-301), first half: pulses of the vt=0.3 pitch and the voiced intervals
-    PB("pulses"); launch_pulses(c, cpp_p, pl_cp, q); h->launches += 5; PE();
+    PB("~pulses"); launch_pulses(c, cpp_p, pl_cp, q); h->launches += 5; PE();
     launch_vuv_segments(c, pl_cp, sg, q); h->launches += 1;
     const cudaEvent_t ev_vuv = MARK();
     MAIN();
@@ -826,8 +827,8 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_refine"); launch_pitch_refine(c, ltp, h->tw, fhint75, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, ltp, fhint75, q); h->launches += 1; PE();
     SIDE();
-    PB("viterbi"); launch_pitch_viterbi(c, ltp, q); h->launches += 1; PE();
-    PB("pulses"); launch_pulses(c, ltp, pl_lt, q); h->launches += 5; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, ltp, q); h->launches += 1; PE();
+    PB("~pulses"); launch_pulses(c, ltp, pl_lt, q); h->launches += 5; PE();
     const cudaEvent_t ev_ltas = MARK();
     MAIN();
 
@@ -839,8 +840,8 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_refine"); launch_pitch_refine(c, ccp, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, ccp, fhint, q); h->launches += 1; PE();
     SIDE();
-    PB("viterbi"); launch_pitch_viterbi(c, ccp, q); h->launches += 1; PE();
-    PB("pulses"); launch_pulses(c, ccp, pl_fm, q); h->launches += 5; PE();
+    PB("~viterbi"); launch_pitch_viterbi(c, ccp, q); h->launches += 1; PE();
+    PB("~pulses"); launch_pulses(c, ccp, pl_fm, q); h->launches += 5; PE();
     const cudaEvent_t ev_fmt = MARK();
     MAIN();
 
