@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
     double* red = (double*)(smem + sizeof(double2) * 512);
     __shared__ int s_seg;
     const int total = fprefix[nsegs];
-    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    // 8 consecutive frames per turn: neighbouring frames share most of their samples (L1 hits)
+    for (int turn = blockIdx.x; turn * 8 < total; turn += gridDim.x)
+    for (int f = turn * 8; f < total && f < turn * 8 + 8; f++) {
         __syncthreads();
         if (threadIdx.x == 0) s_seg = find_segment(fprefix, nsegs, f);
         __syncthreads();

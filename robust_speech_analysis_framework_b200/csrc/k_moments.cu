@@ -34,7 +34,9 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
     __shared__ int s_clip, s_voiced;
     const int total = p.fstart[c.n];
     const double dx = c.dx;
-    for (int f = blockIdx.x; f < total; f += gridDim.x) {
+    // 8 consecutive frames per turn: neighbouring frames share most of their samples (L1 hits)
+    for (int turn = blockIdx.x; turn * 8 < total; turn += gridDim.x)
+    for (int f = turn * 8; f < total && f < turn * 8 + 8; f++) {
         __syncthreads();
         if (threadIdx.x == 0) {
             int clip = find_segment(p.fstart, c.n, f);

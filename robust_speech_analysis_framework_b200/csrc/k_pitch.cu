@@ -9,6 +9,7 @@
 // One CTA per frame (persistent grid-stride loop over the flattened frame list of all clips): the frame is staged in
 // shared memory, transformed with the packed real FFT of fft.cuh (AC) or correlated directly (FCC), candidates are
 // refined warp-per-candidate, and only the <=15 candidates leave the SM.
+#include <cstdio>
 #include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
@@ -17,6 +18,9 @@
 
 #define MAXPK 320
 #define FRAMES_PER_TURN 8
+#ifndef CC_TL_LONG
+#define CC_TL_LONG 13
+#endif
 
 // ------------------------------------------------------------------------------------------------ frame grid
 __global__ void k_pitch_grid(Clips c, PitchPass p) {
@@ -180,7 +184,20 @@ __device__ __forceinline__ int cc_products(const double* xs, double* part, int P
         const double* xb = xs + j0 + lag0;
 #pragma unroll
         for (int u = 0; u < TL; u++) { acc[u] = 0.0; yw[u] = xb[u]; }
-        for (int j = 0; j < j1 - j0; j++) {
+        const int len = j1 - j0;
+        int j = 0;
+        // TL steps per trip with the window kept as a ring (sample xb[k] sits in slot k % TL): no register shuffling, the
+        // trip is 2*TL shared-memory loads and TL*TL FMAs
+        for (; j + TL <= len; j += TL) {
+#pragma unroll
+            for (int t = 0; t < TL; t++) {
+                const double xv = xa[j + t];
+#pragma unroll
+                for (int u = 0; u < TL; u++) acc[u] = fma(xv, yw[(u + t) % TL], acc[u]);
+                yw[t] = xb[j + t + TL];
+            }
+        }
+        for (; j < len; j++) {          // tail (< TL steps): slots are aligned again, shift the window
             const double xv = xa[j];
 #pragma unroll
             for (int u = 0; u < TL; u++) acc[u] = fma(xv, yw[u], acc[u]);
@@ -196,7 +213,7 @@ __device__ __forceinline__ int cc_products(const double* xs, double* part, int P
 }
 
 template <bool IS_CC, int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
+__global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(Clips c, PitchPass p, const double2* __restrict__ tw, FrameSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)(smem + L.a);            // AC: packed FFT buffer; CC: xs[] doubles
     double* xs = (double*)(smem + L.a);
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_pitch_frames(Clips c, PitchPa
             const int localMaximumLag = (int)(localSpan - W);
             const int Lmax = localMaximumLag > 0 ? localMaximumLag : 0;
             // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan; zero tail so the tiled loop may read ahead
-            const int xs_len = g.maximumLag + W + 16;
+            const int xs_len = g.maximumLag + W + 32;      // read-ahead of the tiled loop: < 2 * TL + 1 samples past the span
             for (int j = tid; j < xs_len; j += NT) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
             for (int i = tid; i < 2 * B + 1; i += NT) S.rs0[i] = 0.0;
             for (int i = tid; i < Ls; i += NT) rrow[i] = 0.0;
@@ -341,7 +358,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_pitch_frames(Clips c, PitchPa
             // products: work item = (group of TL lags, chunk of the window).  TL is odd so that the lag windows of adjacent
             // lanes start TL doubles apart (an even stride would put the whole warp on 2-4 shared-memory banks)
             int nchunk;
-            if (W >= 600) nchunk = cc_products<7, NT>(xs, part, PS, W, Lmax, L.nchunk_max);
+            // (shared memory, not registers, limits the CTAs per SM here, so the long-window pass can afford 13 lags per thread:
+            // 2 loads per 13 FMAs)
+            if (W >= 600) nchunk = cc_products<CC_TL_LONG, NT>(xs, part, PS, W, Lmax, L.nchunk_max);
             else nchunk = cc_products<5, NT>(xs, part, PS, W, Lmax, L.nchunk_max);
             __syncthreads();
             for (int lag = 1 + tid; lag <= Lmax; lag += NT) {
@@ -433,7 +452,7 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
     int ab = 0, rs = 0, ml = 0;
     for (int k = 0; k < 3; k++) {
         const PitchCfg& g = p.cfg[k];
-        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 24) : (int)sizeof(double2) * g.M;
+        int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 40) : (int)sizeof(double2) * g.M;
         if (need_a > ab) ab = need_a;
         if (2 * g.brent_ixmax + 1 > rs) rs = 2 * g.brent_ixmax + 1;
         if (g.maximumLag > ml) ml = g.maximumLag;
