@@ -11,6 +11,8 @@
 struct PtrY {
     const double* y;
     __device__ __forceinline__ double operator()(int j) const { return y[j]; }
+    __device__ __forceinline__ int lo() const { return 1; }              // entries outside [lo, hi] are known to be zero
+    __device__ __forceinline__ int hi(int n) const { return n; }
 };
 struct SymRowY {            // y(j) = r[|j - centre|], zero beyond the stored lags
     const double* __restrict__ row;
@@ -20,6 +22,8 @@ struct SymRowY {            // y(j) = r[|j - centre|], zero beyond the stored la
         l = l < 0 ? -l : l;
         return l < len ? row[l] : 0.0;
     }
+    __device__ __forceinline__ int lo() const { return centre - len + 1; }
+    __device__ __forceinline__ int hi(int) const { return centre + len - 1; }
 };
 
 // cos(pi*u) for u in [0, 1] from the FFT twiddle table (tw[j] = (cos, -sin)(pi*j/4096), j < 4096) plus a 4th-order
@@ -42,6 +46,8 @@ struct StagedY {            // a window of the 1-based array staged in shared me
     const double* st;
     int j0;
     __device__ __forceinline__ double operator()(int j) const { return st[j - j0]; }
+    __device__ __forceinline__ int lo() const { return 1; }
+    __device__ __forceinline__ int hi(int n) const { return n; }
 };
 
 // y is 1-based: y(1..n) valid.  All 32 lanes must call with identical arguments; all lanes get the result.
@@ -84,6 +90,13 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     const bool rec = stepl <= 1.0 && stepr <= 1.0;
     const double twocl = rec ? 2.0 * cospi_tab(stepl, tw) : 0.0, twocr = rec ? 2.0 * cospi_tab(stepr, tw) : 0.0;
     double clm = 0.0, cl = 0.0, crm = 0.0, cr = 0.0;
+    // taps that only meet entries known to be zero (a correlation row is stored up to its last useful lag; the 700-deep
+    // window of a maximum at lag 2-3 reaches twice as far) add exactly nothing: stop at the last tap that can matter
+    {
+        const int kl = midleft - y.lo() + 1, kr = y.hi(n) - midright + 1;
+        const int kmax = kl > kr ? kl : kr;
+        if (kmax < maxDepth) maxDepth = kmax > 0 ? kmax : 0;
+    }
     // two taps per side and trip: the four divisions 1/(f + k) share ONE reciprocal (of the product of the four
     // denominators, <= 71^4), the individual ones are recovered with multiplications
     for (int k = lane, m = 0; k < maxDepth; k += 2 * nl, m += 2) {
