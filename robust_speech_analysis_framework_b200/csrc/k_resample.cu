@@ -306,8 +306,19 @@ __global__ void __launch_bounds__(512) k_sinc_fir(const ResampleJob* __restrict_
         double w[FIR_R];
 #pragma unroll
         for (int r = 0; r < FIR_R; r++) w[r] = Us[r];
-        int sidx = 0;
-        for (int k = k0; k < D; k += Q) {
+        // the window is a ring (sample Us[i] in slot i mod FIR_R): FIR_R tap steps per trip, no register shuffling
+        int sidx = 0, k = k0;
+        for (; k + (FIR_R - 1) * Q < D; k += FIR_R * Q) {
+#pragma unroll
+            for (int t = 0; t < FIR_R; t++) {
+                const double cf = __ldg(T + k + t * Q);
+#pragma unroll
+                for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[(r - t + FIR_R) % FIR_R], acc[r]);
+                sidx++;
+                w[(FIR_R - 1 - t) % FIR_R] = Us[-sidx];
+            }
+        }
+        for (; k < D; k += Q) {          // tail (< FIR_R steps): slots are aligned again, shift the window
             const double cf = __ldg(T + k);
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[r], acc[r]);
@@ -324,8 +335,18 @@ __global__ void __launch_bounds__(512) k_sinc_fir(const ResampleJob* __restrict_
         double w[FIR_R];
 #pragma unroll
         for (int r = 0; r < FIR_R; r++) w[r] = Us[r];
-        int sidx = 0;
-        for (int k = k0; k < D; k += Q) {
+        int sidx = 0, k = k0;
+        for (; k + (FIR_R - 1) * Q < D; k += FIR_R * Q) {
+#pragma unroll
+            for (int t = 0; t < FIR_R; t++) {
+                const double cf = __ldg(T + D + k + t * Q);
+#pragma unroll
+                for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[(r + t) % FIR_R], acc[r]);
+                sidx++;
+                w[t] = Us[FIR_R - 1 + sidx];
+            }
+        }
+        for (; k < D; k += Q) {
             const double cf = __ldg(T + D + k);
 #pragma unroll
             for (int r = 0; r < FIR_R; r++) acc[r] = fma(cf, w[r], acc[r]);
