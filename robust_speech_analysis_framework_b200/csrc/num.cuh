@@ -99,11 +99,11 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
     }
     // two taps per side and trip: the four divisions 1/(f + k) share ONE reciprocal (of the product of the four
     // denominators, <= 71^4), the individual ones are recovered with multiplications
-    for (int k = lane, m = 0; k < maxDepth; k += 2 * nl, m += 2) {
+    int k = lane, m = 0;
+    for (; k + nl < maxDepth; k += 2 * nl, m += 2) {
         const int k2 = k + nl;
-        const bool has2 = k2 < maxDepth;
         const double al = fl + k, ar = fr + k;                              // in units of pi
-        const double al2 = has2 ? fl + k2 : 1.0, ar2 = has2 ? fr + k2 : 1.0;
+        const double al2 = fl + k2, ar2 = fr + k2;
         double cl0, cr0, cl1, cr1;
         if (!rec || m < 2) {
             cl0 = cospi_tab(fmin(al * invl, 1.0), tw);
@@ -122,15 +122,28 @@ __device__ __forceinline__ double sinc_interp_warp_t(const Y& y, int n, double x
         const double ip = q * r, iq = p * r;
         const double dl = (ar * ip) * (1.0 + cl0), dr = (al * ip) * (1.0 + cr0);
         const double dl2 = (ar2 * iq) * (1.0 + cl1), dr2 = (al2 * iq) * (1.0 + cr1);
-        double yl = y(midleft - k), yr = y(midright + k);
-        double yl2 = has2 ? y(midleft - k2) : 0.0, yr2 = has2 ? y(midright + k2) : 0.0;
-        if (k & 1) { yl = -yl; yr = -yr; }
-        if (k2 & 1) { yl2 = -yl2; yr2 = -yr2; }
-        accl = fma(yl, dl, accl);
-        accr = fma(yr, dr, accr);
-        accl = fma(yl2, dl2, accl);
-        accr = fma(yr2, dr2, accr);
+        accl = fma(y(midleft - k), dl, accl);
+        accr = fma(y(midright + k), dr, accr);
+        accl = fma(y(midleft - k2), dl2, accl);
+        accr = fma(y(midright + k2), dr2, accr);
     }
+    if (k < maxDepth) {                                                     // odd tap left over
+        const double al = fl + k, ar = fr + k;
+        double cl0, cr0;
+        if (!rec || m < 2) {
+            cl0 = cospi_tab(fmin(al * invl, 1.0), tw);
+            cr0 = cospi_tab(fmin(ar * invr, 1.0), tw);
+        } else {
+            cl0 = fma(twocl, cl, -clm);
+            cr0 = fma(twocr, cr, -crm);
+        }
+        const double r = __drcp_rn(al * ar);
+        accl = fma(y(midleft - k), (ar * r) * (1.0 + cl0), accl);
+        accr = fma(y(midright + k), (al * r) * (1.0 + cr0), accr);
+    }
+    // (-1)^k of the tap: k = lane + j * nl has the parity of the lane (nl is even), so the sign is applied once to the
+    // lane's sums instead of to every sample
+    if (lane & 1) { accl = -accl; accr = -accr; }
     return group_sum(accl * hsl + accr * hsr, mask, nl);
 }
 
