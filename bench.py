@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=0, help="clips per step of the CPU baseline sample (0 = one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stages", action="store_true", help="print the per-stage timing table to stderr")
+    ap.add_argument("--chunk-log2", type=int, default=0, help="override the library's chunk size (log2 of samples per chunk)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -187,6 +188,8 @@ def main():
     ex = _lib.Extractor(local_rank)
     stream = torch.cuda.current_stream()
     ex.set_stream(stream.cuda_stream)
+    if args.chunk_log2:
+        ex.set_chunk_samples(1 << args.chunk_log2)
     lib, h = ex._lib, ex._h
     import ctypes as C
 

@@ -23,7 +23,7 @@ __device__ __forceinline__ int bitrev(int k, int logn) { return (int)(__brev((un
 // tw index for exp(SIGN*2*pi*i*pos/len), len a power of two <= TW_N, pos < len/2
 template <int SIGN>
 __device__ __forceinline__ double2 twiddle(const double2* __restrict__ tw, int pos, int len) {
-    double2 w = __ldg(tw + pos * (TW_N / len));
+    double2 w = __ldg(tw + (pos << (13 - (__ffs(len) - 1))));          // pos * (TW_N / len), TW_N = 2^13
     if (SIGN > 0) w.y = -w.y;
     return w;
 }
@@ -77,9 +77,10 @@ __device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __rest
     int half = n >> 1;
     while (half >= 2) {
         const int q = half >> 1;
+        const int lq = __ffs(q) - 1;                       // sizes are powers of two: shifts instead of divisions
         for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
             const int pos = t & (q - 1);
-            const int i0 = (t / q) * 2 * half + pos;
+            const int i0 = ((t >> lq) << (lq + 2)) + pos;
             double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + q)], x2 = a[SWZ(i0 + half)], x3 = a[SWZ(i0 + half + q)];
             const double2 w1 = twiddle<SIGN>(tw, pos, 2 * half);
             const double2 w2 = cmul(w1, w1);                  // exp(i a)^2 instead of a second table look-up
@@ -118,9 +119,10 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
     }
     while (half < n) {
         const int h = half;
+        const int lh = __ffs(h) - 1;
         for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
             const int pos = t & (h - 1);
-            const int i0 = (t / h) * 4 * h + pos;
+            const int i0 = ((t >> lh) << (lh + 2)) + pos;
             double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + h)], x2 = a[SWZ(i0 + 2 * h)], x3 = a[SWZ(i0 + 3 * h)];
             const double2 wB = twiddle<SIGN>(tw, pos, 4 * h);
             if (h > 1) {

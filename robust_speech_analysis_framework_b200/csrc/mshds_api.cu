@@ -1023,6 +1023,7 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             h->arena = nullptr; h->arena_cap = 0;
             CK(cudaMalloc((void**)&h->arena, need + (need >> 3)));
             h->arena_cap = need + (need >> 3);
+            if (getenv("MSHDS_DEBUG_MEM")) fprintf(stderr, "mshds: scratch arena %.2f GB for a chunk of %d clips / %lld samples\n", (double)h->arena_cap / 1e9, n, tot);
         }
         // tail of the arena: staging for pcm / outputs when the caller's buffers live on the host
         size_t tail = h->arena_cap;
