@@ -84,6 +84,20 @@ const char* mshds_last_error(const mshds_handle* h);
 int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
                   double* features, uint32_t* status, unsigned flags);
 
+/*
+ * Clip -> session aggregation, the step that follows the extractor in the reference pipeline: src/utils.py:36-56
+ * aggregate_clip_features = groupby('unique_participant_id').agg(['mean', 'std']) over the clip rows.
+ * features: n_rows x n_cols float64, row-major (NaN = missing, skipped like pandas does); row_group[i] in [0, n_groups) is
+ * the session of row i, or negative for a row that belongs to none.  mean_out / std_out: n_groups x n_cols.  Rows are
+ * visited in index order with pandas' own arithmetic (Kahan-compensated mean, Welford variance, ddof = 1: NaN for fewer
+ * than two values), so the result is bit-identical to the reference's.  row_group is always a HOST array; with
+ * MSHDS_AGG_ON_DEVICE features, mean_out and std_out are device pointers (e.g. the output of mshds_extract with
+ * MSHDS_OUT_ON_DEVICE), otherwise host pointers.
+ */
+#define MSHDS_AGG_ON_DEVICE (1u << 0)
+int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows, int n_cols, const int32_t* row_group,
+                             int n_groups, double* mean_out, double* std_out, unsigned flags);
+
 /* Number of kernel launches issued by this handle since creation (bench.py reports it as gpu_launches). */
 long long mshds_launch_count(const mshds_handle* h);
 

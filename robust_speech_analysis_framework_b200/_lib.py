@@ -23,10 +23,11 @@ FEATURE_NAMES = [  # /root/reference/src/mshds_extractor.py:397-404
 N_FEATURES = 25
 PCM_ON_DEVICE = 1
 OUT_ON_DEVICE = 2
+AGG_ON_DEVICE = 1
 
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
-    "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report",
+    "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report", "mshds_aggregate_sessions",
 ]
 
 _lib = None
@@ -58,6 +59,8 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_launch_count.restype = C.c_longlong
     lib.mshds_profile_enable.argtypes = [C.c_void_p, C.c_int]
     lib.mshds_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.mshds_aggregate_sessions.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_uint]
     lib.mshds_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
@@ -117,6 +120,28 @@ class Extractor:
 
     def profile(self, on: bool):
         self._check(self._lib.mshds_profile_enable(self._h, int(on)))
+
+    def aggregate_sessions(self, features: np.ndarray, row_group: np.ndarray, n_groups: int):
+        """mshds_aggregate_sessions on host arrays: (mean [g, d], std [g, d]) of the rows of every session."""
+        features = np.ascontiguousarray(features, dtype=np.float64)
+        if features.ndim != 2:
+            raise MshdsError("features must be a 2-D array")
+        row_group = np.ascontiguousarray(row_group, dtype=np.int32)
+        n, d = features.shape
+        if len(row_group) != n:
+            raise MshdsError("row_group must have one entry per row")
+        mean = np.full((n_groups, d), np.nan)
+        std = np.full((n_groups, d), np.nan)
+        self._check(self._lib.mshds_aggregate_sessions(self._h, features.ctypes.data, n, d, row_group.ctypes.data, int(n_groups),
+                                                       mean.ctypes.data, std.ctypes.data, 0))
+        return mean, std
+
+    def aggregate_sessions_device(self, feat_ptr: int, n_rows: int, n_cols: int, row_group: np.ndarray, n_groups: int,
+                                  mean_ptr: int, std_ptr: int):
+        """Same on device buffers (e.g. straight from extract_device): nothing but the group list crosses PCIe."""
+        row_group = np.ascontiguousarray(row_group, dtype=np.int32)
+        self._check(self._lib.mshds_aggregate_sessions(self._h, C.c_void_p(feat_ptr), int(n_rows), int(n_cols), row_group.ctypes.data,
+                                                       int(n_groups), C.c_void_p(mean_ptr), C.c_void_p(std_ptr), AGG_ON_DEVICE))
 
     def profile_report(self) -> dict:
         """{stage: (milliseconds, spans)} accumulated since profile(True)."""

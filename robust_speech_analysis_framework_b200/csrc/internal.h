@@ -112,6 +112,8 @@ struct LtasPass {
 void launch_ltas(const Clips& c, const PulseSet& ps, const LtasPass& lt, double* ltas_bands /*[n*50]*/, cudaStream_t s);
 
 // ---- launchers (each in its own .cu) ----------------------------------------------------------------------------
+void launch_session_agg(const double* feat, int n_cols, const int* row_start, const int* rows, int n_groups, double* mean_out,
+                        double* std_out, cudaStream_t s);
 void launch_finalize_status(const Clips& c, cudaStream_t s);
 void launch_clip_stats(const Clips& c, long long max_clip_len, void* scratch /* n*16 bytes */, cudaStream_t s);
 void launch_exclusive_scan(const int* counts, int* prefix, int n, cudaStream_t s);

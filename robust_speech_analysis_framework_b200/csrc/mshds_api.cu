@@ -1100,6 +1100,60 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     return MSHDS_OK;
 }
 
+int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows, int n_cols, const int32_t* row_group,
+                             int n_groups, double* mean_out, double* std_out, unsigned flags) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->err.clear();
+    if (n_rows < 0 || n_cols < 1 || n_groups < 0 || (n_rows > 0 && (!features || !row_group)) ||
+        (n_groups > 0 && (!mean_out || !std_out))) { h->err = "bad argument"; return MSHDS_ERR_ARG; }
+    if ((long long)n_groups * n_cols > 0x7fffffffLL) { h->err = "too many sessions x columns"; return MSHDS_ERR_ARG; }
+    if (n_groups == 0) return MSHDS_OK;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return MSHDS_ERR_CUDA; }
+    cudaStream_t s = h->stream;
+    const bool on_dev = (flags & MSHDS_AGG_ON_DEVICE) != 0;
+    // rows of every session in index order (counting sort on the host; the list is a few hundred entries)
+    std::vector<int> start(n_groups + 1, 0), rows;
+    for (int i = 0; i < n_rows; i++) {
+        if (row_group[i] >= n_groups) { h->err = "row_group out of range"; return MSHDS_ERR_ARG; }
+        if (row_group[i] >= 0) start[row_group[i] + 1]++;
+    }
+    for (int g = 0; g < n_groups; g++) start[g + 1] += start[g];
+    rows.resize(start[n_groups] > 0 ? start[n_groups] : 1);
+    {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int i = 0; i < n_rows; i++) if (row_group[i] >= 0) rows[fill[row_group[i]]++] = i;
+    }
+    const size_t fbytes = sizeof(double) * (size_t)(n_rows > 0 ? n_rows : 1) * n_cols, obytes = sizeof(double) * (size_t)n_groups * n_cols;
+    char* buf = nullptr;
+    const size_t o_start = 0, o_rows = (sizeof(int) * (n_groups + 1) + 255) & ~(size_t)255;
+    const size_t o_feat = o_rows + ((sizeof(int) * rows.size() + 255) & ~(size_t)255);
+    const size_t o_mean = o_feat + (on_dev ? 0 : ((fbytes + 255) & ~(size_t)255));
+    const size_t o_std = o_mean + (on_dev ? 0 : ((obytes + 255) & ~(size_t)255));
+    const size_t total = o_std + (on_dev ? 0 : obytes) + 256;
+    CK(cudaMalloc((void**)&buf, total));
+    int rc = MSHDS_OK;
+    do {
+        if (cudaMemcpyAsync(buf + o_start, start.data(), sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, s) != cudaSuccess ||
+            cudaMemcpyAsync(buf + o_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = MSHDS_ERR_CUDA; break; }
+        const double* d_feat = features;
+        double* d_mean = mean_out; double* d_std = std_out;
+        if (!on_dev) {
+            if (n_rows > 0 && cudaMemcpyAsync(buf + o_feat, features, fbytes, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = MSHDS_ERR_CUDA; break; }
+            d_feat = (const double*)(buf + o_feat); d_mean = (double*)(buf + o_mean); d_std = (double*)(buf + o_std);
+        }
+        launch_session_agg(d_feat, n_cols, (const int*)(buf + o_start), (const int*)(buf + o_rows), n_groups, d_mean, d_std, s);
+        h->launches += 1;
+        if (!on_dev) {
+            if (cudaMemcpyAsync(mean_out, d_mean, obytes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaMemcpyAsync(std_out, d_std, obytes, cudaMemcpyDeviceToHost, s) != cudaSuccess) { rc = MSHDS_ERR_CUDA; break; }
+        }
+        if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = MSHDS_ERR_CUDA; break; }
+    } while (0);
+    cudaFree(buf);
+    if (rc) h->err = "CUDA failure in mshds_aggregate_sessions";
+    return rc;
+}
+
 int mshds_profile_enable(mshds_handle* h, int on) {
     if (!h) return MSHDS_ERR_ARG;
     h->prof_on = on != 0;

@@ -209,3 +209,71 @@ def test_synth_is_deterministic_and_well_formed():
     assert int(a.abs().max()) > 8000 and int(a.abs().max()) <= 32767
     pcm, off = synth_batch(3, [0.5, 0.25, 0.75])
     assert list(off) == [0, 8000, 12000, 24000] and pcm.numel() == 24000
+
+
+# ------------------------------------------------------------------------------------------------ session aggregation (8f-3)
+AGG_GOLDEN = os.path.join(ROOT, "tests", "golden", "session_agg_golden_v1.npz")
+
+
+def _agg_golden_frames():
+    import pandas as pd
+    g = np.load(AGG_GOLDEN, allow_pickle=True)
+    clip = pd.DataFrame(g["clip_values"], columns=list(g["clip_columns"]))
+    clip.insert(0, "filename", list(g["clip_filenames"]))
+    meta = pd.DataFrame({"filename": list(g["meta_filenames"]), "unique_participant_id": list(g["meta_ids"])})
+    return g, clip, meta
+
+
+def test_session_agg_restatement_is_bit_identical_to_the_reference_output():
+    """oracle/session_agg.py against vectors produced by the reference's own aggregate_clip_features (src/utils.py:7-58)."""
+    from oracle import session_agg
+    g, clip, meta = _agg_golden_frames()
+    out = session_agg.aggregate_clip_features(clip, meta)
+    assert list(out["unique_participant_id"]) == list(g["out_ids"])
+    assert list(out.columns[1:]) == list(g["out_columns"])
+    got = out.iloc[:, 1:].to_numpy(dtype=np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(g["out_values"]))
+    assert np.array_equal(got, g["out_values"], equal_nan=True)           # bit for bit
+    assert np.isnan(g["out_values"]).any() and out.shape == (23, 51)
+
+
+def test_session_agg_restatement_matches_live_pandas_on_random_groups():
+    import pandas as pd
+    from oracle import session_agg
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        n, d, k = int(rng.integers(5, 200)), int(rng.integers(1, 9)), int(rng.integers(1, 12))
+        x = rng.normal(size=(n, d)) * 10.0 ** rng.integers(-4, 6, size=d)
+        x[rng.random((n, d)) < 0.1] = np.nan
+        codes = rng.integers(0, k, size=n)
+        df = pd.DataFrame(x, columns=[f"c{j}" for j in range(d)])
+        df["gid"] = codes
+        want = df.groupby("gid").agg(["mean", "std"])
+        present = np.array(sorted(set(codes.tolist())))
+        mean, std = session_agg.group_mean_std(x, codes, k)
+        for j in range(d):
+            assert np.array_equal(mean[present, j], want[(f"c{j}", "mean")].to_numpy(), equal_nan=True)
+            assert np.array_equal(std[present, j], want[(f"c{j}", "std")].to_numpy(), equal_nan=True)
+
+
+class _FakeAggExtractor:
+    def aggregate_sessions(self, x, codes, n_groups):
+        from oracle import session_agg          # the checker standing in for the CUDA call (test only)
+        return session_agg.group_mean_std(np.asarray(x, dtype=np.float64), np.asarray(codes), n_groups)
+
+
+def test_aggregate_clip_features_contract(monkeypatch, capsys):
+    """Host logic of the drop-in (merge, id order, column naming, empty input) without a GPU."""
+    import pandas as pd
+    from robust_speech_analysis_framework_b200 import mshds_extractor as mx, utils as bu
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: _FakeAggExtractor())
+    g, clip, meta = _agg_golden_frames()
+    out = bu.aggregate_clip_features(clip, meta)
+    assert list(out.columns) == ["unique_participant_id"] + list(g["out_columns"])
+    assert list(out["unique_participant_id"]) == list(g["out_ids"])
+    assert np.array_equal(out.iloc[:, 1:].to_numpy(dtype=np.float64), g["out_values"], equal_nan=True)
+    empty = bu.aggregate_clip_features(pd.DataFrame(), meta)
+    assert empty.empty and "Warning: Input clip_features_df is empty" in capsys.readouterr().out      # src/utils.py:31-33
+    sys.path.insert(0, ROOT)
+    from src.utils import aggregate_clip_features as shim
+    assert shim is bu.aggregate_clip_features

@@ -289,3 +289,49 @@ def test_many_short_clips_like_config_4(ex, orc):
     assert_features_close(got, want, "192 x 2 s")
     assert np.array_equal(st, wst)
     assert np.array_equal(got[:, SPEECHRATE], want[:, SPEECHRATE], equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------ session aggregation (8f-3)
+def test_session_aggregation_is_bit_identical_to_the_reference(ex):
+    """mshds_aggregate_sessions against vectors produced by the reference's own aggregate_clip_features
+    (src/utils.py:7-58, tests/golden/make_agg_golden.py) and against the Python restatement on random groups."""
+    import pandas as pd
+    from oracle import session_agg
+    from robust_speech_analysis_framework_b200 import utils as bu
+    g = np.load(os.path.join(ROOT, "tests", "golden", "session_agg_golden_v1.npz"), allow_pickle=True)
+    clip = pd.DataFrame(g["clip_values"], columns=list(g["clip_columns"]))
+    clip.insert(0, "filename", list(g["clip_filenames"]))
+    meta = pd.DataFrame({"filename": list(g["meta_filenames"]), "unique_participant_id": list(g["meta_ids"])})
+    out = bu.aggregate_clip_features(clip, meta)
+    assert list(out.columns) == ["unique_participant_id"] + list(g["out_columns"])
+    assert list(out["unique_participant_id"]) == list(g["out_ids"])
+    assert np.array_equal(out.iloc[:, 1:].to_numpy(dtype=np.float64), g["out_values"], equal_nan=True)     # bit for bit
+    rng = np.random.default_rng(11)
+    for n, d, k in ((1, 1, 1), (7, 3, 9), (866, 25, 109), (5000, 50, 400)):
+        x = rng.normal(size=(n, d)) * 10.0 ** rng.integers(-4, 6, size=d)
+        x[rng.random((n, d)) < 0.08] = np.nan
+        codes = rng.integers(-1, k, size=n).astype(np.int32)            # -1 = row without a session
+        mean, std = ex.aggregate_sessions(x, codes, k)
+        wm, ws = session_agg.group_mean_std(x, codes, k)
+        assert np.array_equal(mean, wm, equal_nan=True) and np.array_equal(std, ws, equal_nan=True)
+    from robust_speech_analysis_framework_b200 import _lib
+    with pytest.raises(_lib.MshdsError):
+        ex.aggregate_sessions(np.zeros((3, 2)), np.array([0, 5, 1], np.int32), 2)
+
+
+def test_session_aggregation_on_device_buffers(ex):
+    """Extraction output stays in HBM and is aggregated there; only the group list crosses PCIe."""
+    import torch
+    from oracle import session_agg
+    pcm, off, _ = _batch([2.0, 2.5, 3.0, 2.2, 2.7], start=70)
+    dpcm = torch.from_numpy(pcm).cuda()
+    feats = torch.empty((5, 25), dtype=torch.float64, device="cuda")
+    status = torch.empty(5, dtype=torch.int32, device="cuda")
+    ex.extract_device(dpcm.data_ptr(), off, feats.data_ptr(), status.data_ptr())
+    codes = np.array([1, 0, 1, 1, 0], np.int32)
+    mean = torch.empty((2, 25), dtype=torch.float64, device="cuda")
+    std = torch.empty((2, 25), dtype=torch.float64, device="cuda")
+    ex.aggregate_sessions_device(feats.data_ptr(), 5, 25, codes, 2, mean.data_ptr(), std.data_ptr())
+    torch.cuda.synchronize()
+    wm, ws = session_agg.group_mean_std(feats.cpu().numpy(), codes, 2)
+    assert np.array_equal(mean.cpu().numpy(), wm, equal_nan=True) and np.array_equal(std.cpu().numpy(), ws, equal_nan=True)
