@@ -45,7 +45,8 @@ void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ candidates
 struct CandScratch {
-    double* rs0;        // [2B+1] symmetric correlation, rs0[B+i] = r[i]
+    double* rs0;        // [2Bs+1] symmetric correlation, rs0[Bs+i] = r[i], Bs = min(B, maximumLag + 32): the first pass
+                        // never looks further than a depth-30 window around a lag below maximumLag
     double* pk_f;       // [MAXPK]
     double* pk_s;
     double* pk_key;
@@ -88,7 +89,7 @@ __device__ __forceinline__ int insert_candidates(const PitchCfg& g, const CandSc
 // of the lower threshold are a superset, the first-pass values are shared).  Returns ncand | ncand2 << 8.
 // Harmonicity pass (maxn = 133 never fills, all path costs zero): only the list of maxima is built; returns their number.
 template <int NT>
-__device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int hnr_mode,
+__device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, const CandScratch& S, int B, int Bs, int hnr_mode,
                                                const double2* __restrict__ tw, double vt2, double* cf2, double* cs2,
                                                double* ckey2, int* cimax2) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -98,7 +99,7 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
     int nlag = upper - 2;                                   // lags 2 .. upper-1
     if (nlag < 0) nlag = 0;
     int nrounds = (nlag + NT - 1) / NT;
-    const double* r = S.rs0 + B;                            // r[i], i in [-B, B]
+    const double* r = S.rs0 + Bs;                           // r[i], i in [-Bs, Bs]
     for (int round = 0; round < nrounds; round++) {
         int i = 2 + round * NT + tid;
         bool flag = false;
@@ -126,12 +127,12 @@ __device__ __forceinline__ int find_candidates(const PitchCfg& g, double dx, con
     const int nmax = S.s_int[0];
     if (hnr_mode) return nmax;          // harmonicity: every maximum is refined, the caller queues them
     const double* y1 = S.rs0 - 1;                           // 1-based view: y1[j] = r[j - B - 1]
-    const int ny = 2 * B + 1;
+    const int ny = 2 * Bs + 1;
     for (int m = warp; m < nmax; m += (NT / 32)) {
         int i = S.pk_lag[m];
         double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
         double freq = 1.0 / dx / (i + dr / d2r);
-        double x = 1.0 / dx / freq + (double)(B + 1);
+        double x = 1.0 / dx / freq + (double)(Bs + 1);
         double strength = sinc_interp_warp(y1, ny, x, 30, lane, tw);
         if (strength > 1.0) strength = 1.0 / strength;
         if (lane == 0) {
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
         const long long leftSample = x_to_low(x1, dx, t), rightSample = leftSample + 1;
         const double globalPeak = c.gpeak[clip];
         const int B = g.brent_ixmax;
+        const int Bs = B < g.maximumLag + 32 ? B : g.maximumLag + 32;      // extent of the shared-memory copy (see CandScratch)
         const int W = g.nsamp_window;
 
         // local mean over one longest period to both sides
@@ -313,8 +315,7 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
             const double ac0 = ac[SWZD(0)];
             for (int i = tid; i <= B; i += NT) {
                 double v = i == 0 ? 1.0 : ac[SWZD(i)] / (ac0 * __ldg(g.windowR + i));
-                S.rs0[B + i] = v;
-                S.rs0[B - i] = v;
+                if (i <= Bs) { S.rs0[Bs + i] = v; S.rs0[Bs - i] = v; }
                 rrow[i] = v;
             }
         } else {
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
             // xs[j-1] = s[startS-1+j] - localMean, j = 1..localSpan; zero tail so the tiled loop may read ahead
             const int xs_len = g.maximumLag + W + 32;      // read-ahead of the tiled loop: < 2 * TL + 1 samples past the span
             for (int j = tid; j < xs_len; j += NT) xs[j] = j < (int)localSpan ? samp(pcm, startS - 1 + j) - localMean : 0.0;
-            for (int i = tid; i < 2 * B + 1; i += NT) S.rs0[i] = 0.0;
+            for (int i = tid; i < 2 * Bs + 1; i += NT) S.rs0[i] = 0.0;
             for (int i = tid; i < Ls; i += NT) rrow[i] = 0.0;
             __syncthreads();
             // prefix sums of squares: sq[k] = sum_{j<k} xs[j]^2  (stored behind the partial products)
@@ -368,11 +369,11 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
                 for (int ch = 0; ch < nchunk; ch++) pr += part[(size_t)ch * PS + lag - 1];
                 double sy = sq[lag + W] - sq[lag];
                 double v = pr / sqrt(sumx2 * sy);
-                S.rs0[B + lag] = v;
-                S.rs0[B - lag] = v;
+                S.rs0[Bs + lag] = v;
+                S.rs0[Bs - lag] = v;
                 if (lag < Ls) rrow[lag] = v;
             }
-            if (tid == 0) { S.rs0[B] = 1.0; rrow[0] = 1.0; }
+            if (tid == 0) { S.rs0[Bs] = 1.0; rrow[0] = 1.0; }
         }
         __syncthreads();
 
@@ -383,8 +384,8 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
             double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
             uvs = g.vt + (uvs > 0 ? uvs : 0);
             int nmax = 0;
-            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates<NT>(g, dx, S, B, 1, tw, -1.0, cf2, cs2, ckey2, cimax2);
-            const double* r = S.rs0 + B;
+            if (localPeak != 0.0 && uvs < 1.0) nmax = find_candidates<NT>(g, dx, S, B, Bs, 1, tw, -1.0, cf2, cs2, ckey2, cimax2);
+            const double* r = S.rs0 + Bs;
             for (int m = tid; m < nmax; m += NT) {
                 const int i = S.pk_lag[m];
                 double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
         const bool dual = p.dual_cand_f != nullptr;
         int ncand = 1, ncand2 = 1;
         if (localPeak != 0.0) {
-            int nn = find_candidates<NT>(g, dx, S, B, 0, tw, dual ? p.dual_vt : -1.0, cf2, cs2, ckey2, cimax2);
+            int nn = find_candidates<NT>(g, dx, S, B, Bs, 0, tw, dual ? p.dual_vt : -1.0, cf2, cs2, ckey2, cimax2);
             ncand = nn & 0xff;
             if (dual) ncand2 = nn >> 8;
         } else if (tid == 0) {
@@ -454,7 +455,8 @@ static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
         const PitchCfg& g = p.cfg[k];
         int need_a = is_cc ? (int)sizeof(double) * (g.maximumLag + g.nsamp_window + 40) : (int)sizeof(double2) * g.M;
         if (need_a > ab) ab = need_a;
-        if (2 * g.brent_ixmax + 1 > rs) rs = 2 * g.brent_ixmax + 1;
+        const int bs = g.brent_ixmax < g.maximumLag + 32 ? g.brent_ixmax : g.maximumLag + 32;
+        if (2 * bs + 1 > rs) rs = 2 * bs + 1;
         if (g.maximumLag > ml) ml = g.maximumLag;
     }
     FrameSmem L;
@@ -518,15 +520,18 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     int maxM = 0;
     for (int k = 0; k < 3; k++) if (p.cfg[k].M > maxM) maxM = p.cfg[k].M;
     const int nt = is_cc ? (nt_cc ? nt_cc : 128) : (nt_ac ? nt_ac : (maxM >= 2048 ? 256 : 128));
-    if (nt == 128) {
-        grid = nsm * (blocks_per_sm * 2 > 8 ? 8 : blocks_per_sm * 2);
-        if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
-        if (grid < 1) grid = 1;
-    }
+    // persistent grid: exactly the CTAs that are resident at once (registers or shared memory, whichever binds)
 #define PF_LAUNCH(CC, N) \
     do { \
         cudaFuncSetAttribute(k_pitch_frames<CC, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         cudaFuncSetAttribute(k_pitch_frames<CC, N>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        int occ = 0; \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pitch_frames<CC, N>, N, smem); \
+        if (occ < 1) occ = 1; \
+        grid = nsm * occ; \
+        const int nturn = (max_frames_hint + FRAMES_PER_TURN - 1) / FRAMES_PER_TURN; \
+        if (max_frames_hint > 0 && grid > nturn) grid = nturn; \
+        if (grid < 1) grid = 1; \
         k_pitch_frames<CC, N><<<grid, N, smem, s>>>(c, p, tw, L); \
     } while (0)
     if (is_cc) { if (nt == 128) PF_LAUNCH(true, 128); else PF_LAUNCH(true, 256); }
