@@ -41,7 +41,7 @@ struct mshds_handle {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // latency-bound single-warp-per-clip kernels (Viterbi, pulse walks, interval logic) are issued on a side stream so that
     // they run underneath the frame kernels of the next analysis; `cur` is the stream work is being issued on right now
-    cudaStream_t side = nullptr, cur = nullptr;
+    cudaStream_t side = nullptr, cur = nullptr, copy = nullptr;
     cudaEvent_t ev[12] = {};
     bool overlap = true;
     std::string err;
@@ -429,12 +429,14 @@ static int make_formant_window(mshds_handle* h, int nsw, const double** win) {
 // ------------------------------------------------------------------------------------------------ CPP stage
 // The voiced-segment list only exists on the device; one small read-back per chunk sizes the per-segment FFTs.
 static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long long>& off_host, const std::vector<long long>& lens,
-                         const std::vector<double>& x1_host, const CppSegs& sg, const std::vector<int>& scap, int* d_seg_prefix, double fs, cudaStream_t s) {
+                         const std::vector<double>& x1_host, const CppSegs& sg, const std::vector<int>& scap, int* d_seg_prefix, double fs, cudaStream_t s,
+                         cudaStream_t rb /* read-back stream: already ordered after the voiced-interval kernel */) {
     const int n = c.n;
     const double dx = 1.0 / fs, fs10 = 10000.0;
+    // The host only waits for `rb`; whatever is still queued on `s` keeps the GPU busy while the segment plan is built.
     std::vector<int> cnt(n);
-    CK(cudaMemcpyAsync(cnt.data(), sg.count, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpyAsync(cnt.data(), sg.count, sizeof(int) * n, cudaMemcpyDeviceToHost, rb));
+    CK(cudaStreamSynchronize(rb));
     std::vector<int> sprefix(n + 1, 0);
     for (int i = 0; i < n; i++) sprefix[i + 1] = sprefix[i] + cnt[i];
     const int nsegs = sprefix[n];
@@ -443,11 +445,11 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     std::vector<long long> ix1(scap[n]);
     std::vector<int> nseg(scap[n]);
     if (nsegs > 0) {
-        CK(cudaMemcpyAsync(tmin.data(), sg.tmin, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(tmax.data(), sg.tmax, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ix1.data(), sg.ix1, sizeof(long long) * scap[n], cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(nseg.data(), sg.nseg, sizeof(int) * scap[n], cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(tmin.data(), sg.tmin, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, rb));
+        CK(cudaMemcpyAsync(tmax.data(), sg.tmax, sizeof(double) * scap[n], cudaMemcpyDeviceToHost, rb));
+        CK(cudaMemcpyAsync(ix1.data(), sg.ix1, sizeof(long long) * scap[n], cudaMemcpyDeviceToHost, rb));
+        CK(cudaMemcpyAsync(nseg.data(), sg.nseg, sizeof(int) * scap[n], cudaMemcpyDeviceToHost, rb));
+        CK(cudaStreamSynchronize(rb));
     }
     ResamplePlan plan;
     std::vector<CepSeg> cseg(nsegs);
@@ -854,7 +856,9 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
 
     // ---- _extract_CPP, second half (one small read-back, then resample / cepstrogram / CPPS of every voiced interval)
     WAIT(ev_vuv);
-    if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, q))) return rc;
+    cudaStream_t rb = s;
+    if (side != s) { rb = h->copy; cudaStreamWaitEvent(rb, ev_vuv, 0); }
+    if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, q, rb))) return rc;
 
     WAIT(ev_fmt);
     launch_formant_stats(c, fm, pl_fm, q); h->launches += 1;
@@ -902,7 +906,8 @@ int mshds_create(int device, mshds_handle** out) {
         return MSHDS_ERR_CUDA;
     }
     h->stream = h->own_stream;
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     for (auto& e : h->ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     { const char* e = getenv("MSHDS_NO_OVERLAP"); h->overlap = !(e && atoi(e)); }     // development switch
     // twiddle table exp(-2 pi i j / TW_N), j < TW_N/2
@@ -935,6 +940,7 @@ void mshds_destroy(mshds_handle* h) {
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->copy) cudaStreamDestroy(h->copy);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
 }
