@@ -98,6 +98,45 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
 int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows, int n_cols, const int32_t* row_group,
                              int n_groups, double* mean_out, double* std_out, unsigned flags);
 
+/*
+ * Frame-level low-level descriptors + functionals: first slice of the reference's OTHER handcrafted extractor, the
+ * OpenSMILE run of src/opensmile_extractor.py:9-103 with Androids.conf (the SMILExtract binary itself is
+ * not available, so the component chain is restated here and in oracle/lld_oracle.py -- parity unpinned).  Covered:
+ * cFramer -> cVectorPreemphasis -> cWindower -> cTransformFFT -> cFFTmagphase -> cMelspec -> cMfcc (Androids.conf:73-115),
+ * cEnergy rms (:117-123), cMZcr zcr (:125-132), and the mean / standard deviation functionals over a recording.
+ *
+ * Definitions (fs = sample_rate, x = pcm / 32768):
+ *   frames      nf = round(frame_size * fs) samples every ns = round(frame_step * fs); only complete frames:
+ *               n_frames = nx >= nf ? (nx - nf) / ns + 1 : 0
+ *   zcr         #{ j in 1..nf-1 : x[j] * x[j-1] < 0 } / (nf - 1), on the raw frame
+ *   pre-emph    y[0] = (1 - k) * x[0],  y[j] = x[j] - k * x[j-1]
+ *   window      Hamming  w[j] = 0.54 - 0.46 cos(2 pi j / (nf - 1))
+ *   energy      sqrt( sum (y w)^2 / nf )
+ *   spectrum    magnitude of the n_fft-point DFT of the zero-padded windowed frame, bins k = 0 .. n_fft/2
+ *   mel bank    mel(f) = 1127 ln(1 + f / 700); n_mel + 2 points equally spaced on [mel(mel_lo), mel(min(mel_hi, fs/2))];
+ *               band m = triangle over points m-1, m, m+1 evaluated at mel(k fs / n_fft); E_m = sum_k H_m(k) |X[k]|
+ *   mfcc        c_i = sqrt(2 / n_mel) sum_m ln(max(E_m, 1e-10)) cos(pi i (m - 1/2) / n_mel), i = 1 .. n_mfcc,
+ *               times 1 + (L / 2) sin(pi i / L) for cep_lifter L > 0
+ * Row layout of a frame: mfcc[1..n_mfcc], energy, zcr (D = n_mfcc + 2 values).  functionals: n_clips x 2D (D means, then D
+ * population standard deviations; NaN for a clip without a complete frame).  frames_out (optional, may be NULL): all frame
+ * rows, clips back to back; frame_offsets (optional HOST array, n_clips + 1) receives the first row of every clip.
+ * flags: MSHDS_PCM_ON_DEVICE / MSHDS_OUT_ON_DEVICE as for mshds_extract (the latter covers functionals and frames_out).
+ */
+typedef struct mshds_lld_params {
+    double frame_size;      /* s     0.025   Androids.conf:77  */
+    double frame_step;      /* s     0.010   Androids.conf:78  */
+    double preemph;         /*       0.97    Androids.conf:83  */
+    int n_fft;              /*       0 = smallest power of two >= nf (cTransformFFT zero-pads); else a power of two in [nf, 8192] */
+    int n_mel;              /*       26      cMelspec default nBands */
+    double mel_lo, mel_hi;  /* Hz    20, 8000  Androids.conf:106-107 */
+    int n_mfcc;             /*       12      Androids.conf:112-113 (coefficients 1..12) */
+    double cep_lifter;      /*       22      cMfcc default */
+} mshds_lld_params;
+void mshds_lld_default_params(mshds_lld_params* p);
+int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
+                      const mshds_lld_params* params, double* functionals, double* frames_out, int64_t* frame_offsets,
+                      unsigned flags);
+
 /* Number of kernel launches issued by this handle since creation (bench.py reports it as gpu_launches). */
 long long mshds_launch_count(const mshds_handle* h);
 

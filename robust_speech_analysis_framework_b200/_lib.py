@@ -28,6 +28,7 @@ AGG_ON_DEVICE = 1
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
     "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report", "mshds_aggregate_sessions",
+    "mshds_lld_default_params", "mshds_lld_extract",
 ]
 
 _lib = None
@@ -35,6 +36,13 @@ _lib = None
 
 class MshdsError(RuntimeError):
     pass
+
+
+class LldParams(C.Structure):
+    """struct mshds_lld_params (include/mshds_b200.h)."""
+    _fields_ = [("frame_size", C.c_double), ("frame_step", C.c_double), ("preemph", C.c_double), ("n_fft", C.c_int),
+                ("n_mel", C.c_int), ("mel_lo", C.c_double), ("mel_hi", C.c_double), ("n_mfcc", C.c_int),
+                ("cep_lifter", C.c_double)]
 
 
 def load(build_if_needed: bool = True) -> C.CDLL:
@@ -61,6 +69,10 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.mshds_aggregate_sessions.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_uint]
+    lib.mshds_lld_default_params.argtypes = [C.POINTER(LldParams)]
+    lib.mshds_lld_default_params.restype = None
+    lib.mshds_lld_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(LldParams), C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_uint]
     lib.mshds_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
@@ -120,6 +132,41 @@ class Extractor:
 
     def profile(self, on: bool):
         self._check(self._lib.mshds_profile_enable(self._h, int(on)))
+
+    def lld_params(self, **kw) -> "LldParams":
+        p = LldParams()
+        self._lib.mshds_lld_default_params(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise MshdsError(f"unknown LLD parameter {k!r}")
+            setattr(p, k, v)
+        return p
+
+    def lld_extract(self, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int = 16000, want_frames: bool = False, **params):
+        """mshds_lld_extract on host arrays -> (functionals [n, 2D], frames [total, D] or None, frame_offsets [n + 1])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        p = self.lld_params(**params)
+        D = p.n_mfcc + 2
+        fun = np.full((max(n, 0), 2 * D), np.nan)
+        fo = np.zeros(n + 1, dtype=np.int64)
+        frames = None
+        if want_frames:
+            nf, ns = int(np.floor(p.frame_size * sample_rate + 0.5)), int(np.floor(p.frame_step * sample_rate + 0.5))
+            lens = np.diff(offsets)
+            total = int(np.where(lens >= nf, (lens - nf) // max(ns, 1) + 1, 0).sum()) if nf >= 2 and ns >= 1 else 0
+            frames = np.zeros((total, D))
+        self._check(self._lib.mshds_lld_extract(self._h, pcm.ctypes.data, offsets.ctypes.data, n, int(sample_rate), C.byref(p),
+                                                fun.ctypes.data, frames.ctypes.data if frames is not None and frames.size else None,
+                                                fo.ctypes.data, 0))
+        return fun, frames, fo
+
+    def lld_extract_device(self, pcm_ptr: int, offsets: np.ndarray, out_ptr: int, sample_rate: int = 16000, **params):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        p = self.lld_params(**params)
+        self._check(self._lib.mshds_lld_extract(self._h, C.c_void_p(pcm_ptr), offsets.ctypes.data, len(offsets) - 1, int(sample_rate),
+                                                C.byref(p), C.c_void_p(out_ptr), None, None, PCM_ON_DEVICE | OUT_ON_DEVICE))
 
     def aggregate_sessions(self, features: np.ndarray, row_group: np.ndarray, n_groups: int):
         """mshds_aggregate_sessions on host arrays: (mean [g, d], std [g, d]) of the rows of every session."""

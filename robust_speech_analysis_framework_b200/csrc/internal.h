@@ -112,6 +112,24 @@ struct LtasPass {
 void launch_ltas(const Clips& c, const PulseSet& ps, const LtasPass& lt, double* ltas_bands /*[n*50]*/, cudaStream_t s);
 
 // ---- launchers (each in its own .cu) ----------------------------------------------------------------------------
+// frame-level descriptors of the OpenSMILE path (k_lld.cu)
+struct LldPass {
+    int nf, ns;                 // frame length / step in samples
+    int n_fft, M, logM;         // transform size, M = n_fft / 2
+    int n_mel, n_mfcc;
+    double preemph, lifter, dct_scale, log_floor;
+    const double* window;       // [nf] Hamming
+    const double* melbin;       // [M + 1] mel value of every bin
+    const double* centres;      // [n_mel + 2] band edges / centres on the mel axis
+    const int* klo; const int* khi;   // [n_mel] first / last bin with a non-zero weight
+    const double* dct;          // [n_mfcc * n_mel] cos(pi * i * (m + 0.5) / n_mel), i = 1..n_mfcc
+    int* nF; int* fstart;       // [n], [n + 1]
+    double* frames;             // [total_frames * (n_mfcc + 2)]
+};
+void launch_lld_grid(int n, const long long* off, int nf, int ns, int* nF, int* fstart, cudaStream_t s);
+void launch_lld_frames(const LldPass& p, const int16_t* pcm, const long long* off, int n, const double2* tw, long long frames_hint,
+                       cudaStream_t s);
+void launch_lld_functionals(const LldPass& p, int n, double* out, cudaStream_t s);
 void launch_session_agg(const double* feat, int n_cols, const int* row_start, const int* rows, int n_groups, double* mean_out,
                         double* std_out, cudaStream_t s);
 void launch_finalize_status(const Clips& c, cudaStream_t s);

@@ -59,6 +59,9 @@ struct mshds_handle {
     // scratch of the resample-to-16-kHz front-end
     char* front_buf = nullptr;
     size_t front_cap = 0;
+    // scratch of the frame-level descriptor path (mshds_lld_extract)
+    char* lld_buf = nullptr;
+    size_t lld_cap = 0;
     // arena
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -936,6 +939,7 @@ void mshds_destroy(mshds_handle* h) {
     for (auto& kv : h->gauss_formant) cudaFree(kv.second);
     cudaFree(h->cpp_buf);
     cudaFree(h->front_buf);
+    cudaFree(h->lld_buf);
     cudaFree(h->tw);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1103,6 +1107,117 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
         prof_collect(h);
         c0 = c1;
     }
+    return MSHDS_OK;
+}
+
+void mshds_lld_default_params(mshds_lld_params* p) {
+    if (!p) return;
+    p->frame_size = 0.025; p->frame_step = 0.010; p->preemph = 0.97; p->n_fft = 0; p->n_mel = 26;
+    p->mel_lo = 20.0; p->mel_hi = 8000.0; p->n_mfcc = 12; p->cep_lifter = 22.0;
+}
+
+int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
+                      const mshds_lld_params* prm, double* functionals, double* frames_out, int64_t* frame_offsets,
+                      unsigned flags) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->err.clear();
+    mshds_lld_params P;
+    if (prm) P = *prm; else mshds_lld_default_params(&P);
+    if (n_clips < 0 || !offsets || (n_clips > 0 && !functionals) || sample_rate < 1000 || sample_rate > 384000) { h->err = "bad argument"; return MSHDS_ERR_ARG; }
+    for (int i = 0; i < n_clips; i++) if (offsets[i + 1] < offsets[i]) { h->err = "offsets must be non-decreasing"; return MSHDS_ERR_ARG; }
+    if (n_clips > 0 && offsets[n_clips] > offsets[0] && !pcm) { h->err = "pcm is NULL"; return MSHDS_ERR_ARG; }
+    const double fs = (double)sample_rate;
+    const int nf = (int)floor(P.frame_size * fs + 0.5), ns = (int)floor(P.frame_step * fs + 0.5);
+    if (nf < 2 || ns < 1 || nf > 8192) { h->err = "frame_size / frame_step out of range"; return MSHDS_ERR_ARG; }
+    int n_fft = P.n_fft;
+    if (n_fft == 0) { n_fft = 64; while (n_fft < nf) n_fft <<= 1; }
+    if (n_fft < nf || n_fft < 64 || n_fft > 8192 || (n_fft & (n_fft - 1))) { h->err = "n_fft must be a power of two in [max(64, frame length), 8192]"; return MSHDS_ERR_ARG; }
+    if (P.n_mel < 2 || P.n_mel > 256 || P.n_mfcc < 1 || P.n_mfcc >= P.n_mel || !(P.preemph >= 0.0 && P.preemph < 1.0)) { h->err = "bad n_mel / n_mfcc / preemph"; return MSHDS_ERR_ARG; }
+    const double hi = P.mel_hi < 0.5 * fs ? P.mel_hi : 0.5 * fs;
+    if (!(P.mel_lo >= 0.0 && P.mel_lo < hi)) { h->err = "bad mel range"; return MSHDS_ERR_ARG; }
+    if (n_clips == 0) return MSHDS_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->cur = s;
+    const bool pcm_dev = (flags & MSHDS_PCM_ON_DEVICE) != 0, out_dev = (flags & MSHDS_OUT_ON_DEVICE) != 0;
+    const int M = n_fft / 2, D = P.n_mfcc + 2;
+    int logM = 0; while ((1 << logM) < M) logM++;
+    // ---- host tables
+    std::vector<double> window(nf), melbin(M + 1), centres(P.n_mel + 2), dct((size_t)P.n_mfcc * P.n_mel);
+    std::vector<int> klo(P.n_mel), khi(P.n_mel);
+    for (int j = 0; j < nf; j++) window[j] = 0.54 - 0.46 * cos(2.0 * MSHDS_PI * (double)j / (double)(nf - 1));
+    auto mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+    for (int k = 0; k <= M; k++) melbin[k] = mel((double)k * fs / (double)n_fft);
+    const double m_lo = mel(P.mel_lo), m_hi = mel(hi);
+    for (int m = 0; m < P.n_mel + 2; m++) centres[m] = m_lo + (m_hi - m_lo) * (double)m / (double)(P.n_mel + 1);
+    for (int m = 0; m < P.n_mel; m++) {
+        int a = M + 1, b = -1;
+        for (int k = 0; k <= M; k++) if (melbin[k] > centres[m] && melbin[k] < centres[m + 2]) { if (k < a) a = k; b = k; }
+        klo[m] = a; khi[m] = b;                      // empty band: klo > khi
+    }
+    for (int i = 0; i < P.n_mfcc; i++)
+        for (int m = 0; m < P.n_mel; m++) dct[(size_t)i * P.n_mel + m] = cos(MSHDS_PI * (double)(i + 1) * ((double)m + 0.5) / (double)P.n_mel);
+    // ---- frame counts
+    std::vector<long long> off(n_clips + 1);
+    std::vector<long long> fo(n_clips + 1, 0);
+    for (int i = 0; i <= n_clips; i++) off[i] = offsets[i] - offsets[0];
+    for (int i = 0; i < n_clips; i++) {
+        const long long nx = off[i + 1] - off[i];
+        fo[i + 1] = fo[i] + (nx >= nf ? (nx - nf) / ns + 1 : 0);
+    }
+    const long long total_frames = fo[n_clips], total = off[n_clips];
+    if (total_frames > 0x7fffff00LL) { h->err = "too many frames for one call"; return MSHDS_ERR_ARG; }
+    if (frame_offsets) for (int i = 0; i <= n_clips; i++) frame_offsets[i] = fo[i];
+    // ---- device buffer (grow-only)
+    size_t need = 0;
+    auto sz = [&](size_t bytes) { size_t o = (need + 255) & ~(size_t)255; need = o + bytes; return o; };
+    const size_t o_off = sz(sizeof(long long) * (n_clips + 1)), o_nF = sz(sizeof(int) * n_clips), o_fs = sz(sizeof(int) * (n_clips + 1));
+    const size_t o_win = sz(sizeof(double) * nf), o_mb = sz(sizeof(double) * (M + 1)), o_c = sz(sizeof(double) * (P.n_mel + 2));
+    const size_t o_klo = sz(sizeof(int) * P.n_mel), o_khi = sz(sizeof(int) * P.n_mel), o_dct = sz(sizeof(double) * dct.size());
+    const size_t o_fr = (out_dev && frames_out) ? 0 : sz(sizeof(double) * (size_t)(total_frames + 1) * D);
+    const size_t o_fun = out_dev ? 0 : sz(sizeof(double) * (size_t)n_clips * 2 * D);
+    const size_t o_pcm = pcm_dev ? 0 : sz((size_t)total * 2 + 16);
+    if (need > h->lld_cap) {
+        CK(cudaStreamSynchronize(s));
+        if (h->lld_buf) CK(cudaFree(h->lld_buf));
+        h->lld_buf = nullptr; h->lld_cap = 0;
+        CK(cudaMalloc((void**)&h->lld_buf, need + (need >> 3)));
+        h->lld_cap = need + (need >> 3);
+    }
+    char* Bf = h->lld_buf;
+    CK(cudaMemcpyAsync(Bf + o_off, off.data(), sizeof(long long) * (n_clips + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_win, window.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_mb, melbin.data(), sizeof(double) * (M + 1), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_c, centres.data(), sizeof(double) * (P.n_mel + 2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_klo, klo.data(), sizeof(int) * P.n_mel, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_khi, khi.data(), sizeof(int) * P.n_mel, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(Bf + o_dct, dct.data(), sizeof(double) * dct.size(), cudaMemcpyHostToDevice, s));
+    const int16_t* d_pcm = pcm_dev ? pcm + offsets[0] : (const int16_t*)(Bf + o_pcm);
+    if (!pcm_dev && total > 0) CK(cudaMemcpyAsync(Bf + o_pcm, pcm + offsets[0], (size_t)total * 2, cudaMemcpyHostToDevice, s));
+    LldPass L;
+    L.nf = nf; L.ns = ns; L.n_fft = n_fft; L.M = M; L.logM = logM; L.n_mel = P.n_mel; L.n_mfcc = P.n_mfcc;
+    L.preemph = P.preemph; L.lifter = P.cep_lifter; L.dct_scale = sqrt(2.0 / (double)P.n_mel); L.log_floor = 1e-10;
+    L.window = (const double*)(Bf + o_win); L.melbin = (const double*)(Bf + o_mb); L.centres = (const double*)(Bf + o_c);
+    L.klo = (const int*)(Bf + o_klo); L.khi = (const int*)(Bf + o_khi); L.dct = (const double*)(Bf + o_dct);
+    L.nF = (int*)(Bf + o_nF); L.fstart = (int*)(Bf + o_fs);
+    L.frames = (out_dev && frames_out) ? frames_out : (double*)(Bf + o_fr);
+    double* d_fun = out_dev ? functionals : (double*)(Bf + o_fun);
+    PB("lld_frames[mfcc+energy+zcr]");
+    launch_lld_grid(n_clips, (const long long*)(Bf + o_off), nf, ns, L.nF, L.fstart, s);
+    launch_lld_frames(L, d_pcm, (const long long*)(Bf + o_off), n_clips, h->tw, total_frames, s);
+    PE();
+    PB("lld_functionals");
+    launch_lld_functionals(L, n_clips, d_fun, s);
+    PE();
+    h->launches += 4;
+    CK(cudaGetLastError());
+    if (!out_dev) {
+        CK(cudaMemcpyAsync(functionals, d_fun, sizeof(double) * (size_t)n_clips * 2 * D, cudaMemcpyDeviceToHost, s));
+        if (frames_out && total_frames > 0)
+            CK(cudaMemcpyAsync(frames_out, L.frames, sizeof(double) * (size_t)total_frames * D, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    prof_collect(h);
     return MSHDS_OK;
 }
 

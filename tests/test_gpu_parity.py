@@ -357,3 +357,47 @@ def test_androids_scale_ragged_batch_against_stored_oracle_values(ex):
     # the 10 min clip alone, in a chunk of its own, gives the same row bit for bit (batch composition invariance)
     alone, _ = ex.extract_host(pcm[off[0]:off[1]], np.array([0, off[1] - off[0]], np.int64))
     assert np.array_equal(alone[0], got[0], equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------ OpenSMILE LLD slice (8f-1)
+@pytest.mark.parametrize("fs,params", [
+    (16000, {}),
+    (16000, {"n_fft": 512, "n_mel": 40}), (16000, {"n_fft": 1024, "n_mel": 80}), (16000, {"n_fft": 2048, "n_mel": 40}),   # configs[4] sweep
+    (44100, {}),                                                                        # Androids.conf:70 sampleRate
+    (16000, {"frame_size": 0.032, "frame_step": 0.008, "n_mfcc": 19, "n_mel": 64, "cep_lifter": 0.0, "preemph": 0.0}),
+])
+def test_lld_frames_and_functionals_match_the_numpy_restatement(ex, fs, params):
+    """mshds_lld_extract (MFCC 1-12, RMS energy, ZCR per frame; mean / stddev per recording) against oracle/lld_oracle.py.
+    Tolerance: 1e-9 relative / 1e-9 absolute (north_star: 1e-4 relative for spectral / MFCC statistics); ZCR exact."""
+    from oracle import lld_oracle as lo
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    rng = np.random.default_rng(4)
+    clips = [synth_clip(600 + i, d, fs=fs).numpy() for i, d in enumerate([1.5, 0.73, 2.2])]
+    clips += [np.zeros(0, np.int16), np.zeros(int(0.02 * fs), np.int16), np.zeros(int(0.3 * fs), np.int16),
+              (rng.normal(scale=3000, size=int(0.5 * fs))).astype(np.int16)]
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    fun, frames, fo = ex.lld_extract(pcm, off, fs, want_frames=True, **params)
+    wfun, wrows = lo.extract(pcm, off, float(fs), **params)
+    D = wfun.shape[1] // 2
+    assert list(np.diff(fo)) == [len(r) for r in wrows] and frames.shape == (int(fo[-1]), D)
+    want = np.concatenate([r for r in wrows if len(r)])
+    np.testing.assert_allclose(frames, want, rtol=1e-9, atol=1e-9)
+    assert np.array_equal(frames[:, D - 1], want[:, D - 1])                      # zero-crossing rate: integer count / (nf - 1)
+    assert np.array_equal(np.isnan(fun), np.isnan(wfun)) and np.isnan(fun[3]).all() and np.isnan(fun[4]).all()
+    np.testing.assert_allclose(fun, wfun, rtol=1e-9, atol=1e-9, equal_nan=True)
+
+
+def test_lld_device_entry_and_bad_arguments(ex):
+    import torch
+    from robust_speech_analysis_framework_b200 import _lib
+    pcm, off, _ = _batch([1.0, 1.3], start=80)
+    host, _, _ = ex.lld_extract(pcm, off)
+    d = torch.from_numpy(pcm).cuda()
+    out = torch.empty((2, 28), dtype=torch.float64, device="cuda")
+    ex.lld_extract_device(d.data_ptr(), off, out.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host)
+    for bad in ({"n_fft": 300}, {"n_fft": 256}, {"n_mel": 1}, {"n_mfcc": 26}, {"frame_step": 0.0}, {"mel_lo": 9000.0}):
+        with pytest.raises(_lib.MshdsError):
+            ex.lld_extract(pcm, off, **bad)
