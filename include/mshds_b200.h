@@ -99,6 +99,26 @@ int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows
                              int n_groups, double* mean_out, double* std_out, unsigned flags);
 
 /*
+ * Frame-level contours behind the 25 columns (the per-frame descriptors the dissertation names as the input a
+ * sequence model would need, PDF p.32).  Runs the same pipeline as mshds_extract and copies ONE contour out per call:
+ *   MSHDS_CONTOUR_F0         width 2: frequency in Hz (0 = unvoiced) and strength of the chosen candidate, the Pitch object
+ *                            of _extract_pitch (mshds_extractor.py:178), one row per 5 ms frame
+ *   MSHDS_CONTOUR_INTENSITY  width 1: dB, the Intensity object of :198
+ *   MSHDS_CONTOUR_HNR        width 1: dB (-200 = voiceless), the Harmonicity object of :221
+ *   MSHDS_CONTOUR_FORMANTS   width 4: F1, B1, F2, B2 in Hz (NaN = fewer formants in the frame), the Formant object of :319
+ *   MSHDS_CONTOUR_MOMENTS    width 4: gravity, standard deviation, skewness, kurtosis of voiced spectrogram frames (NaN =
+ *                            unvoiced, skipped at :364), the loop of :362-369
+ * values: HOST buffer of capacity_rows x width doubles, clips back to back; frame_offsets (HOST, n_clips + 1): first row of
+ * every clip; t1 (HOST, n_clips): time of a clip's first frame (NaN if it has none); *dt: frame step; frame k of clip i is at
+ * t1[i] + k * dt.  A clip has at most floor(duration / 0.005) + 2 frames.  features (optional, HOST, n_clips x 25) receives
+ * the feature rows as well.  flags: MSHDS_PCM_ON_DEVICE only.
+ */
+enum mshds_contour { MSHDS_CONTOUR_F0 = 0, MSHDS_CONTOUR_INTENSITY, MSHDS_CONTOUR_HNR, MSHDS_CONTOUR_FORMANTS, MSHDS_CONTOUR_MOMENTS };
+int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate, int contour,
+                           double* values, size_t capacity_rows, int64_t* frame_offsets, double* t1, double* dt, int* width,
+                           double* features, unsigned flags);
+
+/*
  * Frame-level low-level descriptors + functionals: first slice of the reference's OTHER handcrafted extractor, the
  * OpenSMILE run of src/opensmile_extractor.py:9-103 with Androids.conf (the SMILExtract binary itself is
  * not available, so the component chain is restated here and in oracle/lld_oracle.py -- parity unpinned).  Covered:

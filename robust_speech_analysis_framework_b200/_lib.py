@@ -24,11 +24,12 @@ N_FEATURES = 25
 PCM_ON_DEVICE = 1
 OUT_ON_DEVICE = 2
 AGG_ON_DEVICE = 1
+CONTOURS = {"f0": 0, "intensity": 1, "hnr": 2, "formants": 3, "moments": 4}
 
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
     "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report", "mshds_aggregate_sessions",
-    "mshds_lld_default_params", "mshds_lld_extract",
+    "mshds_lld_default_params", "mshds_lld_extract", "mshds_extract_contours",
 ]
 
 _lib = None
@@ -73,6 +74,8 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_lld_default_params.restype = None
     lib.mshds_lld_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(LldParams), C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_uint]
+    lib.mshds_extract_contours.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.c_uint]
     lib.mshds_debug_fetch.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
@@ -132,6 +135,28 @@ class Extractor:
 
     def profile(self, on: bool):
         self._check(self._lib.mshds_profile_enable(self._h, int(on)))
+
+    def extract_contours(self, pcm: np.ndarray, offsets: np.ndarray, which: str, sample_rate: int = 16000):
+        """mshds_extract_contours: per-frame contour `which` in CONTOURS for every clip.
+        Returns dict(values [rows, width], frame_offsets [n + 1], t1 [n], dt, features [n, 25])."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        lens = np.diff(offsets).astype(np.float64)
+        cap = int(np.sum(np.floor(lens / sample_rate / 0.005) + 2)) + 1
+        width = C.c_int(0)
+        dt = C.c_double(0.0)
+        values = np.full((cap, 4), np.nan)
+        fo = np.zeros(n + 1, dtype=np.int64)
+        t1 = np.full(max(n, 1), np.nan)
+        feats = np.full((max(n, 0), N_FEATURES), np.nan)
+        # the library writes rows of `width` doubles; width <= 4, so a [cap, 4] buffer always suffices
+        self._check(self._lib.mshds_extract_contours(self._h, pcm.ctypes.data, offsets.ctypes.data, n, int(sample_rate), CONTOURS[which],
+                                                     values.ctypes.data, cap, fo.ctypes.data, t1.ctypes.data, C.byref(dt), C.byref(width),
+                                                     feats.ctypes.data if n > 0 else None, 0))
+        rows, w = int(fo[-1]), width.value
+        vals = values.ravel()[: rows * w].reshape(rows, w).copy()
+        return dict(values=vals, frame_offsets=fo, t1=t1[:n], dt=dt.value, features=feats)
 
     def lld_params(self, **kw) -> "LldParams":
         p = LldParams()

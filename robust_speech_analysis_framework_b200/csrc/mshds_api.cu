@@ -59,6 +59,11 @@ struct mshds_handle {
     // scratch of the resample-to-16-kHz front-end
     char* front_buf = nullptr;
     size_t front_cap = 0;
+    // per-frame contours of the chunk processed last (sources on the device) and the sink mshds_extract_contours fills
+    struct ContourSrc { const double* a; const double* b; const int* nform; const int* fstart; const int* nF; const double* t1; double dt; };
+    ContourSrc csrc[5] = {};
+    struct ContourSink { int which; double* values; size_t cap_rows; int64_t* frame_offsets; double* t1; long long rows; bool overflow; };
+    ContourSink* sink = nullptr;
     // scratch of the frame-level descriptor path (mshds_lld_extract)
     char* lld_buf = nullptr;
     size_t lld_cap = 0;
@@ -891,6 +896,60 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     reg_debug(h, "resampled10k", fdev.out, nullptr, nullptr, 0, 8);
     h->debug["resampled10k"].host_prefix = fplan.out_prefix;
     h->last_n = n;
+    h->csrc[MSHDS_CONTOUR_F0] = {mainp.sel_f, mainp.sel_s, nullptr, mainp.fstart, mainp.nF, mainp.t1, mainp.cfg[0].dt};
+    h->csrc[MSHDS_CONTOUR_INTENSITY] = {imain.out, nullptr, nullptr, imain.fstart, imain.nF, imain.t1, imain.dt};
+    h->csrc[MSHDS_CONTOUR_HNR] = {hnr.sel_s, nullptr, nullptr, hnr.fstart, hnr.nF, hnr.t1, hnr.cfg[0].dt};
+    h->csrc[MSHDS_CONTOUR_FORMANTS] = {fm.freq, fm.bw, fm.nform, fm.fstart, fm.nF, fm.t1, fm.dt};
+    h->csrc[MSHDS_CONTOUR_MOMENTS] = {spec.mom, nullptr, nullptr, spec.fstart, spec.nF, spec.t1, spec.timeStep};
+    return MSHDS_OK;
+}
+
+static const int kContourWidth[5] = {2, 1, 1, 4, 4};
+
+// copy one contour of the chunk just processed (clips [c0, c0 + n) of the call) into the caller's buffers
+static int collect_contours(mshds_handle* h, int c0, int n) {
+    mshds_handle::ContourSink& K = *h->sink;
+    const mshds_handle::ContourSrc& S = h->csrc[K.which];
+    cudaStream_t s = h->stream;
+    const int W = kContourWidth[K.which];
+    std::vector<int> fstart(n + 1);
+    std::vector<double> t1(n);
+    CK(cudaMemcpyAsync(fstart.data(), S.fstart, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(t1.data(), S.t1, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int total = fstart[n];
+    std::vector<double> a, b;
+    std::vector<int> nform;
+    const int src_w = K.which == MSHDS_CONTOUR_FORMANTS ? 5 : (K.which == MSHDS_CONTOUR_MOMENTS ? 4 : 1);
+    if (total > 0) {
+        a.resize((size_t)total * src_w);
+        CK(cudaMemcpyAsync(a.data(), S.a, sizeof(double) * a.size(), cudaMemcpyDeviceToHost, s));
+        if (S.b) { b.resize((size_t)total * src_w); CK(cudaMemcpyAsync(b.data(), S.b, sizeof(double) * b.size(), cudaMemcpyDeviceToHost, s)); }
+        if (S.nform) { nform.resize(total); CK(cudaMemcpyAsync(nform.data(), S.nform, sizeof(int) * total, cudaMemcpyDeviceToHost, s)); }
+        CK(cudaStreamSynchronize(s));
+    }
+    const double nan = std::nan("");
+    for (int i = 0; i < n; i++) {
+        if (K.t1) K.t1[c0 + i] = fstart[i + 1] > fstart[i] ? t1[i] : nan;
+        if (K.frame_offsets) K.frame_offsets[c0 + i] = K.rows + fstart[i];
+    }
+    for (int f = 0; f < total; f++) {
+        const long long r = K.rows + f;
+        if ((size_t)r >= K.cap_rows) { K.overflow = true; break; }
+        double* o = K.values + (size_t)r * W;
+        switch (K.which) {
+        case MSHDS_CONTOUR_F0: o[0] = a[f]; o[1] = b[f]; break;                              // Hz (0 = unvoiced), strength
+        case MSHDS_CONTOUR_INTENSITY: o[0] = a[f]; break;                                    // dB
+        case MSHDS_CONTOUR_HNR: o[0] = a[f] == a[f] ? 10.0 * log10(a[f] / (1.0 - a[f])) : -200.0; break;   // dB, -200 = voiceless
+        case MSHDS_CONTOUR_FORMANTS:
+            o[0] = nform[f] >= 1 ? a[(size_t)f * 5] : nan; o[1] = nform[f] >= 1 ? b[(size_t)f * 5] : nan;
+            o[2] = nform[f] >= 2 ? a[(size_t)f * 5 + 1] : nan; o[3] = nform[f] >= 2 ? b[(size_t)f * 5 + 1] : nan;
+            break;
+        default: for (int k = 0; k < 4; k++) o[k] = a[(size_t)f * 4 + k];
+        }
+    }
+    K.rows += total;
+    if (K.frame_offsets) K.frame_offsets[c0 + n] = K.rows;
     return MSHDS_OK;
 }
 
@@ -1105,8 +1164,29 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
         }
         CK(cudaStreamSynchronize(s));
         prof_collect(h);
+        if (h->sink && (rc = collect_contours(h, c0, n))) return rc;
         c0 = c1;
     }
+    return MSHDS_OK;
+}
+
+int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate, int contour,
+                           double* values, size_t capacity_rows, int64_t* frame_offsets, double* t1, double* dt, int* width,
+                           double* features, unsigned flags) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->err.clear();
+    if (contour < 0 || contour > 4 || (capacity_rows > 0 && !values) || (flags & MSHDS_OUT_ON_DEVICE)) { h->err = "bad contour argument"; return MSHDS_ERR_ARG; }
+    if (width) *width = kContourWidth[contour];
+    std::vector<double> feat_tmp;
+    if (!features) { feat_tmp.resize((size_t)(n_clips > 0 ? n_clips : 1) * 25); features = feat_tmp.data(); }
+    mshds_handle::ContourSink K{contour, values, capacity_rows, frame_offsets, t1, 0, false};
+    if (frame_offsets && n_clips >= 0) frame_offsets[0] = 0;
+    h->sink = &K;
+    int rc = mshds_extract(h, pcm, offsets, n_clips, sample_rate, features, nullptr, flags);
+    h->sink = nullptr;
+    if (rc) return rc;
+    if (dt) *dt = n_clips > 0 ? h->csrc[contour].dt : 0.0;
+    if (K.overflow) { h->err = "values buffer too small (capacity_rows)"; return MSHDS_ERR_ARG; }
     return MSHDS_OK;
 }
 

@@ -401,3 +401,44 @@ def test_lld_device_entry_and_bad_arguments(ex):
     for bad in ({"n_fft": 300}, {"n_fft": 256}, {"n_mel": 1}, {"n_mfcc": 26}, {"frame_step": 0.0}, {"mel_lo": 9000.0}):
         with pytest.raises(_lib.MshdsError):
             ex.lld_extract(pcm, off, **bad)
+
+
+# ------------------------------------------------------------------------------------------------ frame-level contours (8f-4)
+def test_frame_level_contours_match_the_oracle_objects(ex, orc):
+    """mshds_extract_contours: the Pitch / Intensity / Harmonicity / Formant objects and the per-frame spectral moments behind
+    the 25 columns, against the oracle's per-frame outputs (same tolerances as the stage-level test)."""
+    pcm, off, clips = _batch([3.0, 2.50006, 0.02], start=90)            # the last clip is too short for any analysis
+    want_feats, _ = orc.extract(pcm, off, 16000.0, nthreads=3)
+    res = {k: ex.extract_contours(pcm, off, k) for k in ("f0", "intensity", "hnr", "formants", "moments")}
+    for k, r in res.items():
+        assert r["values"].shape[1] == {"f0": 2, "intensity": 1, "hnr": 1, "formants": 4, "moments": 4}[k]
+        assert r["dt"] == 0.005 and len(r["frame_offsets"]) == 4 and r["frame_offsets"][3] == r["frame_offsets"][2]
+        assert np.isnan(r["t1"][2])
+        assert_features_close(r["features"], want_feats, f"features next to contour {k}")
+    for c in range(2):
+        x = orc.pcm_to_float(clips[c])
+        fl, ce, _ = orc.pitch_values(x)
+        sl = lambda r: r["values"][r["frame_offsets"][c]:r["frame_offsets"][c + 1]]
+        ref = orc.pitch(x, 16000.0, 0, 0.005, fl, 3.0, 15, 0.03, 0.45, 0.01, 0.35, 0.14, ce)
+        got = sl(res["f0"])
+        assert len(got) == len(ref["freq"]) and abs(res["f0"]["t1"][c] - ref["x1"]) < 1e-12
+        np.testing.assert_allclose(got[:, 0], ref["freq"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(got[:, 1], ref["strength"], rtol=0, atol=1e-9)
+        ic, ix1 = orc.intensity(x, 16000.0, fl, 0.005)
+        np.testing.assert_allclose(sl(res["intensity"])[:, 0], ic, rtol=0, atol=1e-10)
+        assert abs(res["intensity"]["t1"][c] - ix1) < 1e-12
+        ph = orc.pitch(x, 16000.0, 2, 0.005, fl, 4.5, 15, 0.1, 0.0, 0.0, 0.0, 0.0, 8000.0)
+        want_h = np.where(ph["freq"] == 0, -200.0, 10.0 * np.log10(np.maximum(ph["strength"], 1e-300) / (1.0 - ph["strength"])))
+        np.testing.assert_allclose(sl(res["hnr"])[:, 0], want_h, rtol=1e-8, atol=1e-8)
+        assert abs(np.mean(want_h[want_h != -200.0]) - want_feats[c, 9]) < 1e-8          # "Get mean" of the Harmonicity (:222)
+        fo = orc.formants(x, 16000.0)
+        gf = sl(res["formants"])
+        assert len(gf) == len(fo["f"])
+        for col, (arr, j) in enumerate(((fo["f"], 0), (fo["bw"], 0), (fo["f"], 1), (fo["bw"], 1))):
+            w = np.where(fo["n"] > j, arr[:, j], np.nan)
+            np.testing.assert_allclose(gf[:, col], w, rtol=1e-6, atol=1e-4, equal_nan=True)
+        gm = sl(res["moments"])
+        np.testing.assert_allclose(np.nanmean(gm, axis=0), want_feats[c, 21:25], rtol=1e-9)    # :371-374
+    from robust_speech_analysis_framework_b200 import _lib
+    with pytest.raises(KeyError):
+        ex.extract_contours(pcm, off, "nope")
