@@ -6,8 +6,9 @@
 // (smooth, getCPPS), LPC/PowerCepstrum.cpp (fitTiltLine, getPeakProminence), dwsys/NUM2.cpp (Theil line fit).
 //
 // One CTA per cepstrogram frame: mean removal, Gaussian window, packed real FFT-1024, log power and the inverse
-// transform stay in shared memory; a second kernel does the 5-frame / 10-bin box smoothing, the dB conversion, the
-// robust tilt line (medians by rank counting, no sort) and the parabolic peak per frame.
+// transform stay in shared memory; a second kernel (one WARP per frame, k_cpp_frames_warp) does the 5-frame / 10-bin box
+// smoothing, the dB conversion, the robust tilt line (two medians by bitonic sorting networks held in registers) and the
+// parabolic peak per frame.
 #include <cstdlib>
 #include "internal.h"
 #define NT_CEP_DEFAULT 128

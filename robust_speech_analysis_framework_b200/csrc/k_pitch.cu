@@ -6,10 +6,12 @@
 // :320 (to_pitch_cc) -- i.e. fon/Sound_to_Pitch.cpp Sound_to_Pitch_any + Sound_into_PitchFrame and
 // fon/Pitch.cpp Pitch_pathFinder.
 //
-// One CTA per frame (persistent grid-stride loop over the flattened frame list of all clips): the frame is staged in
-// shared memory, transformed with the packed real FFT of fft.cuh (AC) or correlated directly (FCC), candidates are
-// refined warp-per-candidate, and only the <=15 candidates leave the SM.
-#include <cstdio>
+// Frame kernel: one CTA (128 or 256 threads) per frame, persistent grid over the flattened frame list of all clips, 8
+// consecutive frames per turn.  The frame is staged in shared memory, transformed with the packed real FFT of fft.cuh (AC) or
+// correlated directly with register-tiled lag windows (FCC); the first pass (maxima, parabolic frequency, sinc30 strength,
+// Praat's slot rule) runs in the CTA.  The correlation row and the <= 15 candidates leave the SM; the candidates that can
+// matter are queued for the refinement kernels (sinc70/700 + Brent, 4 / 8 lanes per item), then k_pitch_score and the
+// warp-per-clip Viterbi (issued on the side stream by mshds_api.cu).
 #include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
