@@ -72,9 +72,105 @@ __device__ __forceinline__ double2 quarter_turn(double2 a) {      // a * exp(SIG
     return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
 }
 
+// a * exp(SIGN * i * pi / 4) and a * exp(SIGN * 3 i pi / 4)
+template <int SIGN>
+__device__ __forceinline__ double2 eighth_turn(double2 a) {
+    const double r = 0.70710678118654752440;
+    return SIGN > 0 ? make_double2((a.x - a.y) * r, (a.x + a.y) * r) : make_double2((a.x + a.y) * r, (a.y - a.x) * r);
+}
+template <int SIGN>
+__device__ __forceinline__ double2 three_eighth_turn(double2 a) {
+    const double r = 0.70710678118654752440;
+    return SIGN > 0 ? make_double2(-(a.x + a.y) * r, (a.x - a.y) * r) : make_double2((a.y - a.x) * r, -(a.x + a.y) * r);
+}
+
+// Three radix-2 DIF stages (spans half, half/2, half/4) fused: 8 points in registers, one shared-memory round trip and one
+// barrier instead of two (radix-2x2 + radix-2).  Same stage sequence, same bit-reversed ordering as the plain radix-2 form.
+template <int SIGN>
+__device__ __forceinline__ void fft_dif_pass8(double2* a, int n, int half, const double2* __restrict__ tw) {
+    const int q = half >> 2;
+    const int lq = __ffs(q) - 1;
+    for (int t = threadIdx.x; t < (n >> 3); t += blockDim.x) {
+        const int pos = t & (q - 1);
+        const int i0 = ((t >> lq) << (lq + 3)) + pos;
+        double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + q)], x2 = a[SWZ(i0 + 2 * q)], x3 = a[SWZ(i0 + 3 * q)];
+        double2 x4 = a[SWZ(i0 + 4 * q)], x5 = a[SWZ(i0 + 5 * q)], x6 = a[SWZ(i0 + 6 * q)], x7 = a[SWZ(i0 + 7 * q)];
+        const double2 w8 = twiddle<SIGN>(tw, pos, 2 * half);
+        const double2 w4 = cmul(w8, w8);
+        const double2 w2 = cmul(w4, w4);
+        // span half: (j, j + 4), twiddle w8 * exp(SIGN 2 pi i j / 8)
+        double2 s0 = cadd(x0, x4), s1 = cadd(x1, x5), s2 = cadd(x2, x6), s3 = cadd(x3, x7);
+        double2 d0 = cmul(csub(x0, x4), w8);
+        double2 d1 = cmul(eighth_turn<SIGN>(csub(x1, x5)), w8);
+        double2 d2 = cmul(quarter_turn<SIGN>(csub(x2, x6)), w8);
+        double2 d3 = cmul(three_eighth_turn<SIGN>(csub(x3, x7)), w8);
+        // span half/2: (j, j + 2) inside each half, twiddle w4 * exp(SIGN 2 pi i (j & 1) / 4)
+        double2 a0 = cadd(s0, s2), a1 = cadd(s1, s3);
+        double2 b0 = cmul(csub(s0, s2), w4), b1 = cmul(quarter_turn<SIGN>(csub(s1, s3)), w4);
+        double2 c0 = cadd(d0, d2), c1 = cadd(d1, d3);
+        double2 e0 = cmul(csub(d0, d2), w4), e1 = cmul(quarter_turn<SIGN>(csub(d1, d3)), w4);
+        // span half/4: neighbours, twiddle w2
+        a[SWZ(i0)] = cadd(a0, a1);
+        a[SWZ(i0 + q)] = cmul(csub(a0, a1), w2);
+        a[SWZ(i0 + 2 * q)] = cadd(b0, b1);
+        a[SWZ(i0 + 3 * q)] = cmul(csub(b0, b1), w2);
+        a[SWZ(i0 + 4 * q)] = cadd(c0, c1);
+        a[SWZ(i0 + 5 * q)] = cmul(csub(c0, c1), w2);
+        a[SWZ(i0 + 6 * q)] = cadd(e0, e1);
+        a[SWZ(i0 + 7 * q)] = cmul(csub(e0, e1), w2);
+    }
+    __syncthreads();
+}
+// the DIT mirror: spans h, 2h, 4h
+template <int SIGN>
+__device__ __forceinline__ void fft_dit_pass8(double2* a, int n, int h, const double2* __restrict__ tw) {
+    const int lh = __ffs(h) - 1;
+    for (int t = threadIdx.x; t < (n >> 3); t += blockDim.x) {
+        const int pos = t & (h - 1);
+        const int i0 = ((t >> lh) << (lh + 3)) + pos;
+        double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + h)], x2 = a[SWZ(i0 + 2 * h)], x3 = a[SWZ(i0 + 3 * h)];
+        double2 x4 = a[SWZ(i0 + 4 * h)], x5 = a[SWZ(i0 + 5 * h)], x6 = a[SWZ(i0 + 6 * h)], x7 = a[SWZ(i0 + 7 * h)];
+        const double2 w8 = twiddle<SIGN>(tw, pos, 8 * h);
+        const double2 w4 = cmul(w8, w8);
+        const double2 w2 = cmul(w4, w4);
+        // span h: neighbours, twiddle w2
+        x1 = cmul(x1, w2); x3 = cmul(x3, w2); x5 = cmul(x5, w2); x7 = cmul(x7, w2);
+        double2 y0 = cadd(x0, x1), y1 = csub(x0, x1), y2 = cadd(x2, x3), y3 = csub(x2, x3);
+        double2 y4 = cadd(x4, x5), y5 = csub(x4, x5), y6 = cadd(x6, x7), y7 = csub(x6, x7);
+        // span 2h: (j, j + 2), twiddle w4 * exp(SIGN 2 pi i (j & 1) / 4)
+        y2 = cmul(y2, w4); y3 = cmul(quarter_turn<SIGN>(y3), w4); y6 = cmul(y6, w4); y7 = cmul(quarter_turn<SIGN>(y7), w4);
+        double2 z0 = cadd(y0, y2), z2 = csub(y0, y2), z1 = cadd(y1, y3), z3 = csub(y1, y3);
+        double2 z4 = cadd(y4, y6), z6 = csub(y4, y6), z5 = cadd(y5, y7), z7 = csub(y5, y7);
+        // span 4h: (j, j + 4), twiddle w8 * exp(SIGN 2 pi i j / 8)
+        z4 = cmul(z4, w8);
+        z5 = cmul(eighth_turn<SIGN>(z5), w8);
+        z6 = cmul(quarter_turn<SIGN>(z6), w8);
+        z7 = cmul(three_eighth_turn<SIGN>(z7), w8);
+        a[SWZ(i0)] = cadd(z0, z4);
+        a[SWZ(i0 + 4 * h)] = csub(z0, z4);
+        a[SWZ(i0 + h)] = cadd(z1, z5);
+        a[SWZ(i0 + 5 * h)] = csub(z1, z5);
+        a[SWZ(i0 + 2 * h)] = cadd(z2, z6);
+        a[SWZ(i0 + 6 * h)] = csub(z2, z6);
+        a[SWZ(i0 + 3 * h)] = cadd(z3, z7);
+        a[SWZ(i0 + 7 * h)] = csub(z3, z7);
+    }
+    __syncthreads();
+}
+
+#ifndef FFT_RADIX8
+#define FFT_RADIX8 1
+#endif
+
 template <int SIGN>
 __device__ __forceinline__ void fft_dif(double2* a, int n, const double2* __restrict__ tw) {
     int half = n >> 1;
+#if FFT_RADIX8
+    while (half >= 4) {            // as many radix-8 passes as fit; a radix-4 or radix-2 pass finishes the small spans
+        fft_dif_pass8<SIGN>(a, n, half, tw);
+        half >>= 3;
+    }
+#endif
     while (half >= 2) {
         const int q = half >> 1;
         const int lq = __ffs(q) - 1;                       // sizes are powers of two: shifts instead of divisions
@@ -108,6 +204,37 @@ __device__ __forceinline__ void fft_dit(double2* a, int n, const double2* __rest
     int logn = 0;
     while ((1 << logn) < n) logn++;
     int half = 1;
+#if FFT_RADIX8
+    {   // mirror of fft_dif: the small-span remainder (radix-2 or radix-4) first, radix-8 passes for everything above
+        const int rem = logn % 3;
+        if (rem == 1) {
+            for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
+                double2 u = a[SWZ(2 * b)], v = a[SWZ(2 * b + 1)];
+                a[SWZ(2 * b)] = cadd(u, v);
+                a[SWZ(2 * b + 1)] = csub(u, v);
+            }
+            __syncthreads();
+            half = 2;
+        } else if (rem == 2) {
+            for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) {
+                const int i0 = t << 2;
+                double2 x0 = a[SWZ(i0)], x1 = a[SWZ(i0 + 1)], x2 = a[SWZ(i0 + 2)], x3 = a[SWZ(i0 + 3)];
+                double2 y0 = cadd(x0, x1), y1 = csub(x0, x1), y2 = cadd(x2, x3), y3 = quarter_turn<SIGN>(csub(x2, x3));
+                a[SWZ(i0)] = cadd(y0, y2);
+                a[SWZ(i0 + 2)] = csub(y0, y2);
+                a[SWZ(i0 + 1)] = cadd(y1, y3);
+                a[SWZ(i0 + 3)] = csub(y1, y3);
+            }
+            __syncthreads();
+            half = 4;
+        }
+        while (half < n) {
+            fft_dit_pass8<SIGN>(a, n, half, tw);
+            half <<= 3;
+        }
+        return;
+    }
+#endif
     if (logn & 1) {
         for (int b = threadIdx.x; b < (n >> 1); b += blockDim.x) {
             double2 u = a[SWZ(2 * b)], v = a[SWZ(2 * b + 1)];
