@@ -48,6 +48,7 @@ enum mshds_feature {
 /* flags of mshds_extract */
 #define MSHDS_PCM_ON_DEVICE (1u << 0)   /* pcm is a device pointer on the handle's device */
 #define MSHDS_OUT_ON_DEVICE (1u << 1)   /* features / status are device pointers */
+#define MSHDS_PCM_FLOAT64   (1u << 2)   /* pcm points to float64 samples in [-1, 1) instead of int16 (24/32-bit and float files) */
 
 /* error codes */
 #define MSHDS_OK 0
@@ -76,6 +77,8 @@ const char* mshds_last_error(const mshds_handle* h);
  * batch of mono recordings already decoded to 16-bit PCM (sample value = pcm / 32768, as parselmouth.Sound(path)
  * gives at :415).  Clip i is pcm[offsets[i] .. offsets[i+1]).  offsets is a HOST array of n_clips + 1 entries.
  * features: n_clips x 25 float64, row-major, column order as enum mshds_feature; status: n_clips words (may be NULL).
+ * With MSHDS_PCM_FLOAT64 `pcm` points to float64 samples in [-1, 1) instead (what parselmouth.Sound holds for 24/32-bit,
+ * float or multi-channel files after convert_to_mono, :415-417); offsets still count samples.
  * sample_rate is the rate of every clip of the call.  Anything but 16000 is first resampled to 16 kHz on the device exactly
  * as the reference does (:418-419 snd.resample(16000, 50): FFT brick-wall low-pass when down-sampling, sinc depth 50), and the
  * analyses then read the float64 result.  8000 Hz is refused with MSHDS_ERR_UNSUPPORTED (Praat switches to Sound_upsample

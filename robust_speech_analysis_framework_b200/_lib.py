@@ -23,6 +23,7 @@ FEATURE_NAMES = [  # /root/reference/src/mshds_extractor.py:397-404
 N_FEATURES = 25
 PCM_ON_DEVICE = 1
 OUT_ON_DEVICE = 2
+PCM_FLOAT64 = 4
 AGG_ON_DEVICE = 1
 CONTOURS = {"f0": 0, "intensity": 1, "hnr": 2, "formants": 3, "moments": 4}
 
@@ -124,6 +125,17 @@ class Extractor:
         status = np.zeros(n, dtype=np.uint32)
         self._check(self._lib.mshds_extract(self._h, pcm.ctypes.data, offsets.ctypes.data, n, int(sample_rate),
                                             out.ctypes.data, status.ctypes.data, 0))
+        return out, status
+
+    def extract_host_f64(self, samples: np.ndarray, offsets: np.ndarray, sample_rate: int = 16000):
+        """Same as extract_host for float64 samples in [-1, 1) (MSHDS_PCM_FLOAT64): 24/32-bit, float and multi-channel files."""
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        out = np.full((max(n, 0), N_FEATURES), np.nan, dtype=np.float64)
+        status = np.zeros(max(n, 0), dtype=np.uint32)
+        self._check(self._lib.mshds_extract(self._h, samples.ctypes.data, offsets.ctypes.data, n, int(sample_rate),
+                                            out.ctypes.data, status.ctypes.data, PCM_FLOAT64))
         return out, status
 
     def extract_device(self, pcm_ptr: int, offsets: np.ndarray, out_ptr: int, status_ptr: int, sample_rate: int = 16000):

@@ -1041,6 +1041,10 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     cudaStream_t s = h->stream;
     h->cur = s;
     const bool pcm_dev = flags & MSHDS_PCM_ON_DEVICE, out_dev = flags & MSHDS_OUT_ON_DEVICE;
+    // MSHDS_PCM_FLOAT64: `pcm` really points to float64 samples in [-1, 1) (what parselmouth.Sound holds for a 24/32-bit or
+    // float file); every kernel reads them through the same SPtr accessor the resampling front-end uses
+    const bool f64_in = (flags & MSHDS_PCM_FLOAT64) != 0;
+    const size_t ssz = f64_in ? 8 : 2;
     const double fs_in = (double)sample_rate;
     const bool front = sample_rate != 16000;          // mshds_extractor.py:418-419  snd.resample(16000, 50)
     const double fs = 16000.0;
@@ -1085,7 +1089,7 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
         int rc = process_chunk(h, SPtr{nullptr, nullptr}, off, fs, x1v, xmaxv, nullptr, nullptr, true);
         h->arena = saved; h->arena_cap = saved_cap;
         if (rc) return rc;
-        size_t need = h->arena_off + (pcm_dev ? 0 : (size_t)tot * 2 + 512) + (out_dev ? 0 : (size_t)n * (25 * 8 + 4) + 512) + 4096;
+        size_t need = h->arena_off + (pcm_dev ? 0 : (size_t)tot * ssz + 512) + (out_dev ? 0 : (size_t)n * (25 * 8 + 4) + 512) + 4096;
         if (need > h->arena_cap) {
             CK(cudaStreamSynchronize(s));
             if (h->arena) CK(cudaFree(h->arena));
@@ -1096,12 +1100,13 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
         }
         // tail of the arena: staging for pcm / outputs when the caller's buffers live on the host
         size_t tail = h->arena_cap;
-        const int16_t* d_pcm;
-        if (pcm_dev) d_pcm = pcm + offsets[c0];
+        const char* d_pcm;
+        const char* pcm_bytes = (const char*)pcm + (size_t)offsets[c0] * ssz;
+        if (pcm_dev) d_pcm = pcm_bytes;
         else {
-            tail = (tail - (size_t)tot * 2 - 256) & ~(size_t)255;
-            CK(cudaMemcpyAsync(h->arena + tail, pcm + offsets[c0], (size_t)tot * 2, cudaMemcpyHostToDevice, s));
-            d_pcm = (const int16_t*)(h->arena + tail);
+            tail = (tail - (size_t)tot * ssz - 256) & ~(size_t)255;
+            CK(cudaMemcpyAsync(h->arena + tail, pcm_bytes, (size_t)tot * ssz, cudaMemcpyHostToDevice, s));
+            d_pcm = h->arena + tail;
         }
         double* d_feat;
         uint32_t* d_status;
@@ -1118,7 +1123,7 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             d_status = (uint32_t*)(h->arena + tail);
         }
 
-        SPtr src{d_pcm, nullptr};
+        SPtr src{f64_in ? nullptr : (const int16_t*)d_pcm, f64_in ? (const double*)d_pcm : nullptr};
         const double* d_front_out = nullptr;
         if (front) {
             // ---- front-end: every clip -> 16 kHz float64 (FFT low-pass when down-sampling, sinc depth 50), own scratch

@@ -56,6 +56,38 @@ def read_wav_mono_int16(path: str):
     return np.clip(x, -32768, 32767).astype(np.int16), int(fs)
 
 
+def read_wav_mono(path: str):
+    """Decode a PCM WAV into (mono samples, sample_rate) the way parselmouth.Sound(path) + convert_to_mono hold it (:415-417).
+
+    Mono 16-bit audio stays int16 (value / 32768 is formed on the device, exactly); everything else -- 8/24/32-bit samples,
+    several channels (Praat averages the channels in floating point, which int16 cannot hold) -- is returned as float64 in
+    [-1, 1) and goes through the library's float64 entry (MSHDS_PCM_FLOAT64).
+    """
+    try:
+        with wave.open(path, "rb") as w:
+            nch, sw, fs, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
+            raw = w.readframes(n)
+    except Exception as e:
+        raise AudioLoadError(str(e)) from e
+    if sw == 2:
+        x = np.frombuffer(raw, dtype="<i2")
+        if nch == 1:
+            return x.copy(), int(fs)
+        x = x.astype(np.float64) / 32768.0
+    elif sw == 1:
+        x = (np.frombuffer(raw, dtype=np.uint8).astype(np.float64) - 128.0) / 128.0
+    elif sw == 3:
+        b = np.frombuffer(raw, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        x = (((b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)) << 8) >> 8).astype(np.float64) / 8388608.0
+    elif sw == 4:
+        x = np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0
+    else:
+        raise AudioLoadError(f"unsupported sample width {sw}")
+    if nch > 1:
+        x = x.reshape(-1, nch).mean(axis=1)
+    return np.ascontiguousarray(x, dtype=np.float64), int(fs)
+
+
 _EXTRACTORS = {}
 
 
@@ -94,9 +126,12 @@ def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True,
         if not batch_idx:
             return
         offs = np.cumsum([0] + [len(p) for p in batch_pcm]).astype(np.int64)
-        pcm = np.concatenate(batch_pcm) if batch_pcm else np.zeros(0, np.int16)
+        pcm = np.concatenate(batch_pcm)
         try:
-            out, _status = ex.extract_host(pcm, offs, fs)
+            if pcm.dtype == np.int16:
+                out, _status = ex.extract_host(pcm, offs, fs[0])
+            else:
+                out, _status = ex.extract_host_f64(pcm, offs, fs[0])
             feats[np.asarray(batch_idx)] = out
         except Exception as e:  # mirrors the whole-file handler at :450-457
             if verbose:
@@ -112,7 +147,8 @@ def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True,
             pass
     for i in iterator:
         try:
-            pcm, fs = read_wav_mono_int16(paths[i])
+            pcm, rate = read_wav_mono(paths[i])
+            fs = (rate, pcm.dtype == np.int16)            # one open batch per (rate, sample type)
             if len(pcm) == 0:
                 raise AudioLoadError("empty sound")
         except Exception as e:
@@ -123,7 +159,7 @@ def extract_mshds_features(input_df, audio_file_column='filepath', verbose=True,
         b[0].append(i)
         b[1].append(pcm)
         batches[fs] = (b[0], b[1], b[2] + len(pcm))
-        if batches[fs][2] >= max_batch_seconds * fs:
+        if batches[fs][2] >= max_batch_seconds * rate:
             flush(fs)
     for fs in list(batches):
         flush(fs)

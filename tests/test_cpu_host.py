@@ -89,6 +89,22 @@ def test_wav_reader(tmp_path):
     assert np.all(y == 0)
     with pytest.raises(AudioLoadError):
         read_wav_mono_int16(str(tmp_path / "missing.wav"))
+    # the reader of the drop-in: mono 16-bit stays int16, anything else becomes float64 exactly as Praat holds it
+    import wave
+    from robust_speech_analysis_framework_b200.mshds_extractor import read_wav_mono
+    _write_wav(p, x)
+    y, _ = read_wav_mono(p)
+    assert y.dtype == np.int16 and np.array_equal(x, y)
+    st2 = np.stack([x, x + 1], axis=1).ravel()                 # channel mean = x + 0.5: not an int16 value
+    _write_wav(p, st2, nch=2)
+    y, _ = read_wav_mono(p)
+    assert y.dtype == np.float64 and np.array_equal(y, (x.astype(np.float64) + 0.5) / 32768.0)
+    v24 = np.array([-8388608, -1, 0, 1, 8388607, 123456], dtype=np.int64)
+    with wave.open(p, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(3); w.setframerate(22050)
+        w.writeframes(b"".join(int(v & 0xffffff).to_bytes(3, "little") for v in v24))
+    y, fs = read_wav_mono(p)
+    assert fs == 22050 and y.dtype == np.float64 and np.array_equal(y, v24 / 8388608.0)
 
 
 class _FakeExtractor:
@@ -106,6 +122,11 @@ class _FakeExtractor:
             seg = pcm[offsets[i]:offsets[i + 1]].astype(np.float64)
             out[i] = seg.sum() + np.arange(25)
         return out, np.zeros(n, np.uint32)
+
+    def extract_host_f64(self, samples, offsets, sample_rate=16000):
+        out, st = self.extract_host(np.asarray(samples) * 32768.0, offsets, sample_rate)
+        self.calls[-1] = (self.calls[-1][0], self.calls[-1][1], "f64")
+        return out, st
 
 
 def test_dataframe_contract_matches_reference(tmp_path, monkeypatch, capsys):

@@ -442,3 +442,29 @@ def test_frame_level_contours_match_the_oracle_objects(ex, orc):
     from robust_speech_analysis_framework_b200 import _lib
     with pytest.raises(KeyError):
         ex.extract_contours(pcm, off, "nope")
+
+
+def test_float64_sample_entry(ex, orc, tmp_path):
+    """MSHDS_PCM_FLOAT64: float64 samples (24/32-bit, multi-channel files) through the same kernels.  Samples that are exact
+    int16 / 32768 values must give the int16 path's rows bit for bit; a 24-bit-resolution signal is compared with the oracle."""
+    import pandas as pd
+    from src.mshds_extractor import extract_mshds_features
+    pcm, off, clips = _batch([2.5, 3.1], start=95)
+    a, sa = ex.extract_host(pcm, off)
+    b, sb = ex.extract_host_f64(pcm.astype(np.float64) / 32768.0, off)
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb)
+    rng = np.random.default_rng(8)
+    x = np.round((clips[0].astype(np.float64) / 32768.0 + rng.uniform(-0.5, 0.5, len(clips[0])) / 32768.0) * 8388608.0) / 8388608.0
+    got, _ = ex.extract_host_f64(x, np.array([0, len(x)], np.int64))
+    want, _ = orc.extract_f64(x, 16000.0)
+    assert_features_close(got, want[None, :] if want.ndim == 1 else want, "24-bit resolution samples")
+    # a stereo 16-bit file: Praat's channel mean has half-integer values; the DataFrame API routes it through the float64 entry
+    st2 = np.stack([clips[1], np.clip(clips[1].astype(np.int32) + 1, -32768, 32767).astype(np.int16)], axis=1).ravel()
+    path = str(tmp_path / "stereo.wav")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(16000)
+        w.writeframes(st2.astype("<i2").tobytes())
+    df = extract_mshds_features(pd.DataFrame({"filepath": [path]}), verbose=False)
+    mono = st2.reshape(-1, 2).astype(np.float64).mean(axis=1) / 32768.0
+    wantm, _ = orc.extract_f64(mono, 16000.0)
+    assert_features_close(df.iloc[:, 1:].to_numpy(dtype=np.float64), wantm[None, :] if wantm.ndim == 1 else wantm, "stereo file")
