@@ -81,8 +81,9 @@ const char* mshds_last_error(const mshds_handle* h);
  * float or multi-channel files after convert_to_mono, :415-417); offsets still count samples.
  * sample_rate is the rate of every clip of the call.  Anything but 16000 is first resampled to 16 kHz on the device exactly
  * as the reference does (:418-419 snd.resample(16000, 50): FFT brick-wall low-pass when down-sampling, sinc depth 50), and the
- * analyses then read the float64 result.  8000 Hz is refused with MSHDS_ERR_UNSUPPORTED (Praat switches to Sound_upsample
- * for an exact doubling).  Returns MSHDS_OK or an error code; per-clip analysis failures are NOT errors.
+ * analyses then read the float64 result.  8000 Hz takes Praat's special case for an exact doubling (Sound_upsample: spectrum
+ * tapered above 95 % of Nyquist, inverse transform of twice the length).  Returns MSHDS_OK or an error code; per-clip analysis
+ * failures are NOT errors.
  */
 int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
                   double* features, uint32_t* status, unsigned flags);

@@ -146,6 +146,7 @@ int ltas_fitTiltLine_robust(const double *ltas0, long nx, double dx, double fmin
                             double *intercept);
 
 /* ---- Sound manipulation ---- */
+Sound *sound_upsample(const Sound *me);
 Sound *sound_resample(const Sound *me, double samplingFrequency, long precision);
 Sound *sound_extractPart(const Sound *me, double t1, double t2);  /* rectangular, preserveTimes=false */
 void sound_preEmphasis(Sound *me, double preEmphasisFrequency);

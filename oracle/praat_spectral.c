@@ -175,8 +175,41 @@ int ltas_fitTiltLine_robust(const double *z0, long nx, double dx, double fmin, d
 
 /* fon/Sound.cpp Sound_resample (mshds_extractor.py:419 prec 50; inside To Formant (burg) prec 500; inside
  * To PowerCepstrogram prec 50). */
+/* fon/Sound.cpp Sound_upsample: exact doubling of the sampling frequency.  nfft = power of two >= nx + 2000, the sound sits
+ * at data[1001 .. 1000 + nx] of a zeroed buffer of 2 nfft reals; NUMrealft forward over the first nfft; the packed values
+ * data[i], i > imin = (long)(0.95 nfft), are tapered by (nfft - i) / (nfft - imin) (real and imaginary part of a bin carry
+ * consecutive i), data[2] (Nyquist) = 0; NUMrealft inverse over all 2 nfft; new sample i = data[i + 2000] / nfft.
+ * New time domain: nx' = 2 nx, dx' = dx / 2, x1' = x1 - dx / 4. */
+Sound *sound_upsample(const Sound *me) {
+    long nfft = 1;
+    while (nfft < me->nx + 2000) nfft *= 2;
+    Sound *thee = sound_create(me->xmin, me->xmax, me->nx * 2, me->dx / 2.0, me->x1 - me->dx / 4.0);
+    double *re = (double *)calloc((size_t)2 * nfft, sizeof(double));
+    double *im = (double *)calloc((size_t)2 * nfft, sizeof(double));
+    for (long i = 1; i <= me->nx; i++) re[1000 + i - 1] = Z(me, i);
+    fft_pow2(re, im, nfft, -1);
+    /* packed layout of the half spectrum: data[1] = DC, data[2] = Nyquist, data[2k+1] = Re X_k, data[2k+2] = Im X_k */
+    long imin = (long)(nfft * 0.95);
+    double *sre = (double *)calloc((size_t)2 * nfft, sizeof(double));
+    double *sim = (double *)calloc((size_t)2 * nfft, sizeof(double));
+    sre[0] = re[0];                                            /* data[1]: never tapered (imin >= 1) */
+    for (long k = 1; k < nfft / 2; k++) {
+        long ir = 2 * k + 1, ii = 2 * k + 2;
+        double fr = ir > imin ? (double)(nfft - ir) / (double)(nfft - imin) : 1.0;
+        double fi = ii > imin ? (double)(nfft - ii) / (double)(nfft - imin) : 1.0;
+        sre[k] = re[k] * fr; sim[k] = im[k] * fi;
+        sre[2 * nfft - k] = sre[k]; sim[2 * nfft - k] = -sim[k];      /* Hermitian completion of the 2 nfft spectrum */
+    }
+    fft_pow2(sre, sim, 2 * nfft, +1);
+    double factor = 1.0 / nfft;
+    for (long i = 1; i <= thee->nx; i++) Z(thee, i) = sre[i + 2000 - 1] * factor;
+    free(re); free(im); free(sre); free(sim);
+    return thee;
+}
+
 Sound *sound_resample(const Sound *me, double samplingFrequency, long precision) {
     double upfactor = samplingFrequency * me->dx;
+    if (fabs(upfactor - 2) < 1e-6) return sound_upsample(me);
     if (fabs(upfactor - 1) < 1e-6) return sound_copy(me);
     long numberOfSamples = iround((me->xmax - me->xmin) * samplingFrequency);
     if (numberOfSamples < 1) return NULL;

@@ -198,7 +198,7 @@ struct ResampleJob {
     int table_id, pad;         // row block of the sinc coefficient table
 };
 void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, SPtr pcm, double2* zbuf,
-                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches);
+                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches, int mode = 0);
 #define SINC_FIR_R 7        // outputs per thread of the polyphase FIR kernel (k_resample.cu FIR_R)
 void launch_resample_copy(const ResampleJob* d_jobs, int njobs, long long max_nx, SPtr pcm, double* filt, cudaStream_t s, long long* launches);
 void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_prefix, int njobs, long long total_out_hint,

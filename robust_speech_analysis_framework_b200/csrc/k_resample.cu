@@ -31,7 +31,7 @@ template <bool INVERSE, bool FIRST_FROM_SRC, bool LAST_TO_REAL>
 __global__ void __launch_bounds__(RS_NTHR) k_fft_strided(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
                                                           SPtr pcm, double2* __restrict__ zbuf,
                                                           double* __restrict__ filt, const double2* __restrict__ tw,
-                                                          int logn, int nl, int rb) {
+                                                          int logn, int nl, int rb, int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)smem;
     const int R = 1 << rb;
@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_strided(const ResampleJob* __re
         } else if (LAST_TO_REAL) {
             long long gp = blk * Nl + pos;
             long long i = gp - ANTI_TURN;                    // to[i] = data[i + antiTurnAround] / nfft, i = 1..nx (0-based i here)
-            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = v.x * (1.0 / (double)N);
+            if (i >= 0 && i < J.nx) {
+                if (mode == 0) filt[J.filt_off + i] = v.x * (1.0 / (double)N);
+                else filt[J.out_off + 2 * i + (mode - 1)] = v.x * (1.0 / (double)N);      // `filt` is the output sound here
+            }
         } else {
             z[pos] = v;
         }
@@ -85,8 +88,28 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_strided(const ResampleJob* __re
 
 // Praat: "for (i = floor(upfactor*nfft); i <= nfft; i++) data[i] = 0;  data[2] = 0;" on the NUMrealft-packed spectrum
 // (data[1] = DC, data[2] = Nyquist, data[2k+1] = Re X_k, data[2k+2] = Im X_k).  Returns the masked bin.
-__device__ __forceinline__ double2 apply_lowpass_mask(double2 v, long long k, long long N, long long i0) {
+// mode 1 / 2 = Sound_upsample (exact doubling): packed values data[i], i > imin = (long)(0.95 N), are tapered by
+// (N - i) / (N - imin), data[2] (Nyquist) = 0, and the inverse transform has twice the length.  Its even output samples are
+// the length-N inverse of the tapered spectrum (mode 1), the odd ones the inverse of the spectrum advanced by half a sample
+// (mode 2: bin k times exp(+i pi k / N), k counted as a signed frequency).
+__device__ __forceinline__ double2 apply_lowpass_mask(double2 v, long long k, long long N, long long i0, int mode) {
     long long kk = k <= N / 2 ? k : N - k;
+    if (mode != 0) {
+        if (kk == 0) return v;
+        if (kk == N / 2) return make_double2(0.0, 0.0);
+        const bool neg = k > N / 2;
+        double2 X = neg ? make_double2(v.x, -v.y) : v;                 // the bin of the positive frequency kk
+        const long long imin = (long long)((double)N * 0.95);
+        const long long ir = 2 * kk + 1, ii = 2 * kk + 2;
+        if (ir > imin) X.x *= (double)(N - ir) / (double)(N - imin);
+        if (ii > imin) X.y *= (double)(N - ii) / (double)(N - imin);
+        if (mode == 2) {
+            double sn, cs;
+            sincospi((double)kk / (double)N, &sn, &cs);
+            X = cmul(X, make_double2(cs, sn));
+        }
+        return neg ? make_double2(X.x, -X.y) : X;
+    }
     if (kk == 0) { if (i0 <= 1) v.x = 0.0; v.y = v.y; return v; }
     if (kk == N / 2) return make_double2(0.0, 0.0);
     if (2 * kk + 1 >= i0) v.x = 0.0;
@@ -99,7 +122,7 @@ template <bool WHOLE>     // WHOLE: logn == cb (load from the source, write filt
 __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __restrict__ jobs, const int* __restrict__ ids,
                                                         SPtr pcm, double2* __restrict__ zbuf,
                                                         double* __restrict__ filt, const double2* __restrict__ tw, int logn,
-                                                        int cb, double upfactor) {
+                                                        int cb, double upfactor, int mode) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)smem;
     const int Cn = 1 << cb;
@@ -115,14 +138,17 @@ __global__ void __launch_bounds__(RS_NTHR) k_fft_inner(const ResampleJob* __rest
     for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
         long long pos = chunk * Cn + e;
         long long k = (long long)(__brevll((unsigned long long)pos) >> (64 - logn));
-        a[SWZ(e)] = apply_lowpass_mask(a[SWZ(e)], k, N, i0);
+        a[SWZ(e)] = apply_lowpass_mask(a[SWZ(e)], k, N, i0, mode);
     }
     __syncthreads();
     fft_dit<+1>(a, Cn, tw);
     for (int e = threadIdx.x; e < Cn; e += RS_NTHR) {
         if (WHOLE) {
             long long i = (long long)e - ANTI_TURN;
-            if (i >= 0 && i < J.nx) filt[J.filt_off + i] = a[SWZ(e)].x * (1.0 / (double)N);
+            if (i >= 0 && i < J.nx) {
+                if (mode == 0) filt[J.filt_off + i] = a[SWZ(e)].x * (1.0 / (double)N);
+                else filt[J.out_off + 2 * i + (mode - 1)] = a[SWZ(e)].x * (1.0 / (double)N);
+            }
         } else z[e] = a[SWZ(e)];
     }
 }
@@ -421,14 +447,14 @@ static void plan_passes(int logn, int* cb, int* npass, int rbits[4]) {
 
 // jobs of one FFT size: d_ids lists the job indices, cnt of them
 void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int cnt, int logn, SPtr pcm, double2* zbuf,
-                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches) {
+                               double* filt, const double2* tw, double upfactor, cudaStream_t s, long long* launches, int mode) {
     int cb, npass, rbits[4];
     plan_passes(logn, &cb, &npass, rbits);
     const long long N = 1LL << logn;
     if (npass == 0) {
         size_t smem = sizeof(double2) * (1u << cb);
         cudaFuncSetAttribute(k_fft_inner<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_fft_inner<true><<<cnt, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor);
+        k_fft_inner<true><<<cnt, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor, mode);
         (*launches)++;
         return;
     }
@@ -441,10 +467,10 @@ void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int 
         unsigned grid = (unsigned)(tiles * cnt);
         if (i == 0) {
             cudaFuncSetAttribute(k_fft_strided<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_fft_strided<false, true, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+            k_fft_strided<false, true, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb, mode);
         } else {
             cudaFuncSetAttribute(k_fft_strided<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_fft_strided<false, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+            k_fft_strided<false, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb, mode);
         }
         (*launches)++;
         nl -= rb;
@@ -453,7 +479,7 @@ void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int 
         size_t smem = sizeof(double2) * (1u << cb);
         unsigned grid = (unsigned)((N >> cb) * cnt);
         cudaFuncSetAttribute(k_fft_inner<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_fft_inner<false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor);
+        k_fft_inner<false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, cb, upfactor, mode);
         (*launches)++;
     }
     // inverse strided passes (innermost first)
@@ -465,10 +491,10 @@ void launch_resample_fft_group(const ResampleJob* d_jobs, const int* d_ids, int 
         unsigned grid = (unsigned)(tiles * cnt);
         if (i == 0) {
             cudaFuncSetAttribute(k_fft_strided<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_fft_strided<true, false, true><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+            k_fft_strided<true, false, true><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb, mode);
         } else {
             cudaFuncSetAttribute(k_fft_strided<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_fft_strided<true, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb);
+            k_fft_strided<true, false, false><<<grid, RS_NTHR, smem, s>>>(d_jobs, d_ids, pcm, zbuf, filt, tw, logn, nl, rb, mode);
         }
         (*launches)++;
     }

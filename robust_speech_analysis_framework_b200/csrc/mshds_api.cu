@@ -1029,11 +1029,6 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     h->err.clear();
     if (n_clips < 0 || (n_clips > 0 && (!pcm || !offsets || !features))) { h->err = "null pointer argument"; return MSHDS_ERR_ARG; }
     if (sample_rate < 4000 || sample_rate > 384000) { h->err = "sample_rate out of range"; return MSHDS_ERR_ARG; }
-    if (sample_rate == 8000) {
-        // Sound_resample switches to Sound_upsample (a different algorithm) when the rate exactly doubles
-        h->err = "8 kHz input (exact 2x up-sampling goes through Praat's Sound_upsample) is not supported yet";
-        return MSHDS_ERR_UNSUPPORTED;
-    }
     if (n_clips == 0) return MSHDS_OK;
     for (int i = 0; i < n_clips; i++)
         if (offsets[i + 1] < offsets[i]) { h->err = "offsets must be non-decreasing"; return MSHDS_ERR_ARG; }
@@ -1047,6 +1042,7 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     const size_t ssz = f64_in ? 8 : 2;
     const double fs_in = (double)sample_rate;
     const bool front = sample_rate != 16000;          // mshds_extractor.py:418-419  snd.resample(16000, 50)
+    const bool doubling = sample_rate == 8000;        // Sound_resample hands an exact doubling to Sound_upsample
     const double fs = 16000.0;
 
     int c0 = 0;
@@ -1075,6 +1071,10 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             for (int i = 0; i < n; i++) {
                 const long long len = off_in[i + 1] - off_in[i];
                 fill_resample_job(&fe.jobs[i], off_in[i], len, 1, len, 0.5 * dx_in, (double)len * dx_in, fs);
+                if (doubling) {     // Sound_upsample: nx' = 2 nx, dx' = dx / 2, x1' = x1 - dx / 4
+                    fe.jobs[i].nout = 2 * len;
+                    fe.jobs[i].out_x1 = 0.5 * dx_in - dx_in / 4.0;
+                }
                 if (len <= 0 || fe.jobs[i].nout < 1) fe.jobs[i].nout = 0;    // empty clip (or too short to give one sample): whole row NaN
                 x1v[i] = fe.jobs[i].out_x1; xmaxv[i] = (double)len * dx_in;
             }
@@ -1148,7 +1148,15 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
             D.filt = (double*)(B + o_filt); D.out = (double*)(B + o_out); D.table = (double*)(B + o_tab);
             if ((rc = upload_plan(h, fe, D, s))) return rc;
             PB("frontend_resample_to_16k[fft+sinc50]");
-            run_resample(h, fe, D, src, fs_in, fs, 50, s);
+            if (doubling) {
+                // even output samples = inverse of the tapered spectrum, odd ones = inverse of the half-sample-advanced spectrum
+                int pos = 0;
+                for (auto& g : fe.groups) {
+                    launch_resample_fft_group(D.jobs, D.ids + pos, g.second, g.first, src, D.zbuf, D.out, h->tw, 2.0, s, &h->launches, 1);
+                    launch_resample_fft_group(D.jobs, D.ids + pos, g.second, g.first, src, D.zbuf, D.out, h->tw, 2.0, s, &h->launches, 2);
+                    pos += g.second;
+                }
+            } else run_resample(h, fe, D, src, fs_in, fs, 50, s);
             PE();
             src = SPtr{nullptr, D.out};
             d_front_out = D.out;

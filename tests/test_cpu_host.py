@@ -116,7 +116,7 @@ class _FakeExtractor:
         n = len(offsets) - 1
         self.calls.append((int(sample_rate), n))
         if sample_rate == 8000:
-            raise RuntimeError("8 kHz input is not supported yet")      # what the library answers (MSHDS_ERR_UNSUPPORTED)
+            raise RuntimeError("simulated device failure")             # a failing device call must give NaN rows + messages
         out = np.zeros((n, 25))
         for i in range(n):
             seg = pcm[offsets[i]:offsets[i + 1]].astype(np.float64)

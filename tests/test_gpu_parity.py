@@ -163,8 +163,6 @@ def test_bad_arguments_are_errors_not_crashes(ex):
     from robust_speech_analysis_framework_b200 import _lib
     pcm = np.zeros(1000, np.int16)
     with pytest.raises(_lib.MshdsError):
-        ex.extract_host(pcm, np.array([0, 1000], np.int64), sample_rate=8000)      # Sound_upsample case: refused, not guessed
-    with pytest.raises(_lib.MshdsError):
         ex.extract_host(pcm, np.array([0, 1000], np.int64), sample_rate=100)
     with pytest.raises(_lib.MshdsError):
         ex.extract_host(pcm, np.array([500, 100], np.int64))
@@ -214,11 +212,12 @@ def test_drop_in_dataframe_api_feeds_the_svm_consumer(tmp_path, orc):
     assert scores.shape == (3,) and np.all(np.isfinite(scores))
 
 
-@pytest.mark.parametrize("fs", [44100, 48000, 22050, 32000, 11025])
+@pytest.mark.parametrize("fs", [44100, 48000, 22050, 32000, 11025, 8000])
 def test_front_end_resamples_to_16k_like_the_reference(ex, orc, fs):
     """mshds_extractor.py:418-419: recordings at another rate go through snd.resample(16000, 50) first.  44.1 kHz and
     22.05 kHz have long polyphase periods (160 / 320 phases), 48 and 32 kHz short ones (FIR kernel), 11.025 kHz up-samples
-    (no low-pass).  Lengths include odd ones so that the new time origin is not half a sample."""
+    (no low-pass), 8 kHz is the exact doubling Praat hands to Sound_upsample.  Lengths include odd ones so that the new time
+    origin is not half a sample."""
     from robust_speech_analysis_framework_b200.synth import synth_clip
     durs = [3.0, 2.2 + 1.0 / fs, 4.1 + 3.0 / fs]
     clips = [synth_clip(300 + i, d, fs=fs).numpy() for i, d in enumerate(durs)]

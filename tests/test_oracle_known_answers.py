@@ -235,3 +235,20 @@ def test_formants_of_two_resonator_signal(orc):
     f2 = np.nanmax(np.where(sharp < 2500.0, sharp, np.nan), axis=1)
     assert abs(np.nanmedian(f1) - 600.0) < 40.0
     assert abs(np.nanmedian(f2) - 1700.0) < 60.0
+
+
+def test_exact_doubling_takes_the_upsample_route(orc):
+    """Sound_resample hands upfactor == 2 to Sound_upsample: twice the samples, dx / 2, x1 - dx / 4; the even samples are the
+    original ones (away from the ends) and the odd ones the band-limited values half a sample later."""
+    fs = 8000.0
+    t = np.arange(4001) / fs
+    x = 0.3 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t + 0.7)
+    y, x1 = orc.resample(x, fs, 16000.0, 50)
+    assert len(y) == 2 * len(x) and abs(x1 - (0.5 / fs - 0.25 / fs)) < 1e-15
+    tm = np.arange(len(y)) / 16000.0
+    ref = 0.3 * np.sin(2 * np.pi * 440 * tm) + 0.2 * np.sin(2 * np.pi * 3100 * tm + 0.7)
+    assert np.max(np.abs(y - ref)[600:-600]) < 1e-4
+    # a component above 95 % of the old Nyquist frequency is attenuated by the taper
+    z = np.sin(2 * np.pi * 3950 * t)
+    yz, _ = orc.resample(z, fs, 16000.0, 50)
+    assert 0.1 < np.sqrt(2 * np.mean(yz[2000:-2000] ** 2)) < 0.6
