@@ -127,7 +127,8 @@ int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* o
  * OpenSMILE run of src/opensmile_extractor.py:9-103 with Androids.conf (the SMILExtract binary itself is
  * not available, so the component chain is restated here and in oracle/lld_oracle.py -- parity unpinned).  Covered:
  * cFramer -> cVectorPreemphasis -> cWindower -> cTransformFFT -> cFFTmagphase -> cMelspec -> cMfcc (Androids.conf:73-115),
- * cEnergy rms (:117-123), cMZcr zcr (:125-132), and the mean / standard deviation functionals over a recording.
+ * cEnergy rms (:117-123), cMZcr zcr (:125-132), cContourSmoother and cDeltaRegression on those contours, and the mean /
+ * standard deviation functionals over a recording.
  *
  * Definitions (fs = sample_rate, x = pcm / 32768):
  *   frames      nf = round(frame_size * fs) samples every ns = round(frame_step * fs); only complete frames:
@@ -141,8 +142,11 @@ int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* o
  *               band m = triangle over points m-1, m, m+1 evaluated at mel(k fs / n_fft); E_m = sum_k H_m(k) |X[k]|
  *   mfcc        c_i = sqrt(2 / n_mel) sum_m ln(max(E_m, 1e-10)) cos(pi i (m - 1/2) / n_mel), i = 1 .. n_mfcc,
  *               times 1 + (L / 2) sin(pi i / L) for cep_lifter L > 0
- * Row layout of a frame: mfcc[1..n_mfcc], energy, zcr (D = n_mfcc + 2 values).  functionals: n_clips x 2D (D means, then D
- * population standard deviations; NaN for a clip without a complete frame).  frames_out (optional, may be NULL): all frame
+ *   smoothing   y_t = mean(x_{t-h} .. x_{t+h}), h = smooth_win / 2, frames beyond the ends of the recording repeat the end frame
+ *   delta       d_t = sum_{i=1..delta_win} i (y_{t+i} - y_{t-i}) / (2 sum i^2), same end rule
+ * Row layout of a frame: the D = n_mfcc + 2 (smoothed) descriptors mfcc[1..n_mfcc], energy, zcr, then -- if delta_win > 0 --
+ * their D deltas: W = D or 2D values.  functionals: n_clips x 2W (W means, then W population standard deviations; NaN for a
+ * clip without a complete frame).  frames_out (optional, may be NULL): all frame
  * rows, clips back to back; frame_offsets (optional HOST array, n_clips + 1) receives the first row of every clip.
  * flags: MSHDS_PCM_ON_DEVICE / MSHDS_OUT_ON_DEVICE as for mshds_extract (the latter covers functionals and frames_out).
  */
@@ -155,6 +159,8 @@ typedef struct mshds_lld_params {
     double mel_lo, mel_hi;  /* Hz    20, 8000  Androids.conf:106-107 */
     int n_mfcc;             /*       12      Androids.conf:112-113 (coefficients 1..12) */
     double cep_lifter;      /*       22      cMfcc default */
+    int smooth_win;         /* frames 3      cContourSmoother default smaWin (Androids.conf lld/lld2/lld3); <= 1: no smoothing */
+    int delta_win;          /* frames 2      cDeltaRegression deltawin (Androids.conf delta1..3); 0: no delta columns */
 } mshds_lld_params;
 void mshds_lld_default_params(mshds_lld_params* p);
 int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,

@@ -10,16 +10,45 @@ reading of the components.
 import numpy as np
 
 DEFAULTS = dict(frame_size=0.025, frame_step=0.010, preemph=0.97, n_fft=0, n_mel=26, mel_lo=20.0, mel_hi=8000.0, n_mfcc=12,
-                cep_lifter=22.0)
+                cep_lifter=22.0, smooth_win=3, delta_win=2)
 
 
 def _mel(f):
     return 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
 
 
+def smooth_delta(rows: np.ndarray, smooth_win: int, delta_win: int) -> np.ndarray:
+    """cContourSmoother (moving average, end frames repeated) then cDeltaRegression on the smoothed contours."""
+    T = len(rows)
+    if T == 0 or (smooth_win <= 1 and delta_win <= 0):
+        return rows if delta_win <= 0 else np.zeros((0, 2 * rows.shape[1]))
+    clip = lambda k: np.clip(k, 0, T - 1)
+    t = np.arange(T)
+    h = smooth_win // 2 if smooth_win > 1 else 0
+
+    def sma(k):
+        k = clip(k)
+        acc = np.zeros((len(k), rows.shape[1]))
+        for u in range(-h, h + 1):
+            acc = acc + rows[clip(k + u)]
+        return acc / (2 * h + 1)
+    y = sma(t)
+    if delta_win <= 0:
+        return y
+    acc = np.zeros_like(y)
+    for i in range(1, delta_win + 1):
+        acc = acc + i * (sma(t + i) - sma(t - i))
+    d = acc / sum(2.0 * i * i for i in range(1, delta_win + 1))
+    return np.concatenate([y, d], axis=1)
+
+
 def frame_lld(x: np.ndarray, fs: float, **kw):
-    """x float64 samples of ONE clip -> [n_frames, n_mfcc + 2] rows (mfcc 1..n, rms energy, zcr)."""
+    """x float64 samples of ONE clip -> [n_frames, W] rows: (smoothed) mfcc 1..n, rms energy, zcr, then their deltas."""
     p = dict(DEFAULTS); p.update(kw)
+    return smooth_delta(_raw_lld(x, fs, p), p["smooth_win"], p["delta_win"])
+
+
+def _raw_lld(x: np.ndarray, fs: float, p: dict):
     nf = int(np.floor(p["frame_size"] * fs + 0.5)); ns = int(np.floor(p["frame_step"] * fs + 0.5))
     n_fft = p["n_fft"]
     if n_fft == 0:
@@ -67,7 +96,7 @@ def extract(pcm: np.ndarray, offsets: np.ndarray, fs: float, **kw):
     """packed int16 batch -> (functionals [n, 2D], list of per-clip frame matrices)."""
     n = len(offsets) - 1
     rows = []
-    D = (kw.get("n_mfcc", DEFAULTS["n_mfcc"])) + 2
+    D = ((kw.get("n_mfcc", DEFAULTS["n_mfcc"])) + 2) * (2 if kw.get("delta_win", DEFAULTS["delta_win"]) > 0 else 1)
     fun = np.full((n, 2 * D), np.nan)
     for i in range(n):
         x = pcm[offsets[i]:offsets[i + 1]].astype(np.float64) / 32768.0

@@ -44,7 +44,7 @@ class LldParams(C.Structure):
     """struct mshds_lld_params (include/mshds_b200.h)."""
     _fields_ = [("frame_size", C.c_double), ("frame_step", C.c_double), ("preemph", C.c_double), ("n_fft", C.c_int),
                 ("n_mel", C.c_int), ("mel_lo", C.c_double), ("mel_hi", C.c_double), ("n_mfcc", C.c_int),
-                ("cep_lifter", C.c_double)]
+                ("cep_lifter", C.c_double), ("smooth_win", C.c_int), ("delta_win", C.c_int)]
 
 
 def load(build_if_needed: bool = True) -> C.CDLL:
@@ -185,7 +185,7 @@ class Extractor:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         p = self.lld_params(**params)
-        D = p.n_mfcc + 2
+        D = (p.n_mfcc + 2) * (2 if p.delta_win > 0 else 1)           # width of a frame row
         fun = np.full((max(n, 0), 2 * D), np.nan)
         fo = np.zeros(n + 1, dtype=np.int64)
         frames = None

@@ -124,11 +124,15 @@ struct LldPass {
     const int* klo; const int* khi;   // [n_mel] first / last bin with a non-zero weight
     const double* dct;          // [n_mfcc * n_mel] cos(pi * i * (m + 0.5) / n_mel), i = 1..n_mfcc
     int* nF; int* fstart;       // [n], [n + 1]
-    double* frames;             // [total_frames * (n_mfcc + 2)]
+    double* frames;             // [total_frames * (n_mfcc + 2)] raw descriptors
+    int smooth_win, delta_win;  // contour smoothing window (frames, odd; <= 1 = none), delta regression half-window (0 = none)
+    int W;                      // width of a final row: (n_mfcc + 2) * (delta_win > 0 ? 2 : 1)
+    double* final;              // [total_frames * W]; == frames when neither smoothing nor deltas are requested
 };
 void launch_lld_grid(int n, const long long* off, int nf, int ns, int* nF, int* fstart, cudaStream_t s);
 void launch_lld_frames(const LldPass& p, const int16_t* pcm, const long long* off, int n, const double2* tw, long long frames_hint,
                        cudaStream_t s);
+void launch_lld_post(const LldPass& p, int n, long long frames_hint, cudaStream_t s);
 void launch_lld_functionals(const LldPass& p, int n, double* out, cudaStream_t s);
 void launch_session_agg(const double* feat, int n_cols, const int* row_start, const int* rows, int n_groups, double* mean_out,
                         double* std_out, cudaStream_t s);

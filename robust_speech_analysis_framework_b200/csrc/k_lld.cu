@@ -105,16 +105,16 @@ __global__ void __launch_bounds__(128) k_lld_frames(LldPass p, const int16_t* __
 __global__ void __launch_bounds__(256) k_lld_functionals(LldPass p, int n, double* __restrict__ out) {
     __shared__ double red[32];
     const int clip = blockIdx.x;
-    const int D = p.n_mfcc + 2;
+    const int D = p.W;
     const int f0 = p.fstart[clip], nF = p.fstart[clip + 1] - f0;
     for (int d = 0; d < D; d++) {
         double s = 0.0;
-        for (int i = threadIdx.x; i < nF; i += blockDim.x) s += p.frames[(size_t)(f0 + i) * D + d];
+        for (int i = threadIdx.x; i < nF; i += blockDim.x) s += p.final[(size_t)(f0 + i) * D + d];
         s = block_sum(s, red);
         const double mean = nF > 0 ? s / (double)nF : DEVNAN;
         double v = 0.0;
         for (int i = threadIdx.x; i < nF; i += blockDim.x) {
-            const double e = p.frames[(size_t)(f0 + i) * D + d] - mean;
+            const double e = p.final[(size_t)(f0 + i) * D + d] - mean;
             v = fma(e, e, v);
         }
         v = block_sum(v, red);
@@ -124,6 +124,43 @@ __global__ void __launch_bounds__(256) k_lld_functionals(LldPass p, int n, doubl
         }
         __syncthreads();
     }
+}
+
+// cContourSmoother (moving average over smooth_win frames, Androids.conf lld / lld2 / lld3) and cDeltaRegression (deltawin,
+// Androids.conf delta1..3) on the frame rows of a clip; frames beyond the ends of the clip repeat the first / last frame.
+// Output row: the D smoothed descriptors, then (delta_win > 0) their D regression deltas.
+__global__ void __launch_bounds__(256) k_lld_post(LldPass p, int n) {
+    const int D = p.n_mfcc + 2;
+    const long long total = (long long)p.fstart[n] * D;
+    const int hs = p.smooth_win > 1 ? p.smooth_win / 2 : 0;
+    double dnorm = 0.0;
+    for (int i = 1; i <= p.delta_win; i++) dnorm += 2.0 * i * i;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(t / D), d = (int)(t % D);
+        const int clip = find_segment(p.fstart, n, f);
+        const int f0 = p.fstart[clip], nF = p.fstart[clip + 1] - f0, k = f - f0;
+        auto raw = [&](int kk) { kk = kk < 0 ? 0 : (kk >= nF ? nF - 1 : kk); return p.frames[(size_t)(f0 + kk) * D + d]; };
+        auto sma = [&](int kk) {
+            kk = kk < 0 ? 0 : (kk >= nF ? nF - 1 : kk);
+            double a = 0.0;
+            for (int u = -hs; u <= hs; u++) a += raw(kk + u);
+            return a / (double)(2 * hs + 1);
+        };
+        double* row = p.final + (size_t)f * p.W;
+        row[d] = sma(k);
+        if (p.delta_win > 0) {
+            double a = 0.0;
+            for (int i = 1; i <= p.delta_win; i++) a += (double)i * (sma(k + i) - sma(k - i));
+            row[D + d] = a / dnorm;
+        }
+    }
+}
+
+void launch_lld_post(const LldPass& p, int n, long long frames_hint, cudaStream_t s) {
+    long long blocks = (frames_hint * (p.n_mfcc + 2) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_lld_post<<<(unsigned)blocks, 256, 0, s>>>(p, n);
 }
 
 void launch_lld_grid(int n, const long long* off, int nf, int ns, int* nF, int* fstart, cudaStream_t s) {

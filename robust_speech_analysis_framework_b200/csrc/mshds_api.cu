@@ -1206,7 +1206,7 @@ int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* o
 void mshds_lld_default_params(mshds_lld_params* p) {
     if (!p) return;
     p->frame_size = 0.025; p->frame_step = 0.010; p->preemph = 0.97; p->n_fft = 0; p->n_mel = 26;
-    p->mel_lo = 20.0; p->mel_hi = 8000.0; p->n_mfcc = 12; p->cep_lifter = 22.0;
+    p->mel_lo = 20.0; p->mel_hi = 8000.0; p->n_mfcc = 12; p->cep_lifter = 22.0; p->smooth_win = 3; p->delta_win = 2;
 }
 
 int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
@@ -1226,6 +1226,7 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     if (n_fft == 0) { n_fft = 64; while (n_fft < nf) n_fft <<= 1; }
     if (n_fft < nf || n_fft < 64 || n_fft > 8192 || (n_fft & (n_fft - 1))) { h->err = "n_fft must be a power of two in [max(64, frame length), 8192]"; return MSHDS_ERR_ARG; }
     if (P.n_mel < 2 || P.n_mel > 256 || P.n_mfcc < 1 || P.n_mfcc >= P.n_mel || !(P.preemph >= 0.0 && P.preemph < 1.0)) { h->err = "bad n_mel / n_mfcc / preemph"; return MSHDS_ERR_ARG; }
+    if (P.smooth_win < 0 || P.smooth_win > 101 || (P.smooth_win > 1 && P.smooth_win % 2 == 0) || P.delta_win < 0 || P.delta_win > 50) { h->err = "smooth_win must be odd (or <= 1), delta_win in [0, 50]"; return MSHDS_ERR_ARG; }
     const double hi = P.mel_hi < 0.5 * fs ? P.mel_hi : 0.5 * fs;
     if (!(P.mel_lo >= 0.0 && P.mel_lo < hi)) { h->err = "bad mel range"; return MSHDS_ERR_ARG; }
     if (n_clips == 0) return MSHDS_OK;
@@ -1233,7 +1234,9 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     cudaStream_t s = h->stream;
     h->cur = s;
     const bool pcm_dev = (flags & MSHDS_PCM_ON_DEVICE) != 0, out_dev = (flags & MSHDS_OUT_ON_DEVICE) != 0;
-    const int M = n_fft / 2, D = P.n_mfcc + 2;
+    const int M = n_fft / 2, D0 = P.n_mfcc + 2;
+    const bool post = P.smooth_win > 1 || P.delta_win > 0;
+    const int D = D0 * (P.delta_win > 0 ? 2 : 1);          // width of a final row
     int logM = 0; while ((1 << logM) < M) logM++;
     // ---- host tables
     std::vector<double> window(nf), melbin(M + 1), centres(P.n_mel + 2), dct((size_t)P.n_mfcc * P.n_mel);
@@ -1267,6 +1270,7 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     const size_t o_off = sz(sizeof(long long) * (n_clips + 1)), o_nF = sz(sizeof(int) * n_clips), o_fs = sz(sizeof(int) * (n_clips + 1));
     const size_t o_win = sz(sizeof(double) * nf), o_mb = sz(sizeof(double) * (M + 1)), o_c = sz(sizeof(double) * (P.n_mel + 2));
     const size_t o_klo = sz(sizeof(int) * P.n_mel), o_khi = sz(sizeof(int) * P.n_mel), o_dct = sz(sizeof(double) * dct.size());
+    const size_t o_raw = post ? sz(sizeof(double) * (size_t)(total_frames + 1) * D0) : 0;
     const size_t o_fr = (out_dev && frames_out) ? 0 : sz(sizeof(double) * (size_t)(total_frames + 1) * D);
     const size_t o_fun = out_dev ? 0 : sz(sizeof(double) * (size_t)n_clips * 2 * D);
     const size_t o_pcm = pcm_dev ? 0 : sz((size_t)total * 2 + 16);
@@ -1293,12 +1297,15 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     L.window = (const double*)(Bf + o_win); L.melbin = (const double*)(Bf + o_mb); L.centres = (const double*)(Bf + o_c);
     L.klo = (const int*)(Bf + o_klo); L.khi = (const int*)(Bf + o_khi); L.dct = (const double*)(Bf + o_dct);
     L.nF = (int*)(Bf + o_nF); L.fstart = (int*)(Bf + o_fs);
-    L.frames = (out_dev && frames_out) ? frames_out : (double*)(Bf + o_fr);
+    L.final = (out_dev && frames_out) ? frames_out : (double*)(Bf + o_fr);
+    L.frames = post ? (double*)(Bf + o_raw) : L.final;
+    L.smooth_win = P.smooth_win; L.delta_win = P.delta_win; L.W = D;
     double* d_fun = out_dev ? functionals : (double*)(Bf + o_fun);
     PB("lld_frames[mfcc+energy+zcr]");
     launch_lld_grid(n_clips, (const long long*)(Bf + o_off), nf, ns, L.nF, L.fstart, s);
     launch_lld_frames(L, d_pcm, (const long long*)(Bf + o_off), n_clips, h->tw, total_frames, s);
     PE();
+    if (post) { PB("lld_smooth_delta"); launch_lld_post(L, n_clips, total_frames, s); h->launches += 1; PE(); }
     PB("lld_functionals");
     launch_lld_functionals(L, n_clips, d_fun, s);
     PE();
@@ -1307,7 +1314,7 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     if (!out_dev) {
         CK(cudaMemcpyAsync(functionals, d_fun, sizeof(double) * (size_t)n_clips * 2 * D, cudaMemcpyDeviceToHost, s));
         if (frames_out && total_frames > 0)
-            CK(cudaMemcpyAsync(frames_out, L.frames, sizeof(double) * (size_t)total_frames * D, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(frames_out, L.final, sizeof(double) * (size_t)total_frames * D, cudaMemcpyDeviceToHost, s));
     }
     CK(cudaStreamSynchronize(s));
     prof_collect(h);

@@ -4,8 +4,9 @@ The reference's second handcrafted extractor, /root/reference/src/opensmile_extr
 SMILExtract binary once per file with Androids.conf and returns one row of 911 functionals per recording.  This module
 keeps that function's shape -- DataFrame of file paths in, one row per recording out, 'filename' first, NaN row + printed
 message for a file that cannot be processed (:89-99) -- for the part of the component graph built so far: MFCC 1-12,
-RMS energy and zero-crossing rate per 25 ms / 10 ms frame (Androids.conf:73-132) with their mean and standard deviation
-over the recording.  Column names follow OpenSMILE's '<lld>_<functional>' pattern.  The arithmetic runs in
+RMS energy and zero-crossing rate per 25 ms / 10 ms frame (Androids.conf:73-132), smoothed (cContourSmoother) and with
+regression deltas (cDeltaRegression) like the 'lld' / 'lld_de' levels of the config, with their mean and standard
+deviation over the recording.  Column names follow OpenSMILE's '<lld>_<functional>' pattern.  The arithmetic runs in
 libmshds_b200.so (mshds_lld_extract); there is no CPU fallback.
 """
 from __future__ import annotations
@@ -17,12 +18,18 @@ import numpy as np
 from . import mshds_extractor as _mx
 
 
-def lld_names(n_mfcc: int = 12):
-    return [f"mfcc[{i}]" for i in range(1, n_mfcc + 1)] + ["pcm_RMSenergy", "pcm_zcr"]
+def lld_names(n_mfcc: int = 12, smooth_win: int = 3, delta_win: int = 2):
+    """OpenSMILE-style contour names: 'mfcc_sma[1]', 'pcm_RMSenergy_sma', ..., then the '_de' regression deltas."""
+    sma = "_sma" if smooth_win > 1 else ""
+    base = [f"mfcc{sma}[{i}]" for i in range(1, n_mfcc + 1)] + [f"pcm_RMSenergy{sma}", f"pcm_zcr{sma}"]
+    if delta_win > 0:
+        base = base + [f"mfcc{sma}_de[{i}]" for i in range(1, n_mfcc + 1)] + [f"pcm_RMSenergy{sma}_de", f"pcm_zcr{sma}_de"]
+    return base
 
 
-def functional_names(n_mfcc: int = 12):
-    return [f"{n}_amean" for n in lld_names(n_mfcc)] + [f"{n}_stddev" for n in lld_names(n_mfcc)]
+def functional_names(n_mfcc: int = 12, smooth_win: int = 3, delta_win: int = 2):
+    names = lld_names(n_mfcc, smooth_win, delta_win)
+    return [f"{n}_amean" for n in names] + [f"{n}_stddev" for n in names]
 
 
 def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True, device: int = 0, **params):
@@ -33,7 +40,7 @@ def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True
     ex = _mx.get_extractor(device)
     paths = [row[audio_file_column] for _, row in input_df.iterrows()]
     filenames = [os.path.basename(p) for p in paths]
-    cols = functional_names(int(params.get("n_mfcc", 12)))
+    cols = functional_names(int(params.get("n_mfcc", 12)), int(params.get("smooth_win", 3)), int(params.get("delta_win", 2)))
     feats = np.full((len(paths), len(cols)), np.nan)
     by_rate = {}
     for i, path in enumerate(paths):

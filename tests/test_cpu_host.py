@@ -306,27 +306,34 @@ def test_lld_oracle_known_answers():
     from oracle import lld_oracle as lo
     fs = 16000.0
     # frame count: only complete 400-sample frames every 160 samples
-    assert lo.frame_lld(np.zeros(399), fs).shape == (0, 14)
-    assert lo.frame_lld(np.zeros(400), fs).shape == (1, 14)
-    assert lo.frame_lld(np.zeros(400 + 159), fs).shape == (1, 14) and lo.frame_lld(np.zeros(560), fs).shape == (2, 14)
+    raw = dict(smooth_win=0, delta_win=0)
+    assert lo.frame_lld(np.zeros(399), fs, **raw).shape == (0, 14) and lo.frame_lld(np.zeros(399), fs).shape == (0, 28)
+    assert lo.frame_lld(np.zeros(400), fs, **raw).shape == (1, 14)
+    assert lo.frame_lld(np.zeros(400 + 159), fs, **raw).shape == (1, 14) and lo.frame_lld(np.zeros(560), fs).shape == (2, 28)
     # a 1 kHz sine: 2 sign changes per period -> zcr ~ 2 * 1000 / 16000; energy of the pre-emphasised, windowed frame
     t = np.arange(16000) / fs
     x = 0.5 * np.sin(2 * np.pi * 1000.0 * t + 0.3)
-    f = lo.frame_lld(x, fs)
+    f = lo.frame_lld(x, fs, **raw)
     assert abs(f[:, 13].mean() - 2 * 1000.0 / fs) < 2.0 / 399
     h2 = 1.0 + 0.97 ** 2 - 2 * 0.97 * np.cos(2 * np.pi * 1000.0 / fs)          # |1 - k e^{-jw}|^2
     w = 0.54 - 0.46 * np.cos(2 * np.pi * np.arange(400) / 399)
     want = 0.5 * np.sqrt(h2 / 2.0) * np.sqrt((w * w).mean())
     assert abs(f[5:-5, 12].mean() / want - 1.0) < 2e-2
     # digital silence: log floor everywhere -> all cepstral coefficients of order >= 1 vanish (DCT of a constant)
-    z = lo.frame_lld(np.zeros(800), fs)
+    z = lo.frame_lld(np.zeros(800), fs, **raw)
     assert np.allclose(z[:, :12], 0.0, atol=1e-9) and np.all(z[:, 12:] == 0.0)
     # more mel bands / larger transform change the shapes consistently (BASELINE.json configs[4] sweep)
     for n_fft, n_mel in ((512, 40), (1024, 80), (2048, 40)):
         g = lo.frame_lld(x[:4000], fs, n_fft=n_fft, n_mel=n_mel)
-        assert g.shape == (23, 14) and np.all(np.isfinite(g))
+        assert g.shape == (23, 28) and np.all(np.isfinite(g))
     fun, rows = lo.extract((x * 32767).astype(np.int16), np.array([0, 8000, 8000, 16000]), fs)
-    assert fun.shape == (3, 28) and np.all(np.isnan(fun[1])) and len(rows[1]) == 0
+    assert fun.shape == (3, 56) and np.all(np.isnan(fun[1])) and len(rows[1]) == 0
+    # smoothing and deltas: a linear ramp keeps its values under a symmetric moving average (away from the ends) and has a
+    # constant regression delta equal to its slope
+    ramp = np.arange(20.0)[:, None] * np.array([[1.0, -2.0]])
+    sd = lo.smooth_delta(ramp, 3, 2)
+    assert np.allclose(sd[3:-3, :2], ramp[3:-3]) and np.allclose(sd[3:-3, 2:], [[1.0, -2.0]])
+    assert np.allclose(sd[0, :2], (2 * ramp[0] + ramp[1]) / 3)                 # the end frame is repeated
 
 
 def test_lld_dataframe_contract(tmp_path, monkeypatch):
@@ -345,6 +352,7 @@ def test_lld_dataframe_contract(tmp_path, monkeypatch):
     _write_wav(pa, a)
     _write_wav(pb, a, fs=44100)
     df = lx.extract_lld_functionals(pd.DataFrame({"filepath": [pa, str(tmp_path / "nope.wav"), pb]}), verbose=False)
-    assert list(df.columns) == ["filename"] + lx.functional_names() and df.shape == (3, 29)
+    assert list(df.columns) == ["filename"] + lx.functional_names() and df.shape == (3, 57)
     assert df.iloc[1, 1:].isna().all() and not df.iloc[0, 1:].isna().any() and not df.iloc[2, 1:].isna().any()
-    assert df.columns[1] == "mfcc[1]_amean" and df.columns[-1] == "pcm_zcr_stddev"
+    assert df.columns[1] == "mfcc_sma[1]_amean" and df.columns[-1] == "pcm_zcr_sma_de_stddev"
+    assert "pcm_RMSenergy_sma_amean" in df.columns and "mfcc_sma_de[12]_stddev" in df.columns

@@ -364,6 +364,7 @@ def test_androids_scale_ragged_batch_against_stored_oracle_values(ex):
     (16000, {"n_fft": 512, "n_mel": 40}), (16000, {"n_fft": 1024, "n_mel": 80}), (16000, {"n_fft": 2048, "n_mel": 40}),   # configs[4] sweep
     (44100, {}),                                                                        # Androids.conf:70 sampleRate
     (16000, {"frame_size": 0.032, "frame_step": 0.008, "n_mfcc": 19, "n_mel": 64, "cep_lifter": 0.0, "preemph": 0.0}),
+    (16000, {"smooth_win": 0, "delta_win": 0}), (16000, {"smooth_win": 5, "delta_win": 0}), (16000, {"smooth_win": 1, "delta_win": 3}),
 ])
 def test_lld_frames_and_functionals_match_the_numpy_restatement(ex, fs, params):
     """mshds_lld_extract (MFCC 1-12, RMS energy, ZCR per frame; mean / stddev per recording) against oracle/lld_oracle.py.
@@ -382,7 +383,8 @@ def test_lld_frames_and_functionals_match_the_numpy_restatement(ex, fs, params):
     assert list(np.diff(fo)) == [len(r) for r in wrows] and frames.shape == (int(fo[-1]), D)
     want = np.concatenate([r for r in wrows if len(r)])
     np.testing.assert_allclose(frames, want, rtol=1e-9, atol=1e-9)
-    assert np.array_equal(frames[:, D - 1], want[:, D - 1])                      # zero-crossing rate: integer count / (nf - 1)
+    if params.get("smooth_win", 3) <= 1 and params.get("delta_win", 2) == 0:
+        assert np.array_equal(frames[:, D - 1], want[:, D - 1])                  # raw zero-crossing rate: integer count / (nf - 1)
     assert np.array_equal(np.isnan(fun), np.isnan(wfun)) and np.isnan(fun[3]).all() and np.isnan(fun[4]).all()
     np.testing.assert_allclose(fun, wfun, rtol=1e-9, atol=1e-9, equal_nan=True)
 
@@ -393,11 +395,12 @@ def test_lld_device_entry_and_bad_arguments(ex):
     pcm, off, _ = _batch([1.0, 1.3], start=80)
     host, _, _ = ex.lld_extract(pcm, off)
     d = torch.from_numpy(pcm).cuda()
-    out = torch.empty((2, 28), dtype=torch.float64, device="cuda")
+    out = torch.empty((2, 56), dtype=torch.float64, device="cuda")
     ex.lld_extract_device(d.data_ptr(), off, out.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), host)
-    for bad in ({"n_fft": 300}, {"n_fft": 256}, {"n_mel": 1}, {"n_mfcc": 26}, {"frame_step": 0.0}, {"mel_lo": 9000.0}):
+    for bad in ({"n_fft": 300}, {"n_fft": 256}, {"n_mel": 1}, {"n_mfcc": 26}, {"frame_step": 0.0}, {"mel_lo": 9000.0}, {"smooth_win": 4},
+                {"delta_win": -1}):
         with pytest.raises(_lib.MshdsError):
             ex.lld_extract(pcm, off, **bad)
 
