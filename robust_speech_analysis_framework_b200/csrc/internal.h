@@ -52,6 +52,7 @@ struct PitchPass {
     int rstride;
     int* queue;                // refinement work list: frame*16 + candidate slot
     int* qcount;
+    int* turn_counter;         // work counter of the frame kernel's persistent CTAs
     // dual mode: a second analysis that differs only in its voicing threshold shares frames, correlation and rbuf
     double dual_vt;
     double* dual_cand_f; double* dual_cand_s; unsigned short* dual_cand_imax; uint8_t* dual_ncand; double* dual_inten;

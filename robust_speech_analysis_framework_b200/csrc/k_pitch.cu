@@ -247,8 +247,16 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
     const double dx = c.dx;
 
     // a CTA takes FRAMES_PER_TURN consecutive frames per turn: neighbouring frames share ~90 % of their samples (L1 hits)
+    // turns are handed out by an atomic counter: frames of low-pitched speakers cost up to twice those of high-pitched ones,
+    // and a fixed round-robin share leaves the last CTAs running alone at the end of the launch
     const int nturn = (total + FRAMES_PER_TURN - 1) / FRAMES_PER_TURN;
-    for (int turn = blockIdx.x; turn < nturn; turn += gridDim.x)
+    __shared__ int s_turn;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_turn = atomicAdd(p.turn_counter, 1);
+        __syncthreads();
+        const int turn = s_turn;
+        if (turn >= nturn) break;
     for (int f = turn * FRAMES_PER_TURN; f < total && f < (turn + 1) * FRAMES_PER_TURN; f++) {
         __syncthreads();
         if (tid == 0) {
@@ -449,6 +457,7 @@ __global__ void __launch_bounds__(NT, (IS_CC ? 512 : 1024) / NT) k_pitch_frames(
             if (dual) { p.dual_ncand[f] = (uint8_t)ncand2; p.dual_inten[f] = intensity; }
         }
     }
+    }
 }
 
 static FrameSmem frames_smem_layout(const PitchPass& p, bool is_cc) {
@@ -507,6 +516,7 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
     if (grid < 1) grid = 1;
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
+    cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
     if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
     if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
     static int nt_ac = -1, nt_cc = -1;

@@ -300,6 +300,7 @@ struct CandScratchBuf { double *f, *s, *score, *lf, *inten, *rbuf; uint8_t *ncan
 
 static void alloc_pitch_pass(mshds_handle* h, PitchPass* p, int n, long long fub, const CandScratchBuf& cs) {
     p->nF = take<int>(h, n);
+    p->turn_counter = take<int>(h, 1);
     p->t1 = take<double>(h, n);
     p->fstart = take<int>(h, n + 1);
     p->sel_f = take<double>(h, fub);
