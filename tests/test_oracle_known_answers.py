@@ -252,3 +252,54 @@ def test_exact_doubling_takes_the_upsample_route(orc):
     z = np.sin(2 * np.pi * 3950 * t)
     yz, _ = orc.resample(z, fs, 16000.0, 50)
     assert 0.1 < np.sqrt(2 * np.mean(yz[2000:-2000] ** 2)) < 0.6
+
+
+def test_harmonicity_equals_signal_to_noise_ratio(orc):
+    """A periodic signal plus white noise has autocorrelation r(T0) = S / (S + N) at its period, so the harmonics-to-noise
+    ratio 10 log10(r / (1 - r)) that Sound_to_Harmonicity_cc reports is the SNR in dB (Boersma 1993, eq. 4)."""
+    rng = np.random.default_rng(12)
+    x = pulse_train(125.0, 2.0, amp=0.2)
+    ps = np.mean(x ** 2)
+    for snr_db in (10.0, 20.0):
+        noise = rng.normal(size=len(x))
+        noise *= np.sqrt(ps / 10 ** (snr_db / 10) / np.mean(noise ** 2))
+        h = orc.hnr(x + noise, FS, 0.005, 75.0, 0.1, 4.5)
+        assert abs(h - snr_db) < 1.5, (snr_db, h)
+
+
+def test_glottal_pulses_sit_one_period_apart(orc):
+    """Sound_Pitch_to_PointProcess_cc on a strictly periodic source: consecutive pulses are exactly one period apart and their
+    number is duration * f0 (to within the voiced-stretch ends)."""
+    f0 = 160.0
+    x = pulse_train(f0, 1.5, amp=0.2)
+    for method, ppw in ((0, 3.0), (2, 1.0)):
+        t = orc.pulses(x, FS, method, 0.005, 75.0, ppw, 0.45, 600.0)
+        assert abs(len(t) - 1.5 * f0) <= 8
+        d = np.diff(t)
+        assert np.max(np.abs(d - 1.0 / f0)) < 2e-5
+        assert np.all(np.diff(t) > 0)
+
+
+def test_ltas_slope_of_a_two_band_signal(orc):
+    """'Get slope 50 1000 1000 4000 dB' = mean level of the high band minus that of the low band.  A periodic source whose
+    harmonics above 1 kHz are 20 dB weaker than those below gives about -20 dB; equal levels give about 0 dB."""
+    f0 = 125.0
+    t = np.arange(int(2.0 * FS)) / FS
+    for att_db in (0.0, 20.0):
+        x = np.zeros_like(t)
+        for hnum in range(1, 33):                               # harmonics up to 4 kHz
+            a = 1.0 if hnum * f0 < 1000.0 else 10 ** (-att_db / 20)
+            x += a * np.cos(2 * np.pi * hnum * f0 * t)
+        x *= 0.02
+        bands, out2 = orc.ltas(x, FS, 75.0, 600.0)
+        assert abs(out2[0] - (-att_db)) < 2.5, (att_db, out2)
+        assert out2[1] <= 0.0005 and (att_db == 0.0 or out2[1] < 0.0)          # robust tilt in dB/Hz: falling spectrum
+
+
+def test_pitch_statistics_of_a_two_level_contour(orc):
+    """'Get mean' / 'Get standard deviation (semitones)' over voiced frames: half a second at 100 Hz, half a second one octave
+    higher -> mean 150 Hz, sample standard deviation of 12 log2(f) close to 6 semitones."""
+    x = np.concatenate([pulse_train(100.0, 0.6, amp=0.2), pulse_train(200.0, 0.6, amp=0.2)])
+    f, st = orc.extract_f64(x, FS)
+    assert abs(f[5] - 150.0) < 3.0
+    assert abs(f[6] - 6.0) < 0.25
