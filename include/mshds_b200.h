@@ -63,8 +63,19 @@ typedef struct mshds_handle mshds_handle;
 int mshds_create(int device, mshds_handle** out);
 void mshds_destroy(mshds_handle* h);
 
-/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the handle's own; NULL restores it. */
+/* Issue all work of this handle on the caller's CUDA stream (cudaStream_t passed as void*), so that it is ordered after
+ * whatever the caller queued there (e.g. the kernel that produced a device-resident pcm buffer).  NULL names the legacy
+ * default stream -- what torch.cuda.current_stream().cuda_stream is outside a stream context -- NOT "no stream".
+ * mshds_reset_stream goes back to the handle's private non-blocking stream (the state after mshds_create). */
 int mshds_set_stream(mshds_handle* h, void* cuda_stream);
+int mshds_reset_stream(mshds_handle* h);
+
+/* Development / test switches; none selects a CPU path or changes a result.  Unknown names return MSHDS_ERR_ARG.
+ *   "hnr_exhaustive" 1: refine every correlation maximum of the harmonicity pass (to_harmonicity_cc, mshds_extractor.py:221)
+ *                       instead of skipping those that provably cannot be the frame's best (default 0; identical output)
+ *   "overlap"        0: issue the latency-bound per-clip kernels on the main stream instead of the side stream
+ *   "nvtx"           1: emit one NVTX range per pipeline stage */
+int mshds_set_option(mshds_handle* h, const char* name, long long value);
 
 /* Upper bound, in samples, of the sub-batches the handle processes at once (scratch memory scales with it). */
 int mshds_set_chunk_samples(mshds_handle* h, long long max_samples);

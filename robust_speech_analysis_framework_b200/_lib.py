@@ -30,7 +30,7 @@ CONTOURS = {"f0": 0, "intensity": 1, "hnr": 2, "formants": 3, "moments": 4}
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
     "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report", "mshds_aggregate_sessions",
-    "mshds_lld_default_params", "mshds_lld_extract", "mshds_extract_contours",
+    "mshds_lld_default_params", "mshds_lld_extract", "mshds_extract_contours", "mshds_reset_stream", "mshds_set_option",
 ]
 
 _lib = None
@@ -61,6 +61,8 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_destroy.argtypes = [C.c_void_p]
     lib.mshds_destroy.restype = None
     lib.mshds_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mshds_reset_stream.argtypes = [C.c_void_p]
+    lib.mshds_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     lib.mshds_set_chunk_samples.argtypes = [C.c_void_p, C.c_longlong]
     lib.mshds_last_error.argtypes = [C.c_void_p]
     lib.mshds_last_error.restype = C.c_char_p
@@ -107,7 +109,14 @@ class Extractor:
             raise MshdsError(f"libmshds_b200 error {rc}: {self._lib.mshds_last_error(self._h).decode()}")
 
     def set_stream(self, cuda_stream_ptr: int | None):
+        """Run on the caller's stream; 0 / None is the legacy default stream (torch's default), not the private one."""
         self._check(self._lib.mshds_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def reset_stream(self):
+        self._check(self._lib.mshds_reset_stream(self._h))
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.mshds_set_option(self._h, name.encode(), int(value)))
 
     def set_chunk_samples(self, n: int):
         self._check(self._lib.mshds_set_chunk_samples(self._h, int(n)))

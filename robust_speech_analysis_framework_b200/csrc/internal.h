@@ -11,6 +11,20 @@ struct SPtr {
     __host__ __device__ SPtr operator-(long long o) const { return SPtr{p16 ? p16 - o : nullptr, p64 ? p64 - o : nullptr}; }
 };
 
+// SM count of the current device (grids are sized in multiples of it), queried once per device
+static inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;   // B200
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 #define MAXCAND 15             // Pitch candidates kept per frame for the Viterbi passes (incl. the voiceless one)
 
 // Per speaker-class configuration of one Sound_to_Pitch_any call (fon/Sound_to_Pitch.cpp set-up section).
@@ -62,6 +76,9 @@ struct PitchPass {
     unsigned long long* qcount64;
     unsigned long long q64_cap;
     unsigned long long* best_bits;   // [frames] bits of the largest refined strength (0 = none)
+    unsigned long long* hnr_top;     // [frames] item of the frame's highest maximum (refined first; 0 = none): its refined
+                                     //          strength lets k_hnr_refine skip maxima that provably cannot win the frame
+    int hnr_exhaustive;              // 1: refine every maximum (debug switch "hnr_exhaustive"; identical results)
     // results
     double* sel_f;             // [frames] frequency of the chosen candidate (0 = voiceless)
     double* sel_s;             // [frames] strength of the chosen candidate / HNR: best r (NaN when voiceless)

@@ -558,7 +558,7 @@ void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const
                         const double* wtab, int wtab_n, cudaStream_t s) {
     static int nt = 0;
     if (!nt) { const char* e = getenv("MSHDS_NT_CEP"); nt = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : NT_CEP_DEFAULT); }   // development switch
-    const int cap = nt == 128 ? 148 * 12 : 148 * 8;
+    const int cap = nt == 128 ? sm_count() * 12 : sm_count() * 8;
     int grid = total_frames < cap ? total_frames : cap;
     if (grid < 1) grid = 1;
     size_t smem = sizeof(double2) * 512 + sizeof(double) * 32;
@@ -566,14 +566,14 @@ void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const
 }
 void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {
-    int grid = total_frames < 148 * 8 ? total_frames : 148 * 8;
+    int grid = total_frames < sm_count() * 8 ? total_frames : sm_count() * 8;
     if (grid < 1) grid = 1;
     static int use_block = -1;
     if (use_block < 0) { const char* e = getenv("MSHDS_CPP_BLOCK"); use_block = e && atoi(e) ? 1 : 0; }    // development switch
     if (nqmax <= 513 && !use_block) {
         const size_t smem = sizeof(double) * CPW_STRIDE * CPW;
         int g = (total_frames + CPW - 1) / CPW;
-        if (g > 148 * 2) g = 148 * 2;
+        if (g > sm_count() * 2) g = sm_count() * 2;
         if (g < 1) g = 1;
         cudaFuncSetAttribute(k_cpp_frames_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_cpp_frames_warp<<<g, 32 * CPW, smem, s>>>(segs, fprefix, nsegs, cep, nqmax, nTimeAvg, qAvgWindow, 1.0 / 330.0, 1.0 / 60.0,

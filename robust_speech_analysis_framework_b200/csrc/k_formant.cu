@@ -298,7 +298,7 @@ void launch_formants(const Clips& c, const FormantPass& p, int njobs, const doub
     k_formant_grid<<<(njobs + 127) / 128, 128, 0, s>>>(p, njobs);
     launch_exclusive_scan(p.nF, p.fstart, njobs, s);
     int grid = (max_frames_hint / FGROUP + FW) / FW;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
     if (grid < 1) grid = 1;
     k_formant_frames<<<grid, FW * 32, 0, s>>>(p, njobs, sig);
 }

@@ -65,7 +65,7 @@ void launch_intensity(const Clips& c, const IntensityPass& p, int max_frames_hin
     k_intensity_grid<<<(c.n + 127) / 128, 128, 0, s>>>(c, p);
     launch_exclusive_scan(p.nF, p.fstart, c.n, s);
     int grid = (max_frames_hint + 7) / 8;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > sm_count() * 8) grid = sm_count() * 8;
     if (grid < 1) grid = 1;
     k_intensity_frames<<<grid, 256, 0, s>>>(c, p);
 }

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) k_lld_post(LldPass p, int n) {
 
 void launch_lld_post(const LldPass& p, int n, long long frames_hint, cudaStream_t s) {
     long long blocks = (frames_hint * (p.n_mfcc + 2) + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     if (blocks < 1) blocks = 1;
     k_lld_post<<<(unsigned)blocks, 256, 0, s>>>(p, n);
 }
@@ -174,7 +174,7 @@ void launch_lld_frames(const LldPass& p, const int16_t* pcm, const long long* of
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_lld_frames, 128, smem);
     if (occ < 1) occ = 1;
-    long long grid = 148LL * occ;
+    long long grid = (long long)sm_count() * occ;
     const long long nturn = (frames_hint + 7) / 8;
     if (grid > nturn) grid = nturn;
     if (grid < 1) grid = 1;

@@ -216,6 +216,6 @@ __global__ void k_ltas_final(Clips c, PulseSet ps, LtasPass lt, double* ltas_ban
 void launch_ltas(const Clips& c, const PulseSet& ps, const LtasPass& lt, double* ltas_bands, cudaStream_t s) {
     k_ltas_parts<<<(c.n + 127) / 128, 128, 0, s>>>(c, ps, lt);
     launch_exclusive_scan(lt.part_count, lt.part_start, c.n, s);
-    k_ltas_accum<<<148 * 4, LW * 32, 0, s>>>(c, ps, lt, 5000.0, 100.0, 0.0001, 0.02, 1.3);
+    k_ltas_accum<<<sm_count() * 4, LW * 32, 0, s>>>(c, ps, lt, 5000.0, 100.0, 0.0001, 0.02, 1.3);
     k_ltas_final<<<(c.n + 63) / 64, 64, 0, s>>>(c, ps, lt, ltas_bands, 100.0);
 }

@@ -124,13 +124,13 @@ void launch_moments(const Clips& c, const SpecPass& p, const PitchPass& pp, cons
     k_spec_grid<<<(c.n + 127) / 128, 128, 0, s>>>(c, p);
     launch_exclusive_scan(p.nF, p.fstart, c.n, s);
     size_t smem = sizeof(double2) * p.M + sizeof(double) * (p.M + 8 + 32);
-    int grid = 148 * 8;
+    int grid = sm_count() * 8;
     if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint;
     if (grid < 1) grid = 1;
     cudaFuncSetAttribute(k_spec_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     static int nt = 0;
     if (!nt) { const char* e = getenv("MSHDS_NT_SPEC"); nt = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : NT_SPEC_DEFAULT); }   // development switch
-    if (nt == 128) { grid = 148 * 12; if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint; if (grid < 1) grid = 1; }
+    if (nt == 128) { grid = sm_count() * 12; if (max_frames_hint > 0 && grid > max_frames_hint) grid = max_frames_hint; if (grid < 1) grid = 1; }
     k_spec_frames<<<grid, nt, smem, s>>>(c, p, pp, tw);
     k_spec_reduce<<<c.n, 256, 0, s>>>(c, p, pp);
 }

@@ -335,7 +335,7 @@ __global__ void k_pulses_assemble(Clips c, PitchPass p, PulseSet ps) {
 void launch_pulses(const Clips& c, const PitchPass& p, const PulseSet& ps, cudaStream_t s) {
     k_stretch_list<<<(c.n + 3) / 4, 128, 0, s>>>(c, p, ps);
     launch_exclusive_scan(ps.st_count, ps.st_start, c.n, s);
-    int grid = 148 * 8;
+    int grid = sm_count() * 8;
     k_pulses_stretch<<<grid, PW * 32, 0, s>>>(c, p, ps);
     k_pulses_assemble<<<(c.n + 63) / 64, 64, 0, s>>>(c, p, ps);
 }

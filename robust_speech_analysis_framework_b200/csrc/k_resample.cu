@@ -509,7 +509,7 @@ void launch_sinc_resample(const ResampleJob* d_jobs, const long long* d_out_pref
     double* table_fl = table + (size_t)ntables * (P > 0 ? P : 1) * 2 * D;      // stored behind the coefficient rows
     long long* table_mid = (long long*)(table_fl + (size_t)ntables * (P > 0 ? P : 1));
     long long blocks = (total_out_hint + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     if (blocks < 1) blocks = 1;
     if (fir && ntables > 0 && total_tiles > 0) {
         k_sinc_table<<<ntables, 256, 0, s>>>(d_jobs, d_table_rep, ntables, table, table_fl, table_mid, P, D, dx_src);

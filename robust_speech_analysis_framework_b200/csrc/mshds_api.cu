@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "num.cuh"
 
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +68,12 @@ struct mshds_handle {
     // scratch of the frame-level descriptor path (mshds_lld_extract)
     char* lld_buf = nullptr;
     size_t lld_cap = 0;
+    // scratch of mshds_aggregate_sessions (grow-only)
+    char* agg_buf = nullptr;
+    size_t agg_cap = 0;
+    // development / test switches (mshds_set_option)
+    int hnr_exhaustive = 0;
+    int nvtx = 0;
     // arena
     char* arena = nullptr;
     size_t arena_cap = 0, arena_off = 0;
@@ -82,6 +89,7 @@ struct mshds_handle {
 };
 
 static void prof_begin(mshds_handle* h, const char* name) {
+    if (h->nvtx) nvtxRangePushA(name);          // NVTX range per stage (host-side issue span; "nvtx" option)
     if (!h->prof_on) return;
     mshds_handle::ProfSpan sp;
     sp.name = name;
@@ -91,6 +99,7 @@ static void prof_begin(mshds_handle* h, const char* name) {
     h->prof_open.push_back(sp);
 }
 static void prof_end(mshds_handle* h) {
+    if (h->nvtx) nvtxRangePop();
     if (!h->prof_on || h->prof_open.empty()) return;
     // close the most recent span that has not been closed yet
     for (size_t i = h->prof_open.size(); i-- > 0;) {
@@ -635,6 +644,8 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     hnr.queue64 = take<unsigned long long>(h, hnr.q64_cap);
     hnr.qcount64 = take<unsigned long long>(h, 1);
     hnr.best_bits = take<unsigned long long>(h, fub5);
+    hnr.hnr_top = take<unsigned long long>(h, fub5);
+    hnr.hnr_exhaustive = h->hnr_exhaustive;
     alloc_pitch_pass(h, &srp, n, fub20, cs_sr);
     alloc_pitch_pass(h, &ltp, n, fub75, cs_lt);
     alloc_pitch_pass(h, &ccp, n, fub5, cs_cc);
@@ -1000,6 +1011,7 @@ void mshds_destroy(mshds_handle* h) {
     cudaFree(h->cpp_buf);
     cudaFree(h->front_buf);
     cudaFree(h->lld_buf);
+    cudaFree(h->agg_buf);
     cudaFree(h->tw);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1011,7 +1023,25 @@ void mshds_destroy(mshds_handle* h) {
 
 int mshds_set_stream(mshds_handle* h, void* cuda_stream) {
     if (!h) return MSHDS_ERR_ARG;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    // a NULL cudaStream_t IS a stream: the legacy default stream (what torch.cuda.current_stream().cuda_stream is when no
+    // stream context is active).  Work the caller queued there is ordered before the extraction, like on any other stream.
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
+    return MSHDS_OK;
+}
+
+int mshds_reset_stream(mshds_handle* h) {
+    if (!h) return MSHDS_ERR_ARG;
+    h->stream = h->own_stream;
+    return MSHDS_OK;
+}
+
+int mshds_set_option(mshds_handle* h, const char* name, long long value) {
+    if (!h || !name) return MSHDS_ERR_ARG;
+    const std::string n(name);
+    if (n == "hnr_exhaustive") h->hnr_exhaustive = value != 0;
+    else if (n == "overlap") h->overlap = value != 0;
+    else if (n == "nvtx") h->nvtx = value != 0;
+    else { h->err = "unknown option: " + n; return MSHDS_ERR_ARG; }
     return MSHDS_OK;
 }
 
@@ -1352,7 +1382,14 @@ int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows
     const size_t o_mean = o_feat + (on_dev ? 0 : ((fbytes + 255) & ~(size_t)255));
     const size_t o_std = o_mean + (on_dev ? 0 : ((obytes + 255) & ~(size_t)255));
     const size_t total = o_std + (on_dev ? 0 : obytes) + 256;
-    CK(cudaMalloc((void**)&buf, total));
+    if (total > h->agg_cap) {
+        CK(cudaStreamSynchronize(s));
+        if (h->agg_buf) CK(cudaFree(h->agg_buf));
+        h->agg_buf = nullptr; h->agg_cap = 0;
+        CK(cudaMalloc((void**)&h->agg_buf, total + (total >> 2)));
+        h->agg_cap = total + (total >> 2);
+    }
+    buf = h->agg_buf;
     int rc = MSHDS_OK;
     do {
         if (cudaMemcpyAsync(buf + o_start, start.data(), sizeof(int) * (n_groups + 1), cudaMemcpyHostToDevice, s) != cudaSuccess ||
@@ -1371,7 +1408,6 @@ int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows
         }
         if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = MSHDS_ERR_CUDA; break; }
     } while (0);
-    cudaFree(buf);
     if (rc) h->err = "CUDA failure in mshds_aggregate_sessions";
     return rc;
 }
