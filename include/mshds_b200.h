@@ -187,6 +187,10 @@ long long mshds_launch_count(const mshds_handle* h);
  * figure of the dominant kernel; the reference has no counterpart (it only has a tqdm bar, mshds_extractor.py:406).
  */
 int mshds_profile_enable(mshds_handle* h, int on);
+/* Measured float64 FMA issue peak of the handle's device in TFLOP/s (2 FLOP per DFMA; best of five launches of a
+ * register-only kernel with 8 independent chains per thread): the denominator of the compute-side roofline bench.py reports,
+ * since MEASURED_PEAKS.json only holds HBM and bf16 tensor figures and this path is float64 on the vector pipe. */
+int mshds_fp64_peak(mshds_handle* h, double* tflops);
 int mshds_profile_report(mshds_handle* h, char* buf, size_t cap);
 
 /*

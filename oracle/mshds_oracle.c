@@ -14,6 +14,18 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
+OrcOptions orc_opt = {0};
+
+/* set one Appendix-C switch by name (see praat_core.h); returns 0 for an unknown name */
+EXPORT int orc_set_option(const char *name, int value) {
+#define OPT(f) if (!strcmp(name, #f)) { orc_opt.f = value; return 1; }
+    OPT(silence_boundary) OPT(cut_interval) OPT(theil_tilt_complete) OPT(theil_cpps_complete) OPT(cpps_fit_range)
+    OPT(cpps_time_frames) OPT(cpps_smooth_align) OPT(vuv_overlap) OPT(ltas_fill) OPT(candidate_bound)
+#undef OPT
+    if (!strcmp(name, "reset")) { memset(&orc_opt, 0, sizeof orc_opt); return 1; }
+    return 0;
+}
+
 enum {
     ST_SPEECHRATE = 1u << 0, ST_PITCHRANGE_FALLBACK = 1u << 1, ST_PITCH = 1u << 2, ST_INTENSITY = 1u << 3,
     ST_HNR = 1u << 4, ST_LTAS = 1u << 5, ST_CPP = 1u << 6, ST_FORMANT = 1u << 7, ST_MOMENTS = 1u << 8,
@@ -176,6 +188,7 @@ static double extract_CPP(const Sound *snd, double floor_, double ceiling) {
     double maxT = 0.02, meanT = 0.1, halfMeanT = 0.5 * meanT;
     double sum = 0; long cnt = 0; int fail = 0;
     long ipointright;
+    double prevEnd = snd->xmin;
     for (long ipointleft = 1; ipointleft <= pulses->n; ipointleft = ipointright + 1) {
         for (ipointright = ipointleft + 1; ipointright <= pulses->n; ipointright++)
             if (pulses->t[ipointright - 1] - pulses->t[ipointright - 2] > maxT) break;
@@ -184,6 +197,23 @@ static double extract_CPP(const Sound *snd, double floor_, double ceiling) {
         if (beginVoiced < snd->xmin) beginVoiced = snd->xmin;
         double endVoiced = pulses->t[ipointright - 1] + halfMeanT;
         if (endVoiced > snd->xmax) endVoiced = snd->xmax;
+        if (orc_opt.vuv_overlap == 1) {
+            /* alternative reading: runs whose extended intervals overlap form ONE V interval */
+            while (ipointright < pulses->n) {
+                double nextBegin = pulses->t[ipointright] - halfMeanT;
+                if (nextBegin > endVoiced) break;
+                long j;
+                for (j = ipointright + 2; j <= pulses->n; j++)
+                    if (pulses->t[j - 1] - pulses->t[j - 2] > maxT) break;
+                ipointright = j - 1;
+                endVoiced = pulses->t[ipointright - 1] + halfMeanT;
+                if (endVoiced > snd->xmax) endVoiced = snd->xmax;
+            }
+        } else if (orc_opt.vuv_overlap == 2) {
+            /* alternative reading: a V interval cannot start before the previous one ended */
+            if (beginVoiced < prevEnd) beginVoiced = prevEnd;
+        }
+        prevEnd = endVoiced;
         /* :273 "Down to Table" renders times with 6 decimals; :280-281 float() of the strings */
         char buf[64];
         snprintf(buf, sizeof buf, "%.6f", beginVoiced); double tmin = strtod(buf, NULL);

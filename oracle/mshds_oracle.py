@@ -56,6 +56,23 @@ def lib() -> C.CDLL:
     return _lib
 
 
+OPTIONS = {   # SURVEY.md Appendix C switches (praat_core.h OrcOptions): name -> alternative values
+    "silence_boundary": (1,), "cut_interval": (1,), "theil_tilt_complete": (1,), "theil_cpps_complete": (1,),
+    "cpps_fit_range": (1,), "cpps_time_frames": (1,), "cpps_smooth_align": (1,), "vuv_overlap": (1, 2), "ltas_fill": (1,),
+    "candidate_bound": (1,),
+}
+
+
+def set_option(name: str, value: int) -> None:
+    """Flip one alternative reading of a Praat detail (oracle only; 0 = the default all goldens use)."""
+    if not lib().orc_set_option(name.encode(), C.c_int(int(value))):
+        raise KeyError(name)
+
+
+def reset_options() -> None:
+    lib().orc_set_option(b"reset", C.c_int(0))
+
+
 def _f64(x):
     return np.ascontiguousarray(x, dtype=np.float64)
 

@@ -30,6 +30,28 @@
 static inline int isundef(double x) { return !(x == x) || isinf(x); }
 static inline int isdefined(double x) { return !isundef(x); }
 
+/* ---- alternative readings of Praat details that cannot be checked offline ----
+ * Every choice the restatement had to make without the Praat source at hand sits behind one switch; 0 is the reading all
+ * committed goldens and parity tests use.  tools/appc_sensitivity.py flips them one at a time and reports which of the 25
+ * columns move and by how much.  ORACLE ONLY: the CUDA path implements the default reading. */
+typedef struct {
+    int silence_boundary;      /* C-1  0: boundary at the frame centre x1 + (i-1) dx; 1: half a frame earlier (between frames) */
+    int cut_interval;          /* ADVICE r1  0: removing a too-short interval joins it and both same-label neighbours into one
+                                  (IntervalTier_cutInterval + IntervalTier_cutIntervalsOnLabelMatch); 1: the left neighbour is
+                                  extended only and equal-label neighbours stay separate intervals */
+    int theil_tilt_complete;   /* C-3  0: incomplete Theil (pairs i, i + n/2) in "Report spectral tilt"; 1: all pairs */
+    int theil_cpps_complete;   /* C-3  same for the CPPS trend line */
+    int cpps_fit_range;        /* C-4  0: qendFit = 0 <= qstartFit selects the whole quefrency domain; 1: [0.001, qmax] */
+    int cpps_time_frames;      /* C-5  0: floor(0.01 / 0.002) as IEEE double division gives it (5); 1: one frame fewer (4) */
+    int cpps_smooth_align;     /* C-5  0: an even box window drops its LAST tap; 1: drops its FIRST tap */
+    int vuv_overlap;           /* A.12 0: overlapping V intervals stay separate rows; 1: merged; 2: a V interval starts no earlier
+                                  than the previous one ends */
+    int ltas_fill;             /* C-6  0: empty LTAS bands filled in increasing band order (a filled band can feed the next);
+                                  1: filled from measured bands only */
+    int candidate_bound;       /* C-2  0: candidate lags i < maximumLag && i < brent_ixmax; 1: i <= (inclusive bounds) */
+} OrcOptions;
+extern OrcOptions orc_opt;
+
 /* ---- Sampled (fon/Sampled.cpp) ---- */
 typedef struct {
     double xmin, xmax;

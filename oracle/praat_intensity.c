@@ -91,6 +91,11 @@ static void tier_cut_short(Tier *t, int sounding, double minimumDuration) {
             } else if (i == t->n - 1) {
                 t->v[i - 1].xmax = xmax;
                 t->n -= 1;
+            } else if (orc_opt.cut_interval == 1) {
+                /* alternative reading: extend the left neighbour only; i+1 (same label as i-1) stays its own interval */
+                t->v[i - 1].xmax = xmax;
+                memmove(&t->v[i], &t->v[i + 1], sizeof(Interval) * (size_t)(t->n - i - 1));
+                t->n -= 1;
             } else {
                 /* neighbours i-1 and i+1 carry the other label: merge them across the removed interval */
                 t->v[i - 1].xmax = t->v[i + 1].xmax;
@@ -126,6 +131,7 @@ Tier *intensity_to_silences(const Contour *me, double silenceThreshold_dB, doubl
         int silent = me->y[i - 1] < intensityThreshold;
         if (silent != inSilenceInterval) {
             double time = me->x1 + (i - 1) * me->dx;
+            if (orc_opt.silence_boundary == 1) time -= 0.5 * me->dx;
             t->v[n].xmin = start; t->v[n].xmax = time; t->v[n].sounding = !inSilenceInterval;
             n++;
             start = time;

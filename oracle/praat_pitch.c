@@ -239,7 +239,7 @@ Pitch *sound_to_pitch_any(const Sound *me, double dt, double minimumPitch, doubl
 
         int nCand = 1;
         imax[1] = 0;
-        for (long i = 2; i < maximumLag && i < brent_ixmax; i++)
+        for (long i = 2; orc_opt.candidate_bound == 1 ? (i <= maximumLag && i < brent_ixmax) : (i < maximumLag && i < brent_ixmax); i++)
             if (r[i] > 0.5 * voicingThreshold && r[i] > r[i - 1] && r[i] >= r[i + 1]) {
                 int place = 0;
                 double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];

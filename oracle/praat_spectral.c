@@ -86,9 +86,28 @@ int pointprocess_sound_to_ltas(const Points *pulses, const Sound *sound, double 
         }
     }
     double x1 = 0.5 * bandWidth;
+    double *measured = NULL;
+    if (orc_opt.ltas_fill == 1) {      /* alternative: interpolate between MEASURED bands only */
+        measured = (double *)malloc(sizeof(double) * (size_t)nb);
+        memcpy(measured, ltas, sizeof(double) * (size_t)nb);
+    }
     for (long iband = 1; iband <= nb; iband++) {
-        if (isundef(ltas[iband - 1])) {
+        if (measured ? isundef(measured[iband - 1]) : isundef(ltas[iband - 1])) {
             long ibandleft = iband - 1, ibandright = iband + 1;
+            if (measured) {
+                while (ibandleft >= 1 && isundef(measured[ibandleft - 1])) ibandleft--;
+                while (ibandright <= nb && isundef(measured[ibandright - 1])) ibandright++;
+                if (ibandleft < 1 && ibandright > nb) { free(numbers); free(measured); return 0; }
+                if (ibandleft < 1) ltas[iband - 1] = measured[ibandright - 1];
+                else if (ibandright > nb) ltas[iband - 1] = measured[ibandleft - 1];
+                else {
+                    double frequency = x1 + (iband - 1) * bandWidth;
+                    double fleft = x1 + (ibandleft - 1) * bandWidth;
+                    double fright = x1 + (ibandright - 1) * bandWidth;
+                    ltas[iband - 1] = ((fright - frequency) * measured[ibandleft - 1] + (frequency - fleft) * measured[ibandright - 1]) / (fright - fleft);
+                }
+                continue;
+            }
             while (ibandleft >= 1 && isundef(ltas[ibandleft - 1])) ibandleft--;
             while (ibandright <= nb && isundef(ltas[ibandright - 1])) ibandright++;
             if (ibandleft < 1 && ibandright > nb) { free(numbers); return 0; }
@@ -103,6 +122,7 @@ int pointprocess_sound_to_ltas(const Points *pulses, const Sound *sound, double 
         }
     }
     free(numbers);
+    free(measured);
     return 1;
 }
 
@@ -166,7 +186,7 @@ int ltas_fitTiltLine_robust(const double *z0, long nx, double dx, double fmin, d
         x[i - ifmin] = x1 + (i - 1) * dx;
         y[i - ifmin] = z0[i - 1];
     }
-    NUMlineFit_theil(x - 1, y - 1, n, slope, intercept, 0);
+    NUMlineFit_theil(x - 1, y - 1, n, slope, intercept, orc_opt.theil_tilt_complete);
     free(x); free(y);
     return 1;
 }
@@ -589,7 +609,7 @@ double formant_getValueAtTime(const Formant *me, int iformant, double x, int ban
 static void smooth_moving_average(double *out, const double *in, long n, long window) {
     for (long i = 1; i <= n; i++) {
         long jfrom = i - window / 2, jto = i + window / 2;
-        if ((window % 2) == 0) jto--;
+        if ((window % 2) == 0) { if (orc_opt.cpps_smooth_align == 1) jfrom++; else jto--; }
         jfrom = jfrom < 1 ? 1 : jfrom;
         jto = jto > n ? n : jto;
         double s = 0.0;
@@ -661,6 +681,7 @@ int sound_cpps(const Sound *me, double pitchFloor, double dt, double maximumFreq
 
     /* PowerCepstrogram_smooth */
     long numberOfFrames = (long)floor(timeAveragingWindow / dt);
+    if (orc_opt.cpps_time_frames == 1) numberOfFrames -= 1;
     if (numberOfFrames > 1) {
         double *qout = (double *)malloc(sizeof(double) * (size_t)nFrames);
         for (long iq = 0; iq < nq; iq++) {
@@ -684,13 +705,13 @@ int sound_cpps(const Sound *me, double pitchFloor, double dt, double maximumFreq
         for (long iq = 0; iq < nq; iq++) col2[iq] = 10.0 * log10(col2[iq] + 1e-30);
         /* PowerCepstrum_fitTiltLine: Straight, Robust; qmax <= qmin -> whole domain */
         double qlo = qstartFit, qhi = qendFit;
-        if (qhi <= qlo) { qlo = 0.0; qhi = qmax; }
+        if (qhi <= qlo) { qlo = orc_opt.cpps_fit_range == 1 ? qstartFit : 0.0; qhi = qmax; }
         long imin, imax;
         if (!getWindowSamples(0.0, dq, nq, qlo, qhi, &imin, &imax) || imax - imin + 1 < 2) { sum = NAN; break; }
         long npts = imax - imin + 1;
         for (long i = 0; i < npts; i++) xq[i] = (imin + i - 1) * dq;
         double slope, intercept;
-        NUMlineFit_theil(xq - 1, col2 + (imin - 1) - 1, npts, &slope, &intercept, 0);
+        NUMlineFit_theil(xq - 1, col2 + (imin - 1) - 1, npts, &slope, &intercept, orc_opt.theil_cpps_complete);
         double peakdB, quefrency;
         vector_getMaximumAndX(&c, 1.0 / peakCeiling, 1.0 / peakFloor, PEAK_PARABOLIC, &peakdB, &quefrency);
         sum += peakdB - (slope * quefrency + intercept);

@@ -30,7 +30,7 @@ CONTOURS = {"f0": 0, "intensity": 1, "hnr": 2, "formants": 3, "moments": 4}
 EXPORTED_SYMBOLS = [
     "mshds_create", "mshds_destroy", "mshds_set_stream", "mshds_set_chunk_samples", "mshds_last_error", "mshds_extract",
     "mshds_launch_count", "mshds_debug_fetch", "mshds_profile_enable", "mshds_profile_report", "mshds_aggregate_sessions",
-    "mshds_lld_default_params", "mshds_lld_extract", "mshds_extract_contours", "mshds_reset_stream", "mshds_set_option",
+    "mshds_lld_default_params", "mshds_lld_extract", "mshds_extract_contours", "mshds_reset_stream", "mshds_set_option", "mshds_fp64_peak",
 ]
 
 _lib = None
@@ -61,6 +61,7 @@ def load(build_if_needed: bool = True) -> C.CDLL:
     lib.mshds_destroy.argtypes = [C.c_void_p]
     lib.mshds_destroy.restype = None
     lib.mshds_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mshds_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.mshds_reset_stream.argtypes = [C.c_void_p]
     lib.mshds_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_longlong]
     lib.mshds_set_chunk_samples.argtypes = [C.c_void_p, C.c_longlong]
@@ -153,6 +154,12 @@ class Extractor:
         n = len(offsets) - 1
         self._check(self._lib.mshds_extract(self._h, C.c_void_p(pcm_ptr), offsets.ctypes.data, n, int(sample_rate),
                                             C.c_void_p(out_ptr), C.c_void_p(status_ptr), PCM_ON_DEVICE | OUT_ON_DEVICE))
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured DFMA issue peak of this device (mshds_fp64_peak)."""
+        v = C.c_double(0.0)
+        self._check(self._lib.mshds_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
 
     def profile(self, on: bool):
         self._check(self._lib.mshds_profile_enable(self._h, int(on)))

@@ -965,6 +965,8 @@ static int collect_contours(mshds_handle* h, int c0, int n) {
     return MSHDS_OK;
 }
 
+double run_dfma_peak(double* scratch, cudaStream_t s, int reps);      // k_microbench.cu
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1410,6 +1412,20 @@ int mshds_aggregate_sessions(mshds_handle* h, const double* features, int n_rows
     } while (0);
     if (rc) h->err = "CUDA failure in mshds_aggregate_sessions";
     return rc;
+}
+
+int mshds_fp64_peak(mshds_handle* h, double* tflops) {
+    if (!h || !tflops) return MSHDS_ERR_ARG;
+    h->err.clear();
+    CK(cudaSetDevice(h->device));
+    double* scratch = nullptr;
+    CK(cudaMalloc((void**)&scratch, sizeof(double) * (size_t)sm_count() * 8 * 256));
+    const double tf = run_dfma_peak(scratch, h->stream, 5);
+    cudaFree(scratch);
+    h->launches += 6;
+    if (tf < 0.0) { h->err = "DFMA microbenchmark failed"; return MSHDS_ERR_CUDA; }
+    *tflops = tf;
+    return MSHDS_OK;
 }
 
 int mshds_profile_enable(mshds_handle* h, int on) {

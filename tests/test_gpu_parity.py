@@ -154,9 +154,104 @@ def test_device_resident_entry_point(ex):
         ex.extract_device(d_pcm.data_ptr(), off, d_out.data_ptr(), d_st.data_ptr())
         torch.cuda.synchronize()
     finally:
-        ex.set_stream(None)
+        ex.reset_stream()
     assert np.array_equal(d_out.cpu().numpy(), host, equal_nan=True)
     assert np.array_equal(d_st.cpu().numpy().astype(np.uint32), hst)
+
+
+def test_caller_stream_orders_the_extraction_after_async_producers(ex):
+    """ADVICE r1: the int16 batch is PRODUCED asynchronously on a non-default torch stream (behind a long-running kernel);
+    the extraction is handed that stream and must see the finished data -- and likewise on the legacy default stream,
+    which is what a NULL cudaStream_t names."""
+    import torch
+    pcm, off, _ = _batch([2.5, 3.0], start=84)
+    host, hst = ex.extract_host(pcm, off)
+    src = torch.from_numpy(pcm).cuda()
+    big = torch.empty(1 << 28, dtype=torch.float32, device="cuda")          # 1 GiB: keeps the stream busy for a while
+    for stream in (torch.cuda.Stream(), None):
+        d_pcm = torch.zeros_like(src)
+        d_out = torch.full((2, 25), -1.0, dtype=torch.float64, device="cuda")
+        d_st = torch.empty(2, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.default_stream())
+        with ctx:
+            for _ in range(8):
+                big.mul_(1.0001)                                            # queued work in front of the producer
+            d_pcm.copy_(src, non_blocking=True)                             # the producer, asynchronous on this stream
+            ex.set_stream(torch.cuda.current_stream().cuda_stream)          # 0 for the default stream
+            try:
+                ex.extract_device(d_pcm.data_ptr(), off, d_out.data_ptr(), d_st.data_ptr())
+            finally:
+                ex.reset_stream()
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), host, equal_nan=True), "extraction read the batch before it was written"
+        assert np.array_equal(d_st.cpu().numpy().astype(np.uint32), hst)
+
+
+def test_pruned_harmonicity_refinement_equals_the_exhaustive_one(ex, orc):
+    """k_hnr_refine skips correlation maxima that cannot be the frame's best; "hnr_exhaustive" refines them all.  The HNR
+    contour (and so the column) must be bit-identical -- on speech-like clips and on noise / tone mixtures whose correlation
+    has many comparable maxima."""
+    rng = np.random.default_rng(11)
+    pcm, off, clips = _batch([4.0, 3.00006, 5.0], start=120)
+    t = np.arange(48000) / 16000.0
+    noisy = (0.2 * np.sin(2 * np.pi * 140 * t) + 0.2 * np.sin(2 * np.pi * 287 * t + 1.0) + 0.1 * rng.normal(size=t.size))
+    clips = clips + [(noisy * 12000).astype(np.int16), (rng.normal(scale=3000.0, size=40000)).astype(np.int16)]
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    pruned, _ = ex.extract_host(pcm, off)
+    contours_pruned = [ex.debug_fetch("hnr_r", c) for c in range(len(clips))]
+    ex.set_option("hnr_exhaustive", 1)
+    try:
+        full, _ = ex.extract_host(pcm, off)
+        contours_full = [ex.debug_fetch("hnr_r", c) for c in range(len(clips))]
+    finally:
+        ex.set_option("hnr_exhaustive", 0)
+    for a, b in zip(contours_pruned, contours_full):
+        assert np.array_equal(a, b, equal_nan=True)
+    assert np.array_equal(pruned, full, equal_nan=True)
+    want, _ = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
+    assert_features_close(pruned, want, "hnr pruning")
+
+
+def _sharded_worker(rank, world, port, pcm, off, q):
+    import torch
+    import torch.distributed as dist
+    from robust_speech_analysis_framework_b200 import _lib
+    from robust_speech_analysis_framework_b200.sharding import extract_sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    e = _lib.Extractor(rank)
+    out, st = extract_sharded(pcm, off, e.extract_host, rank, world)
+    if rank == 0:
+        q.put((out, st))
+    dist.barrier()
+    dist.destroy_process_group()
+    e.close()
+
+
+def test_two_gpu_sharded_extraction_equals_single_gpu(ex):
+    """LPT-sharded extraction over 2 GPUs (one process each, NCCL gather of the feature matrix only) is
+    bit-identical to the single-GPU result, row for row in input order."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    pcm, off, _ = _batch([6.0, 2.0, 9.0, 3.5, 4.00006, 7.0, 2.5], start=140)
+    want, wst = ex.extract_host(pcm, off)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, pcm, off, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, gst = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    assert np.array_equal(got, want, equal_nan=True) and np.array_equal(gst, wst)
 
 
 def test_bad_arguments_are_errors_not_crashes(ex):
