@@ -71,8 +71,8 @@ int mshds_set_stream(mshds_handle* h, void* cuda_stream);
 int mshds_reset_stream(mshds_handle* h);
 
 /* Development / test switches; none selects a CPU path or changes a result.  Unknown names return MSHDS_ERR_ARG.
- *   "hnr_exhaustive" 1: refine every correlation maximum of the harmonicity pass (to_harmonicity_cc, mshds_extractor.py:221)
- *                       instead of skipping those that provably cannot be the frame's best (default 0; identical output)
+ *   "legacy_fft"     1: CTA-per-frame shared-memory FFT frame kernels (round 1) instead of the warp-per-frame register FFT with
+ *                       TMA-staged sample spans; same results up to the rounding of another exact FFT order (A/B timing, tests)
  *   "overlap"        0: issue the latency-bound per-clip kernels on the main stream instead of the side stream
  *   "nvtx"           1: emit one NVTX range per pipeline stage */
 int mshds_set_option(mshds_handle* h, const char* name, long long value);

@@ -76,9 +76,6 @@ struct PitchPass {
     unsigned long long* qcount64;
     unsigned long long q64_cap;
     unsigned long long* best_bits;   // [frames] bits of the largest refined strength (0 = none)
-    unsigned long long* hnr_top;     // [frames] item of the frame's highest maximum (refined first; 0 = none): its refined
-                                     //          strength lets k_hnr_refine skip maxima that provably cannot win the frame
-    int hnr_exhaustive;              // 1: refine every maximum (debug switch "hnr_exhaustive"; identical results)
     // results
     double* sel_f;             // [frames] frequency of the chosen candidate (0 = voiceless)
     double* sel_s;             // [frames] strength of the chosen candidate / HNR: best r (NaN when voiceless)
@@ -98,6 +95,10 @@ struct Clips {
     int* cls;                  // [n] speaker class (CLS_*)
     uint32_t* status;          // [n]
     double* feat;              // [n*25]
+    long long total_samples;   // samples of the whole chunk behind pcm (bounds of the bulk copies)
+    const double2* twb512;     // [32][16]  exp(-2 pi i j q / 512): pass twiddles of the warp-resident transforms (fftreg.cuh)
+    const double2* twb1024;    // [32][32]  exp(-2 pi i j q / 1024)
+    int legacy_fft;            // 1: CTA-per-frame shared-memory transforms (development switch "legacy_fft")
 };
 
 // Glottal pulse sets (PointProcess) of one pitch pass
@@ -162,6 +163,8 @@ void launch_pitch_grid(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
 void launch_pitch_refine(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);
 void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);
+bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw, const double2* twb512, const double2* twb1024,
+                           long long total_elems, int max_frames_hint, cudaStream_t s);      // k_acw.cu
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
 void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones

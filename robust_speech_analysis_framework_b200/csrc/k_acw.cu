@@ -1,0 +1,581 @@
+// k_acw.cu -- autocorrelation pitch frames (Sound_into_PitchFrame, AC_HANNING branch of fon/Sound_to_Pitch.cpp), the
+// arithmetic behind to_pitch_ac at mshds_extractor.py:104 (M = 2048 stays on k_pitch_frames), :143, :178 / :355, :241, :270.
+//
+// B200 design (round 2; replaces the CTA-per-frame shared-memory FFT of k_pitch_frames<false> for M <= 1024):
+//
+//   * ONE WARP PER FRAME (half a warp for the 1024-point transforms of high-pitched speakers: two frames per warp).  The
+//     packed real FFT, the power spectrum and the inverse FFT live in registers (fftreg.cuh): 32 complex points per lane,
+//     one XOR-swizzled trip through shared memory per transform, the real-FFT untangle done with warp shuffles.  No
+//     __syncthreads() inside a frame; the only block barriers are the two per staged span.
+//   * SAMPLES ARRIVE BY TMA.  A CTA turn is 8 consecutive frames of one recording = one contiguous span of
+//     W + 7 hops samples (int16: ~3 KB).  Thread 0 fetches the span of the NEXT turn with cp.async.bulk (1-D bulk tensor
+//     copy, completion on an mbarrier) into the other half of a double buffer while the four warps work on the current
+//     one; local mean, window multiply and local peak of all 8 frames read the staged span instead of going through L1
+//     eight times.  Turns are handed out by an atomic counter (frames of low-pitched speakers cost twice as much).
+//   * the candidate search (maxima, parabolic frequency, sinc-30 strength, Praat's slot rule) runs warp-synchronously on
+//     the correlation the warp just produced (rs0 aliases the dead exchange buffer).
+//
+// Results are the same r[lag] = ac[lag] / (ac[0] windowR[lag]) as before up to the rounding of a different (exact) FFT
+// operation order; everything downstream (refinement queue, candidates, path finder) is unchanged.
+#include <cstdio>
+#include <cstdlib>
+#include "internal.h"
+#include "common.cuh"
+#include "fft.cuh"
+#include "num.cuh"
+#include "fftreg.cuh"
+
+#define ACW_WARPS 4
+#define ACW_NT (32 * ACW_WARPS)
+#define ACW_TURN 8
+#define ACW_XCH_BYTES (1024 * 16)          // exchange buffer per warp: 1024 complex doubles
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier helpers
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ staged span
+struct AcwSeg {               // one staged segment: consecutive frames of ONE clip (written by thread 0, read by all)
+    int f0, n;                // first flat frame index, frames (0 = no more work)
+    int clip, cls, k0;        // clip, speaker class, index of the first frame inside the clip
+    long long base;           // chunk offset of the clip's first sample
+    long long sA;             // 1-based clip sample index of staged element 0
+    int count;                // staged elements
+    int shift;                // staged element e sits `shift + e` elements into the stage buffer (16-byte alignment of the source)
+    int head, tail0;          // elements [0, head) and [tail0, count) are NOT covered by the bulk copy: copied by threads
+    int tma_bytes;            // 0 = nothing was issued (barrier not armed)
+};
+
+struct AcwParams {
+    const unsigned char* pcm_bytes;   // chunk samples as bytes
+    long long total_elems;            // samples in the chunk
+    int esz;                          // 2 (int16) or 8 (float64 behind the resampling front-end)
+    int stage_bytes;                  // bytes of ONE stage buffer
+    const double2* twb512;            // [32][16] exp(-2 pi i j q / 512)
+    const double2* twb1024;           // [32][32] exp(-2 pi i j q / 1024)
+};
+
+__device__ __forceinline__ double staged(const unsigned char* st, int esz, int e /* element index incl. shift */) {
+    return esz == 2 ? (double)((const short*)st)[e] * (1.0 / 32768.0) : ((const double*)st)[e];
+}
+
+// thread 0: next segment of work -> *sg, and its bulk copy into `stage` (armed on `bar`)
+__device__ __forceinline__ void acw_fetch(const Clips& c, const PitchPass& p, const AcwParams& A, int total, int nturn,
+                                          int& cur_f, int& turn_end, AcwSeg* sg, unsigned char* stage, unsigned long long* bar) {
+    if (cur_f >= turn_end) {
+        const int turn = atomicAdd(p.turn_counter, 1);
+        if (turn >= nturn) { sg->n = 0; sg->tma_bytes = 0; return; }
+        cur_f = turn * ACW_TURN;
+        turn_end = cur_f + ACW_TURN < total ? cur_f + ACW_TURN : total;
+    }
+    const int clip = find_segment(p.fstart, c.n, cur_f);
+    const int clip_end = p.fstart[clip + 1];
+    const int f1 = turn_end < clip_end ? turn_end : clip_end;
+    const int cls = c.cls[clip];
+    const PitchCfg& g = p.cfg[cls];
+    sg->f0 = cur_f; sg->n = f1 - cur_f; sg->clip = clip; sg->cls = cls; sg->k0 = cur_f - p.fstart[clip];
+    const long long base = c.off[clip], nx = c.off[clip + 1] - base;
+    sg->base = base;
+    // samples the frames k0 .. k0 + n - 1 touch: window [right - half, left + half] and local-mean range [right - period, left + period]
+    const double x1 = c.x1[clip];
+    const double tA = p.t1[clip] + (double)sg->k0 * g.dt, tB = p.t1[clip] + (double)(sg->k0 + sg->n - 1) * g.dt;
+    const long long leftA = x_to_low(x1, c.dx, tA), leftB = x_to_low(x1, c.dx, tB);
+    const int reach = g.halfnsamp_window > g.nsamp_period ? g.halfnsamp_window : g.nsamp_period;
+    long long sA = leftA + 1 - reach, sB = leftB + reach;
+    if (sA < 1) sA = 1;
+    if (sB > nx) sB = nx;
+    if (sB < sA) sB = sA - 1;
+    sg->sA = sA;
+    const int count = (int)(sB - sA + 1);
+    sg->count = count;
+    const int esz = A.esz;
+    const long long gA = base + sA - 1;                                   // chunk element index of staged element 0
+    const unsigned long long addr = (unsigned long long)(A.pcm_bytes + gA * esz);
+    const unsigned long long a0 = addr & ~15ull;
+    sg->shift = (int)((addr - a0) / esz);
+    unsigned long long a1 = (addr + (unsigned long long)count * esz + 15ull) & ~15ull;
+    // bytes the bulk copy may touch: whole 16-byte units inside the chunk's sample array
+    const unsigned long long lo = ((unsigned long long)A.pcm_bytes + 15ull) & ~15ull;
+    const unsigned long long hi = ((unsigned long long)A.pcm_bytes + (unsigned long long)A.total_elems * esz) & ~15ull;
+    unsigned long long t0 = a0 > lo ? a0 : lo, t1 = a1 < hi ? a1 : hi;
+    if (t1 > a0 + (unsigned long long)A.stage_bytes) t1 = a0 + (unsigned long long)A.stage_bytes;    // (cannot happen: stage sized for the worst span)
+    int head = 0, tail0 = count, bytes = 0;
+    if (count > 0 && t1 > t0) {
+        bytes = (int)(t1 - t0);
+        head = t0 > addr ? (int)((t0 - addr + esz - 1) / esz) : 0;
+        tail0 = (int)((t1 - addr) / esz);
+        if (tail0 > count) tail0 = count;
+        mbar_expect_tx(bar, (unsigned)bytes);
+        tma_load_1d(stage + (t0 - a0), (const void*)t0, (unsigned)bytes, bar);
+    } else {
+        head = count; tail0 = count;             // everything by threads
+    }
+    sg->head = head; sg->tail0 = tail0; sg->tma_bytes = bytes;
+    cur_f = f1;
+}
+
+// ------------------------------------------------------------------------------------------------ candidates (warp)
+struct WCand {
+    double* rs0;        // [2Bs+1] symmetric correlation, rs0[Bs + i] = r[i]
+    double* pk_f; double* pk_s; double* pk_key; int* pk_lag;
+    unsigned* masks;
+    double* cf; double* cs; double* ckey; int* cimax;           // [16] 1-based slots, first analysis
+    double* cf2; double* cs2; double* ckey2; int* cimax2;       // second analysis (dual voicing threshold)
+    int* s_int;
+    int pkcap;
+};
+
+__device__ __forceinline__ int w_insert_candidates(const PitchCfg& g, const WCand& S, const double* r, int nmax, double thr,
+                                                   double* cf, double* cs, double* ckey, int* cimax) {
+    int ncand = 1;
+    cf[1] = 0.0; cs[1] = 0.0; cimax[1] = 0;
+    for (int m = 0; m < nmax; m++) {
+        if (!(r[S.pk_lag[m]] > thr)) continue;
+        int place = 0;
+        if (ncand < g.maxn) {
+            place = ++ncand;
+        } else {
+            double weakest = 2;
+            for (int iweak = 2; iweak <= g.maxn; iweak++) {
+                double ls = ckey[iweak];
+                if (ls < weakest) { weakest = ls; place = iweak; }
+            }
+            if (S.pk_key[m] <= weakest) place = 0;
+        }
+        if (place) { cf[place] = S.pk_f[m]; cs[place] = S.pk_s[m]; ckey[place] = S.pk_key[m]; cimax[place] = S.pk_lag[m]; }
+    }
+    return ncand;
+}
+
+// Sound_into_PitchFrame first pass for one frame, executed by one warp (same arithmetic as find_candidates in k_pitch.cu).
+// Returns ncand | ncand2 << 8.
+__device__ __forceinline__ int w_find_candidates(const PitchCfg& g, double dx, const WCand& S, int B, int Bs,
+                                                 const double2* __restrict__ tw, double vt2) {
+    const int lane = threadIdx.x & 31;
+    const double thr1 = 0.5 * g.vt;
+    const double thr = (vt2 >= 0.0 && 0.5 * vt2 < thr1) ? 0.5 * vt2 : thr1;
+    const int upper = g.maximumLag < B ? g.maximumLag : B;      // i < maximumLag && i < brent_ixmax
+    int nlag = upper - 2;
+    if (nlag < 0) nlag = 0;
+    const int nrounds = (nlag + 31) / 32;
+    const double* r = S.rs0 + Bs;
+    int n = 0;
+    for (int round = 0; round < nrounds; round++) {
+        const int i = 2 + round * 32 + lane;
+        bool flag = false;
+        if (i < 2 + nlag) {
+            const double ri = r[i];
+            flag = ri > thr && ri > r[i - 1] && ri >= r[i + 1];
+        }
+        const unsigned m = __ballot_sync(FULL_MASK, flag);
+        // ordered compaction: every lane knows the running count
+        if (flag) {
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            if (pos < S.pkcap) S.pk_lag[pos] = i;
+        }
+        n += __popc(m);
+    }
+    if (n > S.pkcap) n = S.pkcap;
+    __syncwarp();
+    const int nmax = n;
+    const double* y1 = S.rs0 - 1;
+    const int ny = 2 * Bs + 1;
+    for (int m = 0; m < nmax; m++) {
+        const int i = S.pk_lag[m];
+        const double dr = 0.5 * (r[i + 1] - r[i - 1]), d2r = 2 * r[i] - r[i - 1] - r[i + 1];
+        const double freq = 1.0 / dx / (i + dr / d2r);
+        const double x = 1.0 / dx / freq + (double)(Bs + 1);
+        double strength = sinc_interp_warp(y1, ny, x, 30, lane, tw);
+        if (strength > 1.0) strength = 1.0 / strength;
+        if (lane == 0) {
+            S.pk_f[m] = freq;
+            S.pk_s[m] = strength;
+            S.pk_key[m] = strength - g.octave_cost * log2(g.floor_hz / freq);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) S.s_int[1] = w_insert_candidates(g, S, r, nmax, thr1, S.cf, S.cs, S.ckey, S.cimax);
+    if (lane == 1 && vt2 >= 0.0) S.s_int[2] = w_insert_candidates(g, S, r, nmax, 0.5 * vt2, S.cf2, S.cs2, S.ckey2, S.cimax2);
+    __syncwarp();
+    return S.s_int[1] | ((vt2 >= 0.0 ? S.s_int[2] : 0) << 8);
+}
+
+// ------------------------------------------------------------------------------------------------ transforms (warp)
+// One transform of the frame(s) of this warp.  `a` holds pass-A input in logical order (element k = z[j + L k]); on return
+// `a` holds logical element r (k = j + L r) of the result at a[fr_slot<L>(r)].  xch: this lane's frame exchange region.
+template <int L, int SIGN>
+__device__ __forceinline__ void acw_transform(double2 (&a)[32], double2* xch, int j, const double2* __restrict__ twb) {
+    fr_fft<32, SIGN>(a);
+    fr_static_for<0, 32>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        double2 v = a[fr_brev(q, 5)];
+        if constexpr (q > 0) {
+            double2 t = __ldg(twb + q * L + j);                 // exp(-2 pi i j q / M); conjugate for the inverse
+            if (SIGN > 0) t.y = -t.y;
+            v = fr_mul(v, t);
+        }
+        xch[q * L + (j ^ (q & 7))] = v;
+    });
+    __syncwarp();
+    if constexpr (L == 32) {
+        const int q = j;
+        fr_static_for<0, 32>([&](auto jc) {
+            constexpr int jj = decltype(jc)::value;
+            a[jj] = xch[q * 32 + (jj ^ (q & 7))];
+        });
+        fr_fft<32, SIGN>(a);
+    } else {
+        fr_static_for<0, 32>([&](auto sc) {
+            constexpr int sl = decltype(sc)::value, h = sl >> 4, jj = sl & 15;
+            const int q = j + 16 * h;
+            a[sl] = xch[q * 16 + (jj ^ (q & 7))];
+        });
+        fr_fft<16, SIGN>(&a[0]);
+        fr_fft<16, SIGN>(&a[16]);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double2 shfl2(double2 v, int src) {
+    return make_double2(__shfl_sync(FULL_MASK, v.x, src), __shfl_sync(FULL_MASK, v.y, src));
+}
+
+// power spectrum of the packed real transform, in place: Z (slots) -> Y (slots), the packed input of the inverse transform
+template <int L>
+__device__ __forceinline__ void acw_untangle(double2 (&e)[32], int lane, int j, double2 wj /* exp(-2 pi i j / N) */) {
+    const int grp = lane & ~(L - 1);
+    const int pl = grp | ((L - j) & (L - 1));
+    const bool j0 = j == 0;
+    fr_static_for<0, 16>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const double2 mine = e[fr_slot<L>(r)];
+        double2 theirs = shfl2(e[fr_slot<L>(31 - r)], pl);
+        if constexpr (r >= 1) { if (j0) theirs = e[fr_slot<L>(32 - r)]; }
+        const double2 wk = fr_mul(wj, make_double2(fr_cos64(r), -fr_sin64(r)));      // exp(-2 pi i (j + L r) / N)
+        double2 yk, ymk;
+        double pk, pmk;
+        fr_pair(mine, theirs, wk, &yk, &ymk, &pk, &pmk);
+        if constexpr (r == 0) {
+            if (j0) {
+                const double p0 = (mine.x + mine.y) * (mine.x + mine.y), pM = (mine.x - mine.y) * (mine.x - mine.y);
+                yk = make_double2(p0 + pM, p0 - pM);
+            }
+        }
+        const double2 ret = shfl2(ymk, pl);
+        e[fr_slot<L>(r)] = yk;
+        if (!j0) e[fr_slot<L>(31 - r)] = ret;
+        if constexpr (r >= 1) { if (j0) e[fr_slot<L>(32 - r)] = ymk; }
+    });
+    {   // lane j = 0: bin M/2 pairs with itself
+        const double2 z = e[fr_slot<L>(16)];
+        double2 yk, ymk;
+        double pk, pmk;
+        fr_pair(z, z, make_double2(fr_cos64(16), -fr_sin64(16)), &yk, &ymk, &pk, &pmk);
+        if (j0) e[fr_slot<L>(16)] = yk;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the frame, per lane
+// Everything one lane does for the frame it belongs to.  L lanes per frame; `active` = this lane's frame exists.
+template <int L>
+__device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const AcwParams& A, const AcwSeg& sg,
+                                          const unsigned char* st, unsigned char* xw /* warp exchange region */, int fi,
+                                          bool active, const double2* __restrict__ tw) {
+    const int lane = threadIdx.x & 31, j = lane & (L - 1), gidx = lane / L;
+    const unsigned gmask = L == 32 ? FULL_MASK : (0xffffu << (16 * gidx));
+    const PitchCfg& g = p.cfg[sg.cls];
+    const double dx = c.dx;
+    const int W = g.nsamp_window, B = g.brent_ixmax;
+    const int Bs = B < g.maximumLag + 32 ? B : g.maximumLag + 32;
+    const int esz = A.esz;
+    unsigned char* xf = xw + (size_t)gidx * (ACW_XCH_BYTES / (32 / L));           // this frame's exchange region
+    double2* xch = (double2*)xf;
+    const double2* twb = L == 32 ? A.twb1024 : A.twb512;
+
+    const double x1 = c.x1[sg.clip];
+    const double t = p.t1[sg.clip] + (double)(sg.k0 + fi) * g.dt;
+    const long long leftSample = x_to_low(x1, dx, t), rightSample = leftSample + 1;
+    // staged element index (incl. alignment shift) of 1-based clip sample s:  s - sA + shift
+    const int eoff = (int)(-sg.sA) + sg.shift;
+
+    // ---- local mean over one longest period to both sides
+    double acc = 0.0;
+    if (active) {
+        const long long s0 = rightSample - g.nsamp_period, s1 = leftSample + g.nsamp_period;
+        for (long long i = s0 + j; i <= s1; i += L) acc += staged(st, esz, (int)i + eoff);
+    }
+    const double localMean = group_sum(acc, gmask, L) / (double)(2 * g.nsamp_period);
+
+    // ---- frame (s - mean) * Hanning window into registers, packed z[n] = x[2n] + i x[2n+1], n = j + L k; local peak
+    double2 a[32];
+    double lp = 0.0;
+    {
+        const long long startSample = rightSample - g.halfnsamp_window;
+        int pk0 = g.halfnsamp_window + 1 - g.halfnsamp_period; if (pk0 < 1) pk0 = 1;
+        int pk1 = g.halfnsamp_window + g.halfnsamp_period; if (pk1 > W) pk1 = W;
+        const int ebase = (int)startSample + eoff;                        // staged element of frame sample m = 0 (1-based clip sample startSample)
+        fr_static_for<0, 32>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const int m = 2 * (j + L * k);
+            double v0 = 0.0, v1 = 0.0;
+            if (active && m < W) {                                        // W is even: m + 1 < W as well
+                const double2 w = __ldg((const double2*)(g.window + m));
+                v0 = (staged(st, esz, ebase + m) - localMean) * w.x;
+                v1 = (staged(st, esz, ebase + m + 1) - localMean) * w.y;
+                if (m + 1 >= pk0 && m + 1 <= pk1) lp = fmax(lp, fabs(v0));
+                if (m + 2 >= pk0 && m + 2 <= pk1) lp = fmax(lp, fabs(v1));
+            }
+            a[k] = make_double2(v0, v1);
+        });
+    }
+    for (int o = L >> 1; o > 0; o >>= 1) lp = fmax(lp, __shfl_xor_sync(gmask, lp, o));
+    const double localPeak = lp;
+    const double globalPeak = active ? c.gpeak[sg.clip] : 1.0;
+    const double intensity = localPeak > globalPeak ? 1.0 : localPeak / globalPeak;
+
+    // ---- autocorrelation: forward packed FFT, power spectrum, inverse
+    acw_transform<L, -1>(a, xch, j, twb);
+    {
+        const int N = 64 * L;                                             // real transform length
+        const double2 wj = __ldg(tw + j * (TW_N / N));
+        acw_untangle<L>(a, lane, j, wj);
+    }
+    {
+        double2 b[32];
+        fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; b[r] = a[fr_slot<L>(r)]; });
+        acw_transform<L, +1>(b, xch, j, twb);
+        fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; a[r] = b[r]; });
+    }
+    // a[fr_slot(r)] = (ac[2n], ac[2n+1]), n = j + L r.  Normalise and publish r[0..B]: correlation row (global) + rs0 (shared)
+    const double ac0 = __shfl_sync(FULL_MASK, a[fr_slot<L>(0)].x, lane & ~(L - 1));
+    WCand S;
+    {
+        unsigned char* q = xf;
+        S.rs0 = (double*)q; q += ((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15;
+        int pkcap = g.maximumLag / 2 + 2;
+        if (pkcap > 320) pkcap = 320;
+        S.pkcap = pkcap;
+        S.pk_f = (double*)q; q += (size_t)pkcap * 8;
+        S.pk_s = (double*)q; q += (size_t)pkcap * 8;
+        S.pk_key = (double*)q; q += (size_t)pkcap * 8;
+        S.cf = (double*)q; q += 16 * 8; S.cs = (double*)q; q += 16 * 8; S.ckey = (double*)q; q += 16 * 8;
+        S.cf2 = (double*)q; q += 16 * 8; S.cs2 = (double*)q; q += 16 * 8; S.ckey2 = (double*)q; q += 16 * 8;
+        S.pk_lag = (int*)q; q += ((size_t)pkcap * 4 + 15) & ~(size_t)15;
+        S.cimax = (int*)q; q += 16 * 4; S.cimax2 = (int*)q; q += 16 * 4;
+        S.s_int = (int*)q; q += 16;
+        S.masks = (unsigned*)q;
+    }
+    const int f = sg.f0 + fi;
+    double* rrow = p.rbuf + (size_t)(active ? f : 0) * p.rstride;
+    if (active) {
+        fr_static_for<0, 32>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const int i0 = 2 * (j + L * r);
+            if (i0 <= B) {
+                const double2 v = a[fr_slot<L>(r)];
+                const double r0 = i0 == 0 ? 1.0 : v.x / (ac0 * __ldg(g.windowR + i0));
+                rrow[i0] = r0;
+                if (i0 <= Bs) { S.rs0[Bs + i0] = r0; S.rs0[Bs - i0] = r0; }
+                if (i0 + 1 <= B) {
+                    const double r1 = v.y / (ac0 * __ldg(g.windowR + i0 + 1));
+                    rrow[i0 + 1] = r1;
+                    if (i0 + 1 <= Bs) { S.rs0[Bs + i0 + 1] = r1; S.rs0[Bs - i0 - 1] = r1; }
+                }
+            }
+        });
+    }
+    __syncwarp();
+
+    // ---- candidates: the whole warp serves one frame at a time
+    const bool dual = p.dual_cand_f != nullptr;
+    for (int gsel = 0; gsel < 32 / L; gsel++) {
+        const int src = gsel * L;                                          // first lane of that frame's group
+        const bool act = __shfl_sync(FULL_MASK, (int)active, src) != 0;
+        if (!act) continue;
+        const double lpk = __shfl_sync(FULL_MASK, localPeak, src);
+        const double inten = __shfl_sync(FULL_MASK, intensity, src);
+        const int ff = __shfl_sync(FULL_MASK, f, src);
+        // pointers of that frame's scratch (same layout, other region)
+        WCand T = S;
+        if (L != 32) {
+            const long long delta = (long long)(gsel - gidx) * (ACW_XCH_BYTES / (32 / L));
+            T.rs0 = (double*)((unsigned char*)S.rs0 + delta); T.pk_f = (double*)((unsigned char*)S.pk_f + delta);
+            T.pk_s = (double*)((unsigned char*)S.pk_s + delta); T.pk_key = (double*)((unsigned char*)S.pk_key + delta);
+            T.cf = (double*)((unsigned char*)S.cf + delta); T.cs = (double*)((unsigned char*)S.cs + delta);
+            T.ckey = (double*)((unsigned char*)S.ckey + delta); T.cf2 = (double*)((unsigned char*)S.cf2 + delta);
+            T.cs2 = (double*)((unsigned char*)S.cs2 + delta); T.ckey2 = (double*)((unsigned char*)S.ckey2 + delta);
+            T.pk_lag = (int*)((unsigned char*)S.pk_lag + delta); T.cimax = (int*)((unsigned char*)S.cimax + delta);
+            T.cimax2 = (int*)((unsigned char*)S.cimax2 + delta); T.s_int = (int*)((unsigned char*)S.s_int + delta);
+            T.masks = (unsigned*)((unsigned char*)S.masks + delta);
+        }
+        int ncand = 1, ncand2 = 1;
+        if (lpk != 0.0) {
+            const int nn = w_find_candidates(g, dx, T, B, Bs, tw, dual ? p.dual_vt : -1.0);
+            ncand = nn & 0xff;
+            if (dual) ncand2 = nn >> 8;
+        } else {
+            if (lane == 0) { T.cf[1] = 0.0; T.cs[1] = 0.0; T.cimax[1] = 0; T.cf2[1] = 0.0; T.cs2[1] = 0.0; T.cimax2[1] = 0; }
+            __syncwarp();
+        }
+        // candidates leave the SM (lanes 0..14: the analysis itself, lanes 16..30: the dual one); see k_pitch_frames for the
+        // exactness argument of the two skip rules
+        const int set = lane >> 4, ctid = lane & 15;
+        if (ctid < MAXCAND && (set == 0 || dual)) {
+            const double vt = set == 0 ? g.vt : p.dual_vt;
+            double uvs = g.sil <= 0 ? 0.0 : 2.0 - inten / (g.sil / (1.0 + vt));
+            uvs = vt + (uvs > 0 ? uvs : 0);
+            const bool frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
+            const int nc = set == 0 ? ncand : ncand2;
+            const double* scf = set == 0 ? T.cf : T.cf2;
+            const double* scs = set == 0 ? T.cs : T.cs2;
+            const int* sci = set == 0 ? T.cimax : T.cimax2;
+            const int ci = ctid + 1;
+            double fr = 0.0, stn = 0.0;
+            int im = 0;
+            if (ci <= nc) { fr = scf[ci]; stn = scs[ci]; im = sci[ci]; }
+            const size_t o2 = (size_t)ff * MAXCAND + ctid;
+            if (set == 0) { p.cand_f[o2] = fr; p.cand_s[o2] = stn; p.cand_imax[o2] = (unsigned short)im; }
+            else { p.dual_cand_f[o2] = fr; p.dual_cand_s[o2] = stn; p.dual_cand_imax[o2] = (unsigned short)im; }
+            const bool live = ci >= 2 && ci <= nc && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
+            if (live) {
+                if (set == 0) { int slot = atomicAdd(p.qcount, 1); p.queue[slot] = ff * 16 + ctid; }
+                else { int slot = atomicAdd(p.dual_qcount, 1); p.dual_queue[slot] = ff * 16 + ctid; }
+            }
+        }
+        if (lane == 0) {
+            p.ncand[ff] = (uint8_t)ncand; p.inten[ff] = inten;
+            if (dual) { p.dual_ncand[ff] = (uint8_t)ncand2; p.dual_inten[ff] = inten; }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
+                                                             const __grid_constant__ AcwParams A, const double2* __restrict__ tw) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* xch_all = smem;                                        // ACW_WARPS x 16 KB
+    unsigned char* stage0 = smem + ACW_WARPS * ACW_XCH_BYTES;             // 2 x stage_bytes
+    __shared__ __align__(8) unsigned long long bars[2];
+    __shared__ AcwSeg segs[2];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int total = p.fstart[c.n];
+    const int nturn = (total + ACW_TURN - 1) / ACW_TURN;
+    int cur_f = 0, turn_end = 0;                                          // thread 0's position in its current turn
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[0], stage0, &bars[0]);
+    unsigned phase0 = 0, phase1 = 0;
+    int buf = 0;
+    for (;;) {
+        __syncthreads();                      // segs[buf] is published; every warp is done with the other stage buffer
+        const AcwSeg& sg = segs[buf];            // stays valid for this iteration: thread 0 only writes segs[buf ^ 1]
+        if (sg.n == 0) break;
+        unsigned char* st = stage0 + (size_t)buf * A.stage_bytes;
+        if (tid == 0)                         // prefetch the next segment while this one is processed
+            acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[buf ^ 1], stage0 + (size_t)(buf ^ 1) * A.stage_bytes, &bars[buf ^ 1]);
+        // elements the bulk copy could not cover (unaligned ends of the chunk): plain loads
+        if (sg.head > 0 || sg.tail0 < sg.count) {
+            const long long g0 = sg.base + sg.sA - 1;
+            for (int e = tid; e < sg.count; e += ACW_NT) {
+                if (e >= sg.head && e < sg.tail0) continue;
+                if (A.esz == 2) ((short*)st)[sg.shift + e] = ((const short*)A.pcm_bytes)[g0 + e];
+                else ((double*)st)[sg.shift + e] = ((const double*)A.pcm_bytes)[g0 + e];
+            }
+            __syncthreads();
+        }
+        if (sg.tma_bytes > 0) {
+            mbar_wait(&bars[buf], buf == 0 ? phase0 : phase1);
+            if (buf == 0) phase0 ^= 1; else phase1 ^= 1;
+        }
+        unsigned char* xw = xch_all + (size_t)warp * ACW_XCH_BYTES;
+        const int M = p.cfg[sg.cls].M;
+        if (M == 1024) {
+            for (int fr0 = 0; fr0 < sg.n; fr0 += ACW_WARPS) {
+                const int fi = fr0 + warp;
+                if (fi < sg.n) acw_frame<32>(c, p, A, sg, st, xw, fi, true, tw);
+            }
+        } else {
+            const int lane = tid & 31;
+            for (int fr0 = 0; fr0 < sg.n; fr0 += 2 * ACW_WARPS) {
+                const int fi = fr0 + 2 * warp + (lane >> 4);
+                if (fr0 + 2 * warp < sg.n)          // warp-uniform: at least the first of the two frames exists
+                    acw_frame<16>(c, p, A, sg, st, xw, fi, fi < sg.n, tw);
+            }
+        }
+        buf ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+// returns false when this pass cannot run on the warp kernel (transform larger than 1024 points, scratch does not fit)
+bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw, const double2* twb512, const double2* twb1024,
+                           long long total_elems, int max_frames_hint, cudaStream_t s) {
+    int span = 0;
+    for (int k = 0; k < 3; k++) {
+        const PitchCfg& g = p.cfg[k];
+        if (g.method != 0 || (g.M != 512 && g.M != 1024)) return false;
+        const int Bs = g.brent_ixmax < g.maximumLag + 32 ? g.brent_ixmax : g.maximumLag + 32;
+        int pkcap = g.maximumLag / 2 + 2;
+        if (pkcap > 320) pkcap = 320;
+        const size_t need = (((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15) + (size_t)pkcap * 24 + 6 * 128 + (((size_t)pkcap * 4 + 15) & ~(size_t)15) +
+                            2 * 64 + 16 + 64;
+        if (need > (size_t)ACW_XCH_BYTES / (g.M == 1024 ? 1 : 2)) return false;
+        const int reach = g.halfnsamp_window > g.nsamp_period ? g.halfnsamp_window : g.nsamp_period;
+        const int hop = (int)ceil(g.dt / c.dx) + 1;
+        const int sp = 2 * reach + 2 + (ACW_TURN - 1) * hop + 16;
+        if (sp > span) span = sp;
+    }
+    AcwParams A;
+    A.esz = c.pcm.p64 ? 8 : 2;
+    A.pcm_bytes = c.pcm.p64 ? (const unsigned char*)c.pcm.p64 : (const unsigned char*)c.pcm.p16;
+    A.total_elems = total_elems;
+    A.stage_bytes = (span * A.esz + 32 + 127) & ~127;
+    A.twb512 = twb512; A.twb1024 = twb1024;
+    const size_t smem = (size_t)ACW_WARPS * ACW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
+    if (smem > 110 * 1024) return false;
+    cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
+    cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
+    if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
+    cudaFuncSetAttribute(k_ac_frames_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_ac_frames_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ac_frames_w, ACW_NT, smem);
+    if (occ < 1) occ = 1;
+    int grid = sm_count() * occ;
+    const int nturn = (max_frames_hint + ACW_TURN - 1) / ACW_TURN;
+    if (max_frames_hint > 0 && grid > nturn) grid = nturn;
+    if (grid < 1) grid = 1;
+    k_ac_frames_w<<<grid, ACW_NT, smem, s>>>(c, p, A, tw);
+    return true;
+}

@@ -50,6 +50,9 @@ struct mshds_handle {
     long long chunk_samples = 1LL << 27;
     // persistent tables
     double2* tw = nullptr;
+    double2* twb512 = nullptr;          // pass twiddles of the warp-resident transforms (fftreg.cuh), [32][M / 32]
+    double2* twb1024 = nullptr;
+    int legacy_fft = 0;
     std::map<int, std::pair<double*, double*>> ac_windows;      // nsamp_window -> (window, windowR)
     std::map<long long, double*> kaiser;                        // key -> window
     std::map<int, double*> gauss_spec;
@@ -72,7 +75,6 @@ struct mshds_handle {
     char* agg_buf = nullptr;
     size_t agg_cap = 0;
     // development / test switches (mshds_set_option)
-    int hnr_exhaustive = 0;
     int nvtx = 0;
     // arena
     char* arena = nullptr;
@@ -576,6 +578,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     c.x1 = d_x1; c.xmax = d_xmax;
     c.cls = take<int>(h, n);
     c.status = d_status; c.feat = d_feat;
+    c.total_samples = off_host[n]; c.twb512 = h->twb512; c.twb1024 = h->twb1024; c.legacy_fft = h->legacy_fft;
     void* stat_scratch = arena_take(h, (size_t)n * 16);
 
     // ---- pitch pass configurations (parselmouth defaults unless mshds_extractor.py passes a value)
@@ -644,8 +647,6 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     hnr.queue64 = take<unsigned long long>(h, hnr.q64_cap);
     hnr.qcount64 = take<unsigned long long>(h, 1);
     hnr.best_bits = take<unsigned long long>(h, fub5);
-    hnr.hnr_top = take<unsigned long long>(h, fub5);
-    hnr.hnr_exhaustive = h->hnr_exhaustive;
     alloc_pitch_pass(h, &srp, n, fub20, cs_sr);
     alloc_pitch_pass(h, &ltp, n, fub75, cs_lt);
     alloc_pitch_pass(h, &ccp, n, fub5, cs_cc);
@@ -998,6 +999,20 @@ int mshds_create(int device, mshds_handle** out) {
         delete h;
         return MSHDS_ERR_CUDA;
     }
+    for (int M : {512, 1024}) {     // exp(-2 pi i j q / M), row q, L = M / 32 entries per row
+        const int L = M / 32;
+        std::vector<double> t((size_t)2 * M);
+        for (int q = 0; q < 32; q++)
+            for (int j = 0; j < L; j++) {
+                const double ang = 2.0 * MSHDS_PI * (double)(j * q % M) / (double)M;
+                t[2 * (size_t)(q * L + j)] = cos(ang);
+                t[2 * (size_t)(q * L + j) + 1] = -sin(ang);
+            }
+        double2** dst = M == 512 ? &h->twb512 : &h->twb1024;
+        if (cudaMalloc((void**)dst, sizeof(double) * t.size()) != cudaSuccess ||
+            cudaMemcpy(*dst, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    }
+    { const char* e = getenv("MSHDS_LEGACY_FFT"); h->legacy_fft = e && atoi(e); }
     *out = h;
     return MSHDS_OK;
 }
@@ -1015,6 +1030,8 @@ void mshds_destroy(mshds_handle* h) {
     cudaFree(h->lld_buf);
     cudaFree(h->agg_buf);
     cudaFree(h->tw);
+    cudaFree(h->twb512);
+    cudaFree(h->twb1024);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side) cudaStreamDestroy(h->side);
@@ -1040,7 +1057,7 @@ int mshds_reset_stream(mshds_handle* h) {
 int mshds_set_option(mshds_handle* h, const char* name, long long value) {
     if (!h || !name) return MSHDS_ERR_ARG;
     const std::string n(name);
-    if (n == "hnr_exhaustive") h->hnr_exhaustive = value != 0;
+    if (n == "legacy_fft") h->legacy_fft = value != 0;
     else if (n == "overlap") h->overlap = value != 0;
     else if (n == "nvtx") h->nvtx = value != 0;
     else { h->err = "unknown option: " + n; return MSHDS_ERR_ARG; }

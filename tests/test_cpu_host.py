@@ -414,3 +414,13 @@ def test_bench_row_comparison_flags_decision_flips():
     assert not r["parity_ok"] and r["decision_flips"] == 1 and r["columns_out_of_tolerance"] == [0]
     got = want.copy(); got[0, 5] = np.nan
     assert bench.compare_rows(got, want)["nan_mismatches"] == 1
+
+
+def test_register_fft_core_against_direct_dft(tmp_path):
+    """csrc/fftreg.cuh compiles for the host: the register FFTs, the pass-A / exchange / pass-B split and the shuffle untangle
+    (emulated lane by lane) reproduce a direct DFT / direct autocorrelation to rounding error."""
+    import subprocess
+    exe = str(tmp_path / "fftreg_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "fftreg_host_test.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr

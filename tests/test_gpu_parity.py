@@ -188,30 +188,27 @@ def test_caller_stream_orders_the_extraction_after_async_producers(ex):
         assert np.array_equal(d_st.cpu().numpy().astype(np.uint32), hst)
 
 
-def test_pruned_harmonicity_refinement_equals_the_exhaustive_one(ex, orc):
-    """k_hnr_refine skips correlation maxima that cannot be the frame's best; "hnr_exhaustive" refines them all.  The HNR
-    contour (and so the column) must be bit-identical -- on speech-like clips and on noise / tone mixtures whose correlation
-    has many comparable maxima."""
-    rng = np.random.default_rng(11)
-    pcm, off, clips = _batch([4.0, 3.00006, 5.0], start=120)
-    t = np.arange(48000) / 16000.0
-    noisy = (0.2 * np.sin(2 * np.pi * 140 * t) + 0.2 * np.sin(2 * np.pi * 287 * t + 1.0) + 0.1 * rng.normal(size=t.size))
-    clips = clips + [(noisy * 12000).astype(np.int16), (rng.normal(scale=3000.0, size=40000)).astype(np.int16)]
-    pcm = np.concatenate(clips)
-    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
-    pruned, _ = ex.extract_host(pcm, off)
-    contours_pruned = [ex.debug_fetch("hnr_r", c) for c in range(len(clips))]
-    ex.set_option("hnr_exhaustive", 1)
+def test_warp_resident_fft_frames_equal_the_shared_memory_ones(ex):
+    """Round 2 frame kernel (k_acw.cu: warp-per-frame register FFT, TMA-staged sample spans) against the round-1
+    CTA-per-frame shared-memory FFT kernel ("legacy_fft"): same correlation up to the rounding of another exact FFT
+    order, so identical voicing decisions and F0 contours to 1e-9 on both speaker classes and on odd-length clips."""
+    pcm, off, clips = _batch([4.0, 3.00006, 2.5, 5.1], start=60)
+    new, nst = ex.extract_host(pcm, off)
+    cn = {k: [ex.debug_fetch(k, c) for c in range(len(clips))] for k in ("pitch_wide_f", "pitch_main_f", "pitch_main_s", "pitch_ltas_f", "pitch_cpp_f")}
+    ex.set_option("legacy_fft", 1)
     try:
-        full, _ = ex.extract_host(pcm, off)
-        contours_full = [ex.debug_fetch("hnr_r", c) for c in range(len(clips))]
+        old, ost = ex.extract_host(pcm, off)
+        co = {k: [ex.debug_fetch(k, c) for c in range(len(clips))] for k in cn}
     finally:
-        ex.set_option("hnr_exhaustive", 0)
-    for a, b in zip(contours_pruned, contours_full):
-        assert np.array_equal(a, b, equal_nan=True)
-    assert np.array_equal(pruned, full, equal_nan=True)
-    want, _ = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
-    assert_features_close(pruned, want, "hnr pruning")
+        ex.set_option("legacy_fft", 0)
+    assert np.array_equal(nst, ost)
+    for k in cn:
+        for a, b in zip(cn[k], co[k]):
+            assert len(a) == len(b)
+            assert np.array_equal(a == 0, b == 0), f"{k}: voicing decisions differ"
+            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12, err_msg=k)
+    assert_features_close(new, old, "warp FFT vs legacy FFT")
+    assert np.array_equal(new[:, SPEECHRATE], old[:, SPEECHRATE])
 
 
 def _sharded_worker(rank, world, port, pcm, off, q):
