@@ -32,9 +32,11 @@ def functional_names(n_mfcc: int = 12, smooth_win: int = 3, delta_win: int = 2):
     return [f"{n}_amean" for n in names] + [f"{n}_stddev" for n in names]
 
 
-def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True, device: int = 0, **params):
+def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True, device: int = 0, max_batch_seconds: float = 7200.0,
+                            **params):
     """One row per recording: 'filename' + mean / stddev of every descriptor.  `params` override mshds_lld_params fields
-    (frame_size, frame_step, preemph, n_fft, n_mel, mel_lo, mel_hi, n_mfcc, cep_lifter)."""
+    (frame_size, frame_step, preemph, n_fft, n_mel, mel_lo, mel_hi, n_mfcc, cep_lifter).  Recordings are sent to the device in
+    batches of at most `max_batch_seconds` of audio per sampling rate (the library allocates for a whole call)."""
     import pandas as pd
 
     ex = _mx.get_extractor(device)
@@ -54,15 +56,28 @@ def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True
         except Exception as e:
             if verbose:
                 print(f"  - ERROR processing {filenames[i]}: {e}")
-    for fs, (idx, clips) in by_rate.items():
+    def run(idx, clips, fs):
         offs = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
         try:
             fun, _, _ = ex.lld_extract(np.concatenate(clips), offs, fs, **params)
             feats[np.asarray(idx)] = fun
         except Exception as e:
+            if len(idx) > 1:              # isolate the failure: one recording per call
+                for i, c in zip(idx, clips):
+                    run([i], [c], fs)
+                return
+            import warnings
+            warnings.warn(f"LLD extraction failed for '{filenames[idx[0]]}': {e}", RuntimeWarning)
             if verbose:
-                for i in idx:
-                    print(f"  - ERROR processing {filenames[i]}: {e}")
+                print(f"  - ERROR processing {filenames[idx[0]]}: {e}")
+
+    for fs, (idx, clips) in by_rate.items():
+        start, acc = 0, 0
+        for k, c in enumerate(clips):
+            acc += len(c)
+            if acc >= max_batch_seconds * fs or k == len(clips) - 1:
+                run(idx[start:k + 1], clips[start:k + 1], fs)
+                start, acc = k + 1, 0
     df = pd.DataFrame(feats, columns=cols)
     df.insert(0, "filename", filenames)
     return df

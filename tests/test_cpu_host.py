@@ -149,7 +149,8 @@ def test_dataframe_contract_matches_reference(tmp_path, monkeypatch, capsys):
     assert list(out["filename"]) == ["a.wav", "nope.wav", "b.wav", "c44.wav", "d8.wav"]
     assert out.iloc[0]["Speaking_Rate"] == 12000.0 and out.iloc[2]["Spectral_Kurtosis"] == -10000.0 + 24
     # one device call per sampling frequency, each told its rate (the library does resample(16000, 50), :418-419)
-    assert sorted(fake.calls) == [(8000, 1), (16000, 2), (44100, 1)]
+    # (the failing 8 kHz call is retried once, recording by recording)
+    assert sorted(fake.calls) == [(8000, 1), (8000, 1), (16000, 2), (44100, 1)]
     assert out.iloc[3]["Speaking_Rate"] == 12000.0
     assert out.iloc[1][mx.FEATURE_NAMES].isna().all() and out.iloc[4][mx.FEATURE_NAMES].isna().all()
     printed = capsys.readouterr().out
@@ -164,6 +165,57 @@ def test_dataframe_contract_matches_reference(tmp_path, monkeypatch, capsys):
     sys.path.insert(0, ROOT)
     from src.mshds_extractor import extract_mshds_features as shim
     assert shim is mx.extract_mshds_features
+
+
+def test_a_failing_device_call_only_costs_the_recording_that_causes_it(tmp_path, monkeypatch, capsys):
+    """Reference convention (:450-457): a file that cannot be processed gives ONE NaN row.  A batched device call that fails
+    is retried recording by recording, device errors are surfaced with warnings.warn even when verbose is off."""
+    import pandas as pd
+    from robust_speech_analysis_framework_b200 import mshds_extractor as mx
+
+    class Poisoned(_FakeExtractor):
+        def extract_host(self, pcm, offsets, sample_rate=16000):
+            if (np.asarray(pcm) == 666).any():
+                self.calls.append((int(sample_rate), len(offsets) - 1))
+                raise RuntimeError("simulated out of memory")
+            return super().extract_host(pcm, offsets, sample_rate)
+
+    fake = Poisoned()
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: fake)
+    paths = []
+    for k, v in enumerate((3, 666, 5)):
+        p = str(tmp_path / f"f{k}.wav")
+        _write_wav(p, np.full(1000, v, np.int16))
+        paths.append(p)
+    with pytest.warns(RuntimeWarning):
+        out = mx.extract_mshds_features(pd.DataFrame({"filepath": paths}), verbose=False)
+    assert capsys.readouterr().out == ""
+    assert out.iloc[0]["Speaking_Rate"] == 3000.0 and out.iloc[2]["Speaking_Rate"] == 5000.0
+    assert out.iloc[1][mx.FEATURE_NAMES].isna().all()
+    # several devices: LPT split, one thread + handle per device, rows back in input order
+    fake2 = _FakeExtractor()
+    seen = []
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: (seen.append(device), fake2)[1])
+    out2 = mx.extract_mshds_features(pd.DataFrame({"filepath": [paths[0], paths[2], paths[0]]}), verbose=False, devices=[0, 1])
+    assert list(out2["Speaking_Rate"]) == [3000.0, 5000.0, 3000.0] and {0, 1} <= set(seen)
+
+
+def test_float_wav_and_aiff_are_decoded_and_other_containers_are_a_distinct_error(tmp_path):
+    from scipy.io import wavfile
+    from robust_speech_analysis_framework_b200.mshds_extractor import AudioLoadError, read_wav_mono
+    x = (0.25 * np.sin(np.arange(800) * 0.1)).astype(np.float32)
+    p = str(tmp_path / "f32.wav")
+    wavfile.write(p, 16000, x)                                   # IEEE-float WAV: stdlib wave refuses it
+    y, fs = read_wav_mono(p)
+    assert fs == 16000 and y.dtype == np.float64 and np.array_equal(y, x.astype(np.float64))
+    st = np.stack([x, -x], axis=1)
+    wavfile.write(p, 22050, st)
+    y, fs = read_wav_mono(p)
+    assert fs == 22050 and np.allclose(y, 0.0)                   # convert_to_mono averages the channels (:416-417)
+    q = str(tmp_path / "x.flac")
+    open(q, "wb").write(b"fLaC" + bytes(64))
+    with pytest.raises(AudioLoadError, match="FLAC"):
+        read_wav_mono(q)
 
 
 def test_lpt_sharding_is_a_partition_and_balanced():
