@@ -120,6 +120,23 @@ FR_HD constexpr int fr_slot(int r) { return L == 32 ? fr_brev(r, 5) : 16 * (r & 
 template <int L>
 FR_HD constexpr int fr_xch(int q, int j) { return q * L + (j ^ (q & 7)); }
 
+// Real-input untangle split in two: the powers |X[k]|^2, |X[M-k]|^2 of a bin pair of the packed transform ...
+FR_HD void fr_pair_powers(double2 zk, double2 zmk, double2 wk, double* pk_out, double* pmk_out) {
+    const double ex = 0.5 * (zk.x + zmk.x), ey = 0.5 * (zk.y - zmk.y);
+    const double ox = 0.5 * (zk.x - zmk.x), oy = 0.5 * (zk.y + zmk.y);
+    const double2 wo = fr_mul(wk, make_double2(ox, oy));
+    const double xkx = ex + wo.y, xky = ey - wo.x;
+    const double xmx = ex - wo.y, xmy = -ey - wo.x;
+    *pk_out = fma(xkx, xkx, xky * xky);
+    *pmk_out = fma(xmx, xmx, xmy * xmy);
+}
+// ... and the packed inverse-transform input of a real, even spectrum G: Y[k] = (G[k] + G[M-k]) + i conj(w^k) (G[k] - G[M-k])
+FR_HD void fr_pair_retangle(double gk, double gmk, double2 wk, double2* yk, double2* ymk) {
+    const double s = gk + gmk, d = gk - gmk;
+    *yk = make_double2(fma(wk.y, d, s), wk.x * d);
+    *ymk = make_double2(fma(-wk.y, d, s), wk.x * d);
+}
+
 // Real-input untangle for one bin pair.  Zk = Z[k], Zmk = Z[M - k] of the packed transform, wk = exp(-2 pi i k / N), N = 2M.
 // Returns through yk / ymk the packed input of the inverse transform of the (real, even) power spectrum:
 // Y[k] = (P[k] + P[M-k]) + i conj(w^k) (P[k] - P[M-k]) and Y[M-k]; pk / pmk receive the powers |X[k]|^2, |X[M-k]|^2.

@@ -1,0 +1,124 @@
+// fftwarp.cuh -- warp-level pieces of the register-resident packed real FFT (see fftreg.cuh for the decomposition):
+// the two-pass transform with one shared-memory exchange, and the real-input untangle done with warp shuffles.
+// Used by the autocorrelation pitch frames (k_acw.cu), the spectrogram moments (k_moments.cu), the power cepstrogram
+// (k_cpp.cu) and the MFCC frames (k_lld.cu).  L = M / 32 lanes own one frame (L = 32: a warp, L = 16: half a warp).
+#pragma once
+#include "common.cuh"
+#include "fftreg.cuh"
+
+// One transform of the frame(s) of this warp.  `a` holds pass-A input in logical order (element k = z[j + L k]); on return
+// `a` holds logical element r (k = j + L r) of the result at a[fr_slot<L>(r)].  xch: this lane's frame exchange region
+// (M complex doubles); twb: [32][L] table of exp(-2 pi i j q / M).
+template <int L, int SIGN>
+__device__ __forceinline__ void fw_transform(double2 (&a)[32], double2* xch, int j, const double2* __restrict__ twb) {
+    fr_fft<32, SIGN>(a);
+    fr_static_for<0, 32>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        double2 v = a[fr_brev(q, 5)];
+        if constexpr (q > 0) {
+            double2 t = __ldg(twb + q * L + j);                 // exp(-2 pi i j q / M); conjugate for the inverse
+            if (SIGN > 0) t.y = -t.y;
+            v = fr_mul(v, t);
+        }
+        xch[q * L + (j ^ (q & 7))] = v;
+    });
+    __syncwarp();
+    if constexpr (L == 32) {
+        const int q = j;
+        fr_static_for<0, 32>([&](auto jc) {
+            constexpr int jj = decltype(jc)::value;
+            a[jj] = xch[q * 32 + (jj ^ (q & 7))];
+        });
+        fr_fft<32, SIGN>(a);
+    } else {
+        fr_static_for<0, 32>([&](auto sc) {
+            constexpr int sl = decltype(sc)::value, h = sl >> 4, jj = sl & 15;
+            const int q = j + 16 * h;
+            a[sl] = xch[q * 16 + (jj ^ (q & 7))];
+        });
+        fr_fft<16, SIGN>(&a[0]);
+        fr_fft<16, SIGN>(&a[16]);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ double2 fw_shfl2(double2 v, int src) {
+    return make_double2(__shfl_sync(FULL_MASK, v.x, src), __shfl_sync(FULL_MASK, v.y, src));
+}
+
+struct FwIdentity { __device__ __forceinline__ double operator()(double p) const { return p; } };
+
+// Power spectrum of the packed real transform, in place: Z (slots) -> Y (slots), the packed input of the inverse transform
+// of F(|X[k]|^2) (F = identity: autocorrelation; F = log: cepstrum).  Bin k = j + L r pairs with M - k = (L - j) + L (31 - r),
+// held by lane L - j: every lane computes the pairs of its r < 16 (both members) and trades the results by shuffle.  Lane
+// j = 0 pairs inside itself (r with 32 - r; bins 0 and M/2 are their own partners).  wj = exp(-2 pi i j / N), N = 2M.
+template <int L, class F>
+__device__ __forceinline__ void fw_power_retangle(double2 (&e)[32], int lane, int j, double2 wj, F f) {
+    const int grp = lane & ~(L - 1);
+    const int pl = grp | ((L - j) & (L - 1));
+    const bool j0 = j == 0;
+    fr_static_for<0, 16>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        const double2 mine = e[fr_slot<L>(r)];
+        double2 theirs = fw_shfl2(e[fr_slot<L>(31 - r)], pl);
+        if constexpr (r >= 1) { if (j0) theirs = e[fr_slot<L>(32 - r)]; }
+        const double2 wk = fr_mul(wj, make_double2(fr_cos64(r), -fr_sin64(r)));      // exp(-2 pi i (j + L r) / N)
+        double pk, pmk;
+        fr_pair_powers(mine, theirs, wk, &pk, &pmk);
+        double2 yk, ymk;
+        fr_pair_retangle(f(pk), f(pmk), wk, &yk, &ymk);
+        if constexpr (r == 0) {
+            if (j0) {
+                const double p0 = f((mine.x + mine.y) * (mine.x + mine.y)), pM = f((mine.x - mine.y) * (mine.x - mine.y));
+                yk = make_double2(p0 + pM, p0 - pM);
+            }
+        }
+        const double2 ret = fw_shfl2(ymk, pl);
+        e[fr_slot<L>(r)] = yk;
+        if (!j0) e[fr_slot<L>(31 - r)] = ret;
+        if constexpr (r >= 1) { if (j0) e[fr_slot<L>(32 - r)] = ymk; }
+    });
+    {   // lane j = 0: bin M/2 pairs with itself
+        const double2 z = e[fr_slot<L>(16)];
+        const double2 wk = make_double2(fr_cos64(16), -fr_sin64(16));
+        double pk, pmk;
+        fr_pair_powers(z, z, wk, &pk, &pmk);
+        double2 yk, ymk;
+        fr_pair_retangle(f(pk), f(pmk), wk, &yk, &ymk);
+        if (j0) e[fr_slot<L>(16)] = yk;
+    }
+}
+
+// Powers only: P[r] = |X[j + L r]|^2 for r < RMAX (RMAX <= 32) of the real transform whose packed spectrum sits in e (slots).
+// (The bin M itself -- Nyquist -- is not produced.)
+template <int L, int RMAX>
+__device__ __forceinline__ void fw_powers(const double2 (&e)[32], int lane, int j, double2 wj, double (&P)[32]) {
+    const int grp = lane & ~(L - 1);
+    const int pl = grp | ((L - j) & (L - 1));
+    const bool j0 = j == 0;
+    fr_static_for<0, 16>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        // the pair (r, 31 - r) yields P[r] here and, through the partner lane, P[31 - r] there: skip pairs nobody needs
+        if constexpr (r < RMAX || 31 - r < RMAX || 32 - r < RMAX) {
+            const double2 mine = e[fr_slot<L>(r)];
+            double2 theirs = fw_shfl2(e[fr_slot<L>(31 - r)], pl);
+            if constexpr (r >= 1) { if (j0) theirs = e[fr_slot<L>(32 - r)]; }
+            const double2 wk = fr_mul(wj, make_double2(fr_cos64(r), -fr_sin64(r)));
+            double pk, pmk;
+            fr_pair_powers(mine, theirs, wk, &pk, &pmk);
+            if constexpr (r == 0) { if (j0) pk = (mine.x + mine.y) * (mine.x + mine.y); }
+            if constexpr (r < RMAX) P[r] = pk;
+            if constexpr (31 - r < RMAX) {
+                const double got = __shfl_sync(FULL_MASK, pmk, pl);
+                if (!j0) P[31 - r] = got;
+            }
+            if constexpr (r >= 1 && 32 - r < RMAX) { if (j0) P[32 - r] = pmk; }
+        }
+    });
+    if constexpr (16 < RMAX) {
+        const double2 z = e[fr_slot<L>(16)];
+        double pk, pmk;
+        fr_pair_powers(z, z, make_double2(fr_cos64(16), -fr_sin64(16)), &pk, &pmk);
+        if (j0) P[16] = pk;
+    }
+}

@@ -24,6 +24,7 @@
 #include "fft.cuh"
 #include "num.cuh"
 #include "fftreg.cuh"
+#include "fftwarp.cuh"
 
 #define ACW_WARPS 4
 #define ACW_NT (32 * ACW_WARPS)
@@ -224,81 +225,6 @@ __device__ __forceinline__ int w_find_candidates(const PitchCfg& g, double dx, c
     return S.s_int[1] | ((vt2 >= 0.0 ? S.s_int[2] : 0) << 8);
 }
 
-// ------------------------------------------------------------------------------------------------ transforms (warp)
-// One transform of the frame(s) of this warp.  `a` holds pass-A input in logical order (element k = z[j + L k]); on return
-// `a` holds logical element r (k = j + L r) of the result at a[fr_slot<L>(r)].  xch: this lane's frame exchange region.
-template <int L, int SIGN>
-__device__ __forceinline__ void acw_transform(double2 (&a)[32], double2* xch, int j, const double2* __restrict__ twb) {
-    fr_fft<32, SIGN>(a);
-    fr_static_for<0, 32>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        double2 v = a[fr_brev(q, 5)];
-        if constexpr (q > 0) {
-            double2 t = __ldg(twb + q * L + j);                 // exp(-2 pi i j q / M); conjugate for the inverse
-            if (SIGN > 0) t.y = -t.y;
-            v = fr_mul(v, t);
-        }
-        xch[q * L + (j ^ (q & 7))] = v;
-    });
-    __syncwarp();
-    if constexpr (L == 32) {
-        const int q = j;
-        fr_static_for<0, 32>([&](auto jc) {
-            constexpr int jj = decltype(jc)::value;
-            a[jj] = xch[q * 32 + (jj ^ (q & 7))];
-        });
-        fr_fft<32, SIGN>(a);
-    } else {
-        fr_static_for<0, 32>([&](auto sc) {
-            constexpr int sl = decltype(sc)::value, h = sl >> 4, jj = sl & 15;
-            const int q = j + 16 * h;
-            a[sl] = xch[q * 16 + (jj ^ (q & 7))];
-        });
-        fr_fft<16, SIGN>(&a[0]);
-        fr_fft<16, SIGN>(&a[16]);
-    }
-    __syncwarp();
-}
-
-__device__ __forceinline__ double2 shfl2(double2 v, int src) {
-    return make_double2(__shfl_sync(FULL_MASK, v.x, src), __shfl_sync(FULL_MASK, v.y, src));
-}
-
-// power spectrum of the packed real transform, in place: Z (slots) -> Y (slots), the packed input of the inverse transform
-template <int L>
-__device__ __forceinline__ void acw_untangle(double2 (&e)[32], int lane, int j, double2 wj /* exp(-2 pi i j / N) */) {
-    const int grp = lane & ~(L - 1);
-    const int pl = grp | ((L - j) & (L - 1));
-    const bool j0 = j == 0;
-    fr_static_for<0, 16>([&](auto rc) {
-        constexpr int r = decltype(rc)::value;
-        const double2 mine = e[fr_slot<L>(r)];
-        double2 theirs = shfl2(e[fr_slot<L>(31 - r)], pl);
-        if constexpr (r >= 1) { if (j0) theirs = e[fr_slot<L>(32 - r)]; }
-        const double2 wk = fr_mul(wj, make_double2(fr_cos64(r), -fr_sin64(r)));      // exp(-2 pi i (j + L r) / N)
-        double2 yk, ymk;
-        double pk, pmk;
-        fr_pair(mine, theirs, wk, &yk, &ymk, &pk, &pmk);
-        if constexpr (r == 0) {
-            if (j0) {
-                const double p0 = (mine.x + mine.y) * (mine.x + mine.y), pM = (mine.x - mine.y) * (mine.x - mine.y);
-                yk = make_double2(p0 + pM, p0 - pM);
-            }
-        }
-        const double2 ret = shfl2(ymk, pl);
-        e[fr_slot<L>(r)] = yk;
-        if (!j0) e[fr_slot<L>(31 - r)] = ret;
-        if constexpr (r >= 1) { if (j0) e[fr_slot<L>(32 - r)] = ymk; }
-    });
-    {   // lane j = 0: bin M/2 pairs with itself
-        const double2 z = e[fr_slot<L>(16)];
-        double2 yk, ymk;
-        double pk, pmk;
-        fr_pair(z, z, make_double2(fr_cos64(16), -fr_sin64(16)), &yk, &ymk, &pk, &pmk);
-        if (j0) e[fr_slot<L>(16)] = yk;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ the frame, per lane
 // Everything one lane does for the frame it belongs to.  L lanes per frame; `active` = this lane's frame exists.
 template <int L>
@@ -358,16 +284,16 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
     const double intensity = localPeak > globalPeak ? 1.0 : localPeak / globalPeak;
 
     // ---- autocorrelation: forward packed FFT, power spectrum, inverse
-    acw_transform<L, -1>(a, xch, j, twb);
+    fw_transform<L, -1>(a, xch, j, twb);
     {
         const int N = 64 * L;                                             // real transform length
         const double2 wj = __ldg(tw + j * (TW_N / N));
-        acw_untangle<L>(a, lane, j, wj);
+        fw_power_retangle<L>(a, lane, j, wj, FwIdentity());
     }
     {
         double2 b[32];
         fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; b[r] = a[fr_slot<L>(r)]; });
-        acw_transform<L, +1>(b, xch, j, twb);
+        fw_transform<L, +1>(b, xch, j, twb);
         fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; a[r] = b[r]; });
     }
     // a[fr_slot(r)] = (ac[2n], ac[2n+1]), n = j + L r.  Normalise and publish r[0..B]: correlation row (global) + rs0 (shared)
