@@ -193,6 +193,7 @@ struct SpecPass {
     const double* window;      // [nsamp_window] Gaussian (float32-rounded like Praat)
     int* nF; double* t1; int* fstart;
     double* mom;               // [frames*4]
+    int* turn_counter;         // work counter of the warp-per-frame kernel's persistent CTAs
 };
 void launch_moments(const Clips& c, const SpecPass& p, const PitchPass& pp, const double2* tw, int max_frames_hint,
                     cudaStream_t s);

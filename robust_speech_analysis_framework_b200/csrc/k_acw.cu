@@ -25,64 +25,18 @@
 #include "num.cuh"
 #include "fftreg.cuh"
 #include "fftwarp.cuh"
+#include "stage.cuh"
 
 #define ACW_WARPS 4
 #define ACW_NT (32 * ACW_WARPS)
 #define ACW_TURN 8
 #define ACW_XCH_BYTES (1024 * 16)          // exchange buffer per warp: 1024 complex doubles
 
-// ------------------------------------------------------------------------------------------------ TMA / mbarrier helpers
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-// ------------------------------------------------------------------------------------------------ staged span
-struct AcwSeg {               // one staged segment: consecutive frames of ONE clip (written by thread 0, read by all)
-    int f0, n;                // first flat frame index, frames (0 = no more work)
-    int clip, cls, k0;        // clip, speaker class, index of the first frame inside the clip
-    long long base;           // chunk offset of the clip's first sample
-    long long sA;             // 1-based clip sample index of staged element 0
-    int count;                // staged elements
-    int shift;                // staged element e sits `shift + e` elements into the stage buffer (16-byte alignment of the source)
-    int head, tail0;          // elements [0, head) and [tail0, count) are NOT covered by the bulk copy: copied by threads
-    int tma_bytes;            // 0 = nothing was issued (barrier not armed)
-};
-
-struct AcwParams {
-    const unsigned char* pcm_bytes;   // chunk samples as bytes
-    long long total_elems;            // samples in the chunk
-    int esz;                          // 2 (int16) or 8 (float64 behind the resampling front-end)
-    int stage_bytes;                  // bytes of ONE stage buffer
+struct AcwParams : StageParams {
     const double2* twb512;            // [32][16] exp(-2 pi i j q / 512)
     const double2* twb1024;           // [32][32] exp(-2 pi i j q / 1024)
 };
-
-__device__ __forceinline__ double staged(const unsigned char* st, int esz, int e /* element index incl. shift */) {
-    return esz == 2 ? (double)((const short*)st)[e] * (1.0 / 32768.0) : ((const double*)st)[e];
-}
+typedef StageSeg AcwSeg;
 
 // thread 0: next segment of work -> *sg, and its bulk copy into `stage` (armed on `bar`)
 __device__ __forceinline__ void acw_fetch(const Clips& c, const PitchPass& p, const AcwParams& A, int total, int nturn,
@@ -100,7 +54,6 @@ __device__ __forceinline__ void acw_fetch(const Clips& c, const PitchPass& p, co
     const PitchCfg& g = p.cfg[cls];
     sg->f0 = cur_f; sg->n = f1 - cur_f; sg->clip = clip; sg->cls = cls; sg->k0 = cur_f - p.fstart[clip];
     const long long base = c.off[clip], nx = c.off[clip + 1] - base;
-    sg->base = base;
     // samples the frames k0 .. k0 + n - 1 touch: window [right - half, left + half] and local-mean range [right - period, left + period]
     const double x1 = c.x1[clip];
     const double tA = p.t1[clip] + (double)sg->k0 * g.dt, tB = p.t1[clip] + (double)(sg->k0 + sg->n - 1) * g.dt;
@@ -110,32 +63,7 @@ __device__ __forceinline__ void acw_fetch(const Clips& c, const PitchPass& p, co
     if (sA < 1) sA = 1;
     if (sB > nx) sB = nx;
     if (sB < sA) sB = sA - 1;
-    sg->sA = sA;
-    const int count = (int)(sB - sA + 1);
-    sg->count = count;
-    const int esz = A.esz;
-    const long long gA = base + sA - 1;                                   // chunk element index of staged element 0
-    const unsigned long long addr = (unsigned long long)(A.pcm_bytes + gA * esz);
-    const unsigned long long a0 = addr & ~15ull;
-    sg->shift = (int)((addr - a0) / esz);
-    unsigned long long a1 = (addr + (unsigned long long)count * esz + 15ull) & ~15ull;
-    // bytes the bulk copy may touch: whole 16-byte units inside the chunk's sample array
-    const unsigned long long lo = ((unsigned long long)A.pcm_bytes + 15ull) & ~15ull;
-    const unsigned long long hi = ((unsigned long long)A.pcm_bytes + (unsigned long long)A.total_elems * esz) & ~15ull;
-    unsigned long long t0 = a0 > lo ? a0 : lo, t1 = a1 < hi ? a1 : hi;
-    if (t1 > a0 + (unsigned long long)A.stage_bytes) t1 = a0 + (unsigned long long)A.stage_bytes;    // (cannot happen: stage sized for the worst span)
-    int head = 0, tail0 = count, bytes = 0;
-    if (count > 0 && t1 > t0) {
-        bytes = (int)(t1 - t0);
-        head = t0 > addr ? (int)((t0 - addr + esz - 1) / esz) : 0;
-        tail0 = (int)((t1 - addr) / esz);
-        if (tail0 > count) tail0 = count;
-        mbar_expect_tx(bar, (unsigned)bytes);
-        tma_load_1d(stage + (t0 - a0), (const void*)t0, (unsigned)bytes, bar);
-    } else {
-        head = count; tail0 = count;             // everything by threads
-    }
-    sg->head = head; sg->tail0 = tail0; sg->tma_bytes = bytes;
+    stage_issue(A, sg, base, sA, (int)(sB - sA + 1), stage, bar);
     cur_f = f1;
 }
 
@@ -413,12 +341,7 @@ __global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant
     const int total = p.fstart[c.n];
     const int nturn = (total + ACW_TURN - 1) / ACW_TURN;
     int cur_f = 0, turn_end = 0;                                          // thread 0's position in its current turn
-    if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
+    if (tid == 0) mbar_init_pair(bars);
     __syncthreads();
     if (tid == 0) acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[0], stage0, &bars[0]);
     unsigned phase0 = 0, phase1 = 0;
@@ -430,20 +353,7 @@ __global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant
         unsigned char* st = stage0 + (size_t)buf * A.stage_bytes;
         if (tid == 0)                         // prefetch the next segment while this one is processed
             acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[buf ^ 1], stage0 + (size_t)(buf ^ 1) * A.stage_bytes, &bars[buf ^ 1]);
-        // elements the bulk copy could not cover (unaligned ends of the chunk): plain loads
-        if (sg.head > 0 || sg.tail0 < sg.count) {
-            const long long g0 = sg.base + sg.sA - 1;
-            for (int e = tid; e < sg.count; e += ACW_NT) {
-                if (e >= sg.head && e < sg.tail0) continue;
-                if (A.esz == 2) ((short*)st)[sg.shift + e] = ((const short*)A.pcm_bytes)[g0 + e];
-                else ((double*)st)[sg.shift + e] = ((const double*)A.pcm_bytes)[g0 + e];
-            }
-            __syncthreads();
-        }
-        if (sg.tma_bytes > 0) {
-            mbar_wait(&bars[buf], buf == 0 ? phase0 : phase1);
-            if (buf == 0) phase0 ^= 1; else phase1 ^= 1;
-        }
+        stage_complete<ACW_NT>(A, sg, st, &bars[buf], buf == 0 ? phase0 : phase1);
         unsigned char* xw = xch_all + (size_t)warp * ACW_XCH_BYTES;
         const int M = p.cfg[sg.cls].M;
         if (M == 1024) {

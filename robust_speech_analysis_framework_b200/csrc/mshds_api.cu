@@ -759,6 +759,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     if ((rc = make_spec_cfg(h, fs, &spec))) return rc;
     spec.nF = take<int>(h, n); spec.t1 = take<double>(h, n); spec.fstart = take<int>(h, n + 1);
     spec.mom = take<double>(h, fub5 * 4);
+    spec.turn_counter = take<int>(h, 1);
 
     if (dry_run) return MSHDS_OK;           // sizing pass only
     if (h->arena_overflow) { h->err = "internal: arena overflow after sizing"; return MSHDS_ERR_CUDA; }

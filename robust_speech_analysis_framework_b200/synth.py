@@ -37,31 +37,37 @@ def _gauss(idx: torch.Tensor, seed: int) -> torch.Tensor:
     return (u - 2.0) * math.sqrt(3.0)
 
 
-def _schedule(rng: np.random.Generator, duration: float):
-    """Phrase / pause / syllable timeline -> arrays of syllable (start, end, voiced, dip_dB, formants)."""
+def _schedule(rng: np.random.Generator, duration: float, style: str = "plain"):
+    """Phrase / pause / syllable timeline -> arrays of syllable (start, end, voiced, dip_dB, formants).
+
+    style "plain": phrases of 0.8-3 s separated by pauses of 0.35-0.9 s (all longer than the 0.3 s minimum pause of
+    _speechrate).  style "stress": short bursts (0.12-1.5 s) and gaps of 0.03-0.6 s, 30 % unvoiced syllables -- sounding /
+    silent intervals below the 0.1 s / 0.3 s minima that must be cut and merged, voiced runs whose +-50 ms extension overlaps
+    the next one, many voiced/unvoiced transitions for the path finder."""
+    stress = style == "stress"
     syl = []
     t = float(rng.uniform(0.15, 0.5))          # leading pause
     while t < duration - 0.2:
-        phrase_end = min(duration - 0.15, t + float(rng.uniform(0.8, 3.0)))
+        phrase_end = min(duration - 0.15, t + float(rng.uniform(0.12, 1.5) if stress else rng.uniform(0.8, 3.0)))
         rate = float(rng.uniform(3.5, 5.5))
         f_form = np.array([500.0, 1500.0, 2500.0, 3500.0]) + rng.normal(0, 1, 4) * np.array([80, 150, 150, 150.0])
         while t < phrase_end - 0.08:
             d = min(phrase_end - t, float(rng.uniform(0.8, 1.2)) / rate)
             f_form = f_form + rng.normal(0, 1, 4) * np.array([40, 80, 60, 60.0])
             f_form = np.clip(f_form, [300, 1000, 2100, 3100], [800, 2000, 2900, 3900])
-            syl.append((t, t + d, rng.random() > 0.15, float(rng.uniform(6.0, 10.0)), f_form.copy()))
+            syl.append((t, t + d, rng.random() > (0.30 if stress else 0.15), float(rng.uniform(6.0, 10.0)), f_form.copy()))
             t += d
-        t = phrase_end + float(rng.uniform(0.35, 0.9))
+        t = phrase_end + float(rng.uniform(0.03, 0.6) if stress else rng.uniform(0.35, 0.9))
     return syl
 
 
-def synth_clip(index: int, duration: float, device: str | torch.device = "cpu", fs: int = FS) -> torch.Tensor:
-    """One clip as an int16 tensor of round(duration*fs) samples on `device`."""
+def synth_clip(index: int, duration: float, device: str | torch.device = "cpu", fs: int = FS, style: str = "plain") -> torch.Tensor:
+    """One clip as an int16 tensor of round(duration*fs) samples on `device` (style: see _schedule)."""
     rng = np.random.default_rng(BASE_SEED + index)
     n = int(round(duration * fs))
     dev = torch.device(device)
     base_f0 = float(rng.uniform(95, 135)) if index % 2 == 0 else float(rng.uniform(180, 230))
-    syl = _schedule(rng, duration)
+    syl = _schedule(rng, duration, style)
     if not syl:
         syl = [(0.1 * duration, 0.9 * duration, True, 8.0, np.array([500.0, 1500.0, 2500.0, 3500.0]))]
     starts = torch.tensor([s[0] for s in syl], dtype=torch.float64, device=dev)

@@ -206,7 +206,7 @@ def test_warp_resident_fft_frames_equal_the_shared_memory_ones(ex):
         for a, b in zip(cn[k], co[k]):
             assert len(a) == len(b)
             assert np.array_equal(a == 0, b == 0), f"{k}: voicing decisions differ"
-            np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12, err_msg=k)
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-9, err_msg=k)   # Brent stops at sqrt(eps) |x|: 1.5e-8 relative
     assert_features_close(new, old, "warp FFT vs legacy FFT")
     assert np.array_equal(new[:, SPEECHRATE], old[:, SPEECHRATE])
 
