@@ -122,3 +122,87 @@ __device__ __forceinline__ void fw_powers(const double2 (&e)[32], int lane, int 
         if (j0) P[16] = pk;
     }
 }
+
+// ------------------------------------------------------------------------------------------------ looped round trip
+// forward packed real FFT -> G(|X|^2) -> inverse FFT with ONE copy of the transform code, for a run-time L (16 or 32 lanes per
+// frame).  Both sizes share the code because fr_slot<16> == fr_slot<32> == the 5-bit reversal and pass B of the 512-point case
+// is the 32-point butterfly network minus its first stage (= two 16-point transforms); forward and inverse share it because
+// inverse = conj FFT conj, the conjugations folded into the re-tangle step here and into the caller's read-out.
+//   in : a[k] = z[j + L k] (logical order), z[n] = x[2n] + i x[2n+1] the packed real frame
+//   out: a[fr_brev(r, 5)] = conj(y[j + L r]),  y[n] = c[2n] + i c[2n+1],  c = sum_{k<N} G(|X[k]|^2) exp(+2 pi i k n / N)
+// (G = identity: autocorrelation of the frame; G = log: its real cepstrum).  Keeping the unrolled code small matters: the
+// first warp-per-frame kernel of this round had four differently unrolled transforms per size and spent 35 % of its stall
+// samples waiting for instruction fetch (ncu stalled_no_instructions; the L1.5 instruction cache holds 32 KB).
+__device__ __forceinline__ void fw_fft32(double2 (&a)[32], bool two_halves) {
+    if (!two_halves) FrDifStage<32, 16, -1, 0>::run(a);      // first stage pairs (i, i + 16); without it: two 16-point FFTs
+    fr_dif_stages<32, 8, -1>(a);
+}
+
+template <class G>
+__device__ __forceinline__ void fw_roundtrip(double2 (&a)[32], double2* xch, int lane, int j, int L, const double2* __restrict__ twb,
+                                             double2 wj /* exp(-2 pi i j / N) */, G gf) {
+    const int grp = lane & ~(L - 1);
+    const int pl = grp | ((L - j) & (L - 1));
+    const bool j0 = j == 0;
+#pragma unroll 1
+    for (int it = 0; it < 2; it++) {
+        // pass A: 32-point transform of the lane's stride-L elements, twiddle, transpose through shared memory
+        fw_fft32(a, false);
+        fr_static_for<0, 32>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            double2 v = a[fr_brev(q, 5)];
+            if constexpr (q > 0) v = fr_mul(v, __ldg(twb + q * L + j));   // exp(-2 pi i j q / M)
+            xch[q * L + (j ^ (q & 7))] = v;
+        });
+        __syncwarp();
+        fr_static_for<0, 32>([&](auto sc) {
+            constexpr int sl = decltype(sc)::value;
+            const int q = L == 32 ? j : j + 16 * (sl >> 4), jj = L == 32 ? sl : (sl & 15);
+            a[sl] = xch[q * L + (jj ^ (q & 7))];
+        });
+        // pass B: rows of L-point transforms (L = 16: two rows per lane = the 32-point network without its first stage)
+        fw_fft32(a, L == 16);
+        __syncwarp();
+        if (it == 0) {
+            // a[brev5(r)] = Z[j + L r]: powers, G, re-tangled into the CONJUGATE of the packed inverse-transform input; pairs are
+            // traded with lane L - j by shuffle (see fw_power_retangle)
+            fr_static_for<0, 16>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const double2 mine = a[fr_brev(r, 5)];
+                double2 theirs = fw_shfl2(a[fr_brev(31 - r, 5)], pl);
+                if constexpr (r >= 1) { if (j0) theirs = a[fr_brev(32 - r, 5)]; }
+                const double2 wk = fr_mul(wj, make_double2(fr_cos64(r), -fr_sin64(r)));      // exp(-2 pi i (j + L r) / N)
+                double pk, pmk;
+                fr_pair_powers(mine, theirs, wk, &pk, &pmk);
+                double2 yk, ymk;
+                fr_pair_retangle(gf(pk), gf(pmk), wk, &yk, &ymk);
+                if constexpr (r == 0) {
+                    if (j0) {
+                        const double p0 = gf((mine.x + mine.y) * (mine.x + mine.y)), pM = gf((mine.x - mine.y) * (mine.x - mine.y));
+                        yk = make_double2(p0 + pM, p0 - pM);
+                    }
+                }
+                yk.y = -yk.y; ymk.y = -ymk.y;
+                const double2 ret = fw_shfl2(ymk, pl);
+                a[fr_brev(r, 5)] = yk;
+                if (!j0) a[fr_brev(31 - r, 5)] = ret;
+                if constexpr (r >= 1) { if (j0) a[fr_brev(32 - r, 5)] = ymk; }
+            });
+            {   // lane j = 0: bin M/2 pairs with itself
+                const double2 z = a[fr_brev(16, 5)];
+                const double2 wk = make_double2(fr_cos64(16), -fr_sin64(16));
+                double pk, pmk;
+                fr_pair_powers(z, z, wk, &pk, &pmk);
+                double2 yk, ymk;
+                fr_pair_retangle(gf(pk), gf(pmk), wk, &yk, &ymk);
+                yk.y = -yk.y;
+                if (j0) a[fr_brev(16, 5)] = yk;
+            }
+            // slots -> logical order for the next pass A: the 5-bit reversal is an involution, 12 swaps
+            fr_static_for<0, 32>([&](auto rc) {
+                constexpr int r = decltype(rc)::value, br = fr_brev(r, 5);
+                if constexpr (r < br) { const double2 tmp = a[r]; a[r] = a[br]; a[br] = tmp; }
+            });
+        }
+    }
+}

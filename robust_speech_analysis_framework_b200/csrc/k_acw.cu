@@ -154,27 +154,28 @@ __device__ __forceinline__ int w_find_candidates(const PitchCfg& g, double dx, c
 }
 
 // ------------------------------------------------------------------------------------------------ the frame, per lane
-// Everything one lane does for the frame it belongs to.  L lanes per frame; `active` = this lane's frame exists.
-template <int L>
+// The correlation of one frame.  L (16 or 32) lanes per frame is a RUN-TIME value: both transform sizes share one copy of the
+// code (fr_slot<16> == fr_slot<32> == 5-bit reversal; pass B of the 512-point case is the 32-point butterfly network minus its
+// first stage = two 16-point transforms), and forward and inverse transform share it too (inverse = conj FFT conj, the
+// conjugations folded into the untangle step and the read-out).  What is left is ~2,500 instructions of straight-line
+// code executed twice per frame instead of four different unrolled transforms per size: the first version of this kernel
+// spent 35 % of its stall samples waiting for instruction fetch (ncu: stalled_no_instructions).
 __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const AcwParams& A, const AcwSeg& sg,
-                                          const unsigned char* st, unsigned char* xw /* warp exchange region */, int fi,
-                                          bool active, const double2* __restrict__ tw) {
-    const int lane = threadIdx.x & 31, j = lane & (L - 1), gidx = lane / L;
+                                       const unsigned char* st, unsigned char* xw /* warp exchange region */, int fi,
+                                       bool active, int L, const double2* __restrict__ tw) {
+    const int lane = threadIdx.x & 31, j = lane & (L - 1), gidx = L == 32 ? 0 : lane >> 4;
     const unsigned gmask = L == 32 ? FULL_MASK : (0xffffu << (16 * gidx));
     const PitchCfg& g = p.cfg[sg.cls];
     const double dx = c.dx;
     const int W = g.nsamp_window, B = g.brent_ixmax;
-    const int Bs = B < g.maximumLag + 32 ? B : g.maximumLag + 32;
     const int esz = A.esz;
-    unsigned char* xf = xw + (size_t)gidx * (ACW_XCH_BYTES / (32 / L));           // this frame's exchange region
-    double2* xch = (double2*)xf;
+    double2* xch = (double2*)(xw + (size_t)gidx * (ACW_XCH_BYTES / 2));     // this frame's exchange region (L = 16: half)
     const double2* twb = L == 32 ? A.twb1024 : A.twb512;
 
     const double x1 = c.x1[sg.clip];
     const double t = p.t1[sg.clip] + (double)(sg.k0 + fi) * g.dt;
     const long long leftSample = x_to_low(x1, dx, t), rightSample = leftSample + 1;
-    // staged element index (incl. alignment shift) of 1-based clip sample s:  s - sA + shift
-    const int eoff = (int)(-sg.sA) + sg.shift;
+    const int eoff = (int)(-sg.sA) + sg.shift;            // staged element (incl. alignment shift) of 1-based clip sample s: s + eoff
 
     // ---- local mean over one longest period to both sides
     double acc = 0.0;
@@ -191,7 +192,7 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
         const long long startSample = rightSample - g.halfnsamp_window;
         int pk0 = g.halfnsamp_window + 1 - g.halfnsamp_period; if (pk0 < 1) pk0 = 1;
         int pk1 = g.halfnsamp_window + g.halfnsamp_period; if (pk1 > W) pk1 = W;
-        const int ebase = (int)startSample + eoff;                        // staged element of frame sample m = 0 (1-based clip sample startSample)
+        const int ebase = (int)startSample + eoff;                        // staged element of frame sample m = 0
         fr_static_for<0, 32>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             const int m = 2 * (j + L * k);
@@ -211,121 +212,32 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
     const double globalPeak = active ? c.gpeak[sg.clip] : 1.0;
     const double intensity = localPeak > globalPeak ? 1.0 : localPeak / globalPeak;
 
-    // ---- autocorrelation: forward packed FFT, power spectrum, inverse
-    fw_transform<L, -1>(a, xch, j, twb);
-    {
-        const int N = 64 * L;                                             // real transform length
-        const double2 wj = __ldg(tw + j * (TW_N / N));
-        fw_power_retangle<L>(a, lane, j, wj, FwIdentity());
-    }
-    {
-        double2 b[32];
-        fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; b[r] = a[fr_slot<L>(r)]; });
-        fw_transform<L, +1>(b, xch, j, twb);
-        fr_static_for<0, 32>([&](auto rc) { constexpr int r = decltype(rc)::value; a[r] = b[r]; });
-    }
-    // a[fr_slot(r)] = (ac[2n], ac[2n+1]), n = j + L r.  Normalise and publish r[0..B]: correlation row (global) + rs0 (shared)
-    const double ac0 = __shfl_sync(FULL_MASK, a[fr_slot<L>(0)].x, lane & ~(L - 1));
-    WCand S;
-    {
-        unsigned char* q = xf;
-        S.rs0 = (double*)q; q += ((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15;
-        int pkcap = g.maximumLag / 2 + 2;
-        if (pkcap > 320) pkcap = 320;
-        S.pkcap = pkcap;
-        S.pk_f = (double*)q; q += (size_t)pkcap * 8;
-        S.pk_s = (double*)q; q += (size_t)pkcap * 8;
-        S.pk_key = (double*)q; q += (size_t)pkcap * 8;
-        S.cf = (double*)q; q += 16 * 8; S.cs = (double*)q; q += 16 * 8; S.ckey = (double*)q; q += 16 * 8;
-        S.cf2 = (double*)q; q += 16 * 8; S.cs2 = (double*)q; q += 16 * 8; S.ckey2 = (double*)q; q += 16 * 8;
-        S.pk_lag = (int*)q; q += ((size_t)pkcap * 4 + 15) & ~(size_t)15;
-        S.cimax = (int*)q; q += 16 * 4; S.cimax2 = (int*)q; q += 16 * 4;
-        S.s_int = (int*)q; q += 16;
-        S.masks = (unsigned*)q;
-    }
-    const int f = sg.f0 + fi;
-    double* rrow = p.rbuf + (size_t)(active ? f : 0) * p.rstride;
+    // ---- autocorrelation = inverse FFT of |FFT|^2: the SAME transform code runs twice
+    const double2 wj = __ldg(tw + j * (TW_N / (64 * L)));                 // exp(-2 pi i j / N), N = 64 L
+    fw_roundtrip(a, xch, lane, j, L, twb, wj, FwIdentity());
+    // a[brev5(r)] = conj(y[n]), n = j + L r, y[n] = ac[2n] + i ac[2n+1].  Lags 0..B go through shared memory in natural
+    // order; the normalised correlation r[i] = ac[i] / (ac[0] windowR[i]) is written by a compact loop (coalesced rows)
+    double* acs = (double*)xch;
+    fr_static_for<0, 12>([&](auto rc) {                                    // B / 2 < 12 L for every configuration (checked by the launcher)
+        constexpr int r = decltype(rc)::value;
+        const int n = j + L * r;
+        if (2 * n <= B) {
+            const double2 v = a[fr_brev(r, 5)];
+            *(double2*)(acs + 2 * n) = make_double2(v.x, -v.y);
+        }
+    });
+    __syncwarp();
     if (active) {
-        fr_static_for<0, 32>([&](auto rc) {
-            constexpr int r = decltype(rc)::value;
-            const int i0 = 2 * (j + L * r);
-            if (i0 <= B) {
-                const double2 v = a[fr_slot<L>(r)];
-                const double r0 = i0 == 0 ? 1.0 : v.x / (ac0 * __ldg(g.windowR + i0));
-                rrow[i0] = r0;
-                if (i0 <= Bs) { S.rs0[Bs + i0] = r0; S.rs0[Bs - i0] = r0; }
-                if (i0 + 1 <= B) {
-                    const double r1 = v.y / (ac0 * __ldg(g.windowR + i0 + 1));
-                    rrow[i0 + 1] = r1;
-                    if (i0 + 1 <= Bs) { S.rs0[Bs + i0 + 1] = r1; S.rs0[Bs - i0 - 1] = r1; }
-                }
-            }
-        });
+        const int f = sg.f0 + fi;
+        double* rrow = p.rbuf + (size_t)f * p.rstride;
+        const double ac0 = acs[0];
+        for (int i = j; i <= B; i += L) rrow[i] = i == 0 ? 1.0 : acs[i] / (ac0 * __ldg(g.windowR + i));
+        if (j == 0) {
+            p.inten[f] = intensity;
+            p.ncand[f] = localPeak != 0.0 ? 1 : 0;        // hand-over to k_ac_candidates: "the frame has a local peak"
+        }
     }
     __syncwarp();
-
-    // ---- candidates: the whole warp serves one frame at a time
-    const bool dual = p.dual_cand_f != nullptr;
-    for (int gsel = 0; gsel < 32 / L; gsel++) {
-        const int src = gsel * L;                                          // first lane of that frame's group
-        const bool act = __shfl_sync(FULL_MASK, (int)active, src) != 0;
-        if (!act) continue;
-        const double lpk = __shfl_sync(FULL_MASK, localPeak, src);
-        const double inten = __shfl_sync(FULL_MASK, intensity, src);
-        const int ff = __shfl_sync(FULL_MASK, f, src);
-        // pointers of that frame's scratch (same layout, other region)
-        WCand T = S;
-        if (L != 32) {
-            const long long delta = (long long)(gsel - gidx) * (ACW_XCH_BYTES / (32 / L));
-            T.rs0 = (double*)((unsigned char*)S.rs0 + delta); T.pk_f = (double*)((unsigned char*)S.pk_f + delta);
-            T.pk_s = (double*)((unsigned char*)S.pk_s + delta); T.pk_key = (double*)((unsigned char*)S.pk_key + delta);
-            T.cf = (double*)((unsigned char*)S.cf + delta); T.cs = (double*)((unsigned char*)S.cs + delta);
-            T.ckey = (double*)((unsigned char*)S.ckey + delta); T.cf2 = (double*)((unsigned char*)S.cf2 + delta);
-            T.cs2 = (double*)((unsigned char*)S.cs2 + delta); T.ckey2 = (double*)((unsigned char*)S.ckey2 + delta);
-            T.pk_lag = (int*)((unsigned char*)S.pk_lag + delta); T.cimax = (int*)((unsigned char*)S.cimax + delta);
-            T.cimax2 = (int*)((unsigned char*)S.cimax2 + delta); T.s_int = (int*)((unsigned char*)S.s_int + delta);
-            T.masks = (unsigned*)((unsigned char*)S.masks + delta);
-        }
-        int ncand = 1, ncand2 = 1;
-        if (lpk != 0.0) {
-            const int nn = w_find_candidates(g, dx, T, B, Bs, tw, dual ? p.dual_vt : -1.0);
-            ncand = nn & 0xff;
-            if (dual) ncand2 = nn >> 8;
-        } else {
-            if (lane == 0) { T.cf[1] = 0.0; T.cs[1] = 0.0; T.cimax[1] = 0; T.cf2[1] = 0.0; T.cs2[1] = 0.0; T.cimax2[1] = 0; }
-            __syncwarp();
-        }
-        // candidates leave the SM (lanes 0..14: the analysis itself, lanes 16..30: the dual one); see k_pitch_frames for the
-        // exactness argument of the two skip rules
-        const int set = lane >> 4, ctid = lane & 15;
-        if (ctid < MAXCAND && (set == 0 || dual)) {
-            const double vt = set == 0 ? g.vt : p.dual_vt;
-            double uvs = g.sil <= 0 ? 0.0 : 2.0 - inten / (g.sil / (1.0 + vt));
-            uvs = vt + (uvs > 0 ? uvs : 0);
-            const bool frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
-            const int nc = set == 0 ? ncand : ncand2;
-            const double* scf = set == 0 ? T.cf : T.cf2;
-            const double* scs = set == 0 ? T.cs : T.cs2;
-            const int* sci = set == 0 ? T.cimax : T.cimax2;
-            const int ci = ctid + 1;
-            double fr = 0.0, stn = 0.0;
-            int im = 0;
-            if (ci <= nc) { fr = scf[ci]; stn = scs[ci]; im = sci[ci]; }
-            const size_t o2 = (size_t)ff * MAXCAND + ctid;
-            if (set == 0) { p.cand_f[o2] = fr; p.cand_s[o2] = stn; p.cand_imax[o2] = (unsigned short)im; }
-            else { p.dual_cand_f[o2] = fr; p.dual_cand_s[o2] = stn; p.dual_cand_imax[o2] = (unsigned short)im; }
-            const bool live = ci >= 2 && ci <= nc && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
-            if (live) {
-                if (set == 0) { int slot = atomicAdd(p.qcount, 1); p.queue[slot] = ff * 16 + ctid; }
-                else { int slot = atomicAdd(p.dual_qcount, 1); p.dual_queue[slot] = ff * 16 + ctid; }
-            }
-        }
-        if (lane == 0) {
-            p.ncand[ff] = (uint8_t)ncand; p.inten[ff] = inten;
-            if (dual) { p.dual_ncand[ff] = (uint8_t)ncand2; p.dual_inten[ff] = inten; }
-        }
-        __syncwarp();
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -337,7 +249,7 @@ __global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ AcwSeg segs[2];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int total = p.fstart[c.n];
     const int nturn = (total + ACW_TURN - 1) / ACW_TURN;
     int cur_f = 0, turn_end = 0;                                          // thread 0's position in its current turn
@@ -355,21 +267,98 @@ __global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant
             acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[buf ^ 1], stage0 + (size_t)(buf ^ 1) * A.stage_bytes, &bars[buf ^ 1]);
         stage_complete<ACW_NT>(A, sg, st, &bars[buf], buf == 0 ? phase0 : phase1);
         unsigned char* xw = xch_all + (size_t)warp * ACW_XCH_BYTES;
-        const int M = p.cfg[sg.cls].M;
-        if (M == 1024) {
-            for (int fr0 = 0; fr0 < sg.n; fr0 += ACW_WARPS) {
-                const int fi = fr0 + warp;
-                if (fi < sg.n) acw_frame<32>(c, p, A, sg, st, xw, fi, true, tw);
-            }
-        } else {
-            const int lane = tid & 31;
-            for (int fr0 = 0; fr0 < sg.n; fr0 += 2 * ACW_WARPS) {
-                const int fi = fr0 + 2 * warp + (lane >> 4);
-                if (fr0 + 2 * warp < sg.n)          // warp-uniform: at least the first of the two frames exists
-                    acw_frame<16>(c, p, A, sg, st, xw, fi, fi < sg.n, tw);
-            }
+        const int L = p.cfg[sg.cls].M == 1024 ? 32 : 16;
+        const int per_warp = 32 / L;                                     // frames a warp handles at once
+        for (int fr0 = 0; fr0 < sg.n; fr0 += per_warp * ACW_WARPS) {
+            const int first = fr0 + per_warp * warp;
+            if (first >= sg.n) break;                                    // warp-uniform
+            const int fi = first + (L == 32 ? 0 : lane >> 4);
+            acw_frame(c, p, A, sg, st, xw, fi, fi < sg.n, L, tw);
         }
         buf ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ candidate kernel
+// Sound_into_PitchFrame, first pass, for the frames whose correlation rows k_ac_frames_w just wrote: one WARP per frame at
+// high occupancy (this part is a chain of dependent shuffles and a serial slot insertion -- latency, not arithmetic -- and
+// used to sit in the register-heavy transform kernel, where only 8 warps per SM could hide it).
+#define ACC_WARPS 4
+__global__ void __launch_bounds__(32 * ACC_WARPS) k_ac_candidates(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
+                                                                  const double2* __restrict__ tw, int region_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* xf = smem + (size_t)warp * region_bytes;
+    const int total = p.fstart[c.n];
+    const double dx = c.dx;
+    const bool dual = p.dual_cand_f != nullptr;
+    for (int f = blockIdx.x * ACC_WARPS + warp; f < total; f += gridDim.x * ACC_WARPS) {
+        const int clip = find_segment(p.fstart, c.n, f);
+        const PitchCfg& g = p.cfg[c.cls[clip]];
+        const int B = g.brent_ixmax;
+        const int Bs = B < g.maximumLag + 32 ? B : g.maximumLag + 32;
+        WCand S;
+        {
+            unsigned char* q = xf;
+            S.rs0 = (double*)q; q += ((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15;
+            int pkcap = g.maximumLag / 2 + 2;
+            if (pkcap > 320) pkcap = 320;
+            S.pkcap = pkcap;
+            S.pk_f = (double*)q; q += (size_t)pkcap * 8;
+            S.pk_s = (double*)q; q += (size_t)pkcap * 8;
+            S.pk_key = (double*)q; q += (size_t)pkcap * 8;
+            S.cf = (double*)q; q += 16 * 8; S.cs = (double*)q; q += 16 * 8; S.ckey = (double*)q; q += 16 * 8;
+            S.cf2 = (double*)q; q += 16 * 8; S.cs2 = (double*)q; q += 16 * 8; S.ckey2 = (double*)q; q += 16 * 8;
+            S.pk_lag = (int*)q; q += ((size_t)pkcap * 4 + 15) & ~(size_t)15;
+            S.cimax = (int*)q; q += 16 * 4; S.cimax2 = (int*)q; q += 16 * 4;
+            S.s_int = (int*)q; q += 16;
+            S.masks = (unsigned*)q;
+        }
+        const double inten = p.inten[f];
+        const bool has_peak = p.ncand[f] != 0;
+        const double* rrow = p.rbuf + (size_t)f * p.rstride;
+        __syncwarp();
+        for (int i = lane; i <= Bs; i += 32) { const double v = rrow[i]; S.rs0[Bs + i] = v; S.rs0[Bs - i] = v; }
+        __syncwarp();
+        int ncand = 1, ncand2 = 1;
+        if (has_peak) {
+            const int nn = w_find_candidates(g, dx, S, B, Bs, tw, dual ? p.dual_vt : -1.0);
+            ncand = nn & 0xff;
+            if (dual) ncand2 = nn >> 8;
+        } else {
+            if (lane == 0) { S.cf[1] = 0.0; S.cs[1] = 0.0; S.cimax[1] = 0; S.cf2[1] = 0.0; S.cs2[1] = 0.0; S.cimax2[1] = 0; }
+            __syncwarp();
+        }
+        // candidates leave the SM (lanes 0..14: the analysis itself, lanes 16..30: the dual one); see k_pitch_frames for the
+        // exactness argument of the two skip rules
+        const int set = lane >> 4, ctid = lane & 15;
+        if (ctid < MAXCAND && (set == 0 || dual)) {
+            const double vt = set == 0 ? g.vt : p.dual_vt;
+            double uvs = g.sil <= 0 ? 0.0 : 2.0 - inten / (g.sil / (1.0 + vt));
+            uvs = vt + (uvs > 0 ? uvs : 0);
+            const bool frame_stays_unvoiced = uvs > 1.0 + 2.0 * g.vuv_cost * (0.01 / g.dt) + 1e-9;
+            const int nc = set == 0 ? ncand : ncand2;
+            const double* scf = set == 0 ? S.cf : S.cf2;
+            const double* scs = set == 0 ? S.cs : S.cs2;
+            const int* sci = set == 0 ? S.cimax : S.cimax2;
+            const int ci = ctid + 1;
+            double fr = 0.0, stn = 0.0;
+            int im = 0;
+            if (ci <= nc) { fr = scf[ci]; stn = scs[ci]; im = sci[ci]; }
+            const size_t o2 = (size_t)f * MAXCAND + ctid;
+            if (set == 0) { p.cand_f[o2] = fr; p.cand_s[o2] = stn; p.cand_imax[o2] = (unsigned short)im; }
+            else { p.dual_cand_f[o2] = fr; p.dual_cand_s[o2] = stn; p.dual_cand_imax[o2] = (unsigned short)im; }
+            const bool live = ci >= 2 && ci <= nc && (1.0 / dx / (double)(im + 1) < g.ceiling) && !frame_stays_unvoiced;
+            if (live) {
+                if (set == 0) { int slot = atomicAdd(p.qcount, 1); p.queue[slot] = f * 16 + ctid; }
+                else { int slot = atomicAdd(p.dual_qcount, 1); p.dual_queue[slot] = f * 16 + ctid; }
+            }
+        }
+        if (lane == 0) {
+            p.ncand[f] = (uint8_t)ncand;
+            if (dual) { p.dual_ncand[f] = (uint8_t)ncand2; p.dual_inten[f] = inten; }
+        }
+        __syncwarp();
     }
 }
 
@@ -378,20 +367,24 @@ __global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant
 bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw, const double2* twb512, const double2* twb1024,
                            long long total_elems, int max_frames_hint, cudaStream_t s) {
     int span = 0;
+    size_t region = 0;
     for (int k = 0; k < 3; k++) {
         const PitchCfg& g = p.cfg[k];
         if (g.method != 0 || (g.M != 512 && g.M != 1024)) return false;
+        const int Lk = g.M / 32;
+        if (g.brent_ixmax / 2 >= 12 * Lk || (g.nsamp_window & 1)) return false;           // read-out loop covers r < 12
         const int Bs = g.brent_ixmax < g.maximumLag + 32 ? g.brent_ixmax : g.maximumLag + 32;
         int pkcap = g.maximumLag / 2 + 2;
         if (pkcap > 320) pkcap = 320;
         const size_t need = (((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15) + (size_t)pkcap * 24 + 6 * 128 + (((size_t)pkcap * 4 + 15) & ~(size_t)15) +
                             2 * 64 + 16 + 64;
-        if (need > (size_t)ACW_XCH_BYTES / (g.M == 1024 ? 1 : 2)) return false;
+        if (need > region) region = need;
         const int reach = g.halfnsamp_window > g.nsamp_period ? g.halfnsamp_window : g.nsamp_period;
         const int hop = (int)ceil(g.dt / c.dx) + 1;
         const int sp = 2 * reach + 2 + (ACW_TURN - 1) * hop + 16;
         if (sp > span) span = sp;
     }
+    region = (region + 127) & ~(size_t)127;
     AcwParams A;
     A.esz = c.pcm.p64 ? 8 : 2;
     A.pcm_bytes = c.pcm.p64 ? (const unsigned char*)c.pcm.p64 : (const unsigned char*)c.pcm.p16;
@@ -399,7 +392,7 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
     A.stage_bytes = (span * A.esz + 32 + 127) & ~127;
     A.twb512 = twb512; A.twb1024 = twb1024;
     const size_t smem = (size_t)ACW_WARPS * ACW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
-    if (smem > 110 * 1024) return false;
+    if (smem > 110 * 1024 || region * ACC_WARPS > 200 * 1024) return false;
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
     cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
     if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
@@ -413,5 +406,17 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
     if (max_frames_hint > 0 && grid > nturn) grid = nturn;
     if (grid < 1) grid = 1;
     k_ac_frames_w<<<grid, ACW_NT, smem, s>>>(c, p, A, tw);
+    // candidates: one warp per frame, as many warps per SM as the scratch allows
+    const size_t smem2 = region * ACC_WARPS;
+    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int occ2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ac_candidates, 32 * ACC_WARPS, smem2);
+    if (occ2 < 1) occ2 = 1;
+    int grid2 = sm_count() * occ2;
+    const int need_blocks = (max_frames_hint + ACC_WARPS - 1) / ACC_WARPS;
+    if (max_frames_hint > 0 && grid2 > need_blocks) grid2 = need_blocks;
+    if (grid2 < 1) grid2 = 1;
+    k_ac_candidates<<<grid2, 32 * ACC_WARPS, smem2, s>>>(c, p, tw, (int)region);
     return true;
 }

@@ -67,6 +67,21 @@ def test_parity_with_oracle_on_ragged_batch(ex, orc):
     assert np.array_equal(got[:, SPEECHRATE], want[:, SPEECHRATE])
 
 
+def test_parity_on_stress_clips_with_short_bursts_and_gaps(ex, orc):
+    """"stress" clips (synth.py): sounding / silent intervals below the 0.1 s / 0.3 s minima that the silence detector must cut
+    and merge, voiced runs whose +-50 ms extensions overlap, 30 % unvoiced syllables -- the decisions the plain clips never
+    reach (tests/golden/appc_sensitivity.md shows they move Pause_Rate and CPP when read differently)."""
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    clips = [synth_clip(700 + i, d, style="stress").numpy() for i, d in enumerate([8.0, 5.00006, 11.0, 6.5])]
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    got, st = ex.extract_host(pcm, off)
+    want, wst = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
+    assert_features_close(got, want, "stress clips")
+    assert np.array_equal(st, wst)
+    assert np.array_equal(got[:, SPEECHRATE], want[:, SPEECHRATE])
+
+
 def test_stage_level_parity(ex, orc):
     pcm, off, clips = _batch([5.0, 4.00006], start=40)
     ex.extract_host(pcm, off)
