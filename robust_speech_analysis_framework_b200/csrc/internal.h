@@ -262,7 +262,7 @@ struct CepSeg {                // one cepstrogram (host-built from the segment l
 void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, cudaStream_t s);
 void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
                         const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames,
-                        const double* wtab, int wtab_n, cudaStream_t s);
+                        const double* wtab, int wtab_n, cudaStream_t s, const double2* twb512 = nullptr, int* turn_counter = nullptr);
 void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s);
 void launch_cpp_reduce(const Clips& c, const CppSegs& sg, const int* seg_prefix, const int* fprefix, const double* cpp_frame,

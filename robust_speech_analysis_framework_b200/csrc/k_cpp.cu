@@ -14,6 +14,8 @@
 #define NT_CEP_DEFAULT 128
 #include "common.cuh"
 #include "fft.cuh"
+#include "num.cuh"
+#include "fftwarp.cuh"
 
 // ------------------------------------------------------------------------------------------------ V segments
 __global__ void k_vuv_segments(Clips c, PulseSet ps, CppSegs sg, double maxT, double meanT) {
@@ -62,7 +64,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
                                                       const ResampleJob* __restrict__ jobs, const double* __restrict__ sig,
                                                       const double2* __restrict__ tw, double emphasis, double dt,
                                                       double* __restrict__ cep, int nqmax, const double* __restrict__ wtab,
-                                                      int wtab_n) {
+                                                      int wtab_n, int skip_nfft /* frames of this transform size were done by k_cepstrogram_w */) {
     extern __shared__ __align__(16) unsigned char smem[];
     double2* a = (double2*)smem;                      // 512 complex
     double* red = (double*)(smem + sizeof(double2) * 512);
@@ -76,6 +78,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
         __syncthreads();
         const int sgi = s_seg;
         const CepSeg S = segs[sgi];
+        if (S.nfft == skip_nfft) continue;
         const ResampleJob J = jobs[sgi];
         const double* y = sig + J.out_off - 1;                                  // 1-based resampled segment
         const int iframe = f - fprefix[sgi];
@@ -118,6 +121,99 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
             // c[i] for i <= M: natural order ar[i]; c[M] = ar[M] exists since M < nfft
             double cv = ar[SWZD(i)];
             row[i] = cv * cv;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ warp-per-frame version
+// Round 2: half a warp per cepstrogram frame of the usual 1024-point transform (16 lanes x 32 register-resident complex
+// points, fftwarp.cuh fw_roundtrip with G = log power): pre-emphasis, mean, Gaussian window, FFT, log, inverse FFT and the
+// squared cepstrum without a block barrier.  Frames of shorter segments (other transform sizes) stay on k_cepstrogram.
+#define CEW_WARPS 4
+struct CewLog {
+    double dx2, df;
+    __device__ __forceinline__ double operator()(double p) const { return log(p * dx2 + 1e-300) * df; }
+};
+__global__ void __launch_bounds__(32 * CEW_WARPS, 2) k_cepstrogram_w(const CepSeg* __restrict__ segs, const int* __restrict__ fprefix, int nsegs,
+                                                                     const ResampleJob* __restrict__ jobs, const double* __restrict__ sig,
+                                                                     const double2* __restrict__ tw, const double2* __restrict__ twb512,
+                                                                     double emphasis, double dt, double* __restrict__ cep, int nqmax,
+                                                                     const double* __restrict__ wtab, int wtab_n, int* __restrict__ turn_counter) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int L = 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 15, gidx = lane >> 4;
+    const unsigned gmask = 0xffffu << (16 * gidx);
+    double2* xch = (double2*)(smem + (size_t)warp * (1024 * 16) + (size_t)gidx * (512 * 16));
+    const int total = fprefix[nsegs];
+    const double2 wj = __ldg(tw + j * (TW_N / 1024));
+    // a warp takes two consecutive frames per turn (neighbouring frames share 98 % of their samples: L1 hits)
+    for (;;) {
+        int turn = 0;
+        if (lane == 0) turn = atomicAdd(turn_counter, 1);
+        turn = __shfl_sync(FULL_MASK, turn, 0);
+        if (2 * turn >= total) break;
+        const int f = 2 * turn + gidx;
+        bool active = f < total;
+        int sgi = 0;
+        if (active) sgi = find_segment(fprefix, nsegs, f);
+        const CepSeg S = segs[sgi];
+        if (S.nfft != 1024) active = false;                                      // done by k_cepstrogram
+        if (__ballot_sync(FULL_MASK, active) == 0u) continue;
+        const ResampleJob J = jobs[sgi];
+        const double* y = sig + J.out_off - 1;                                   // 1-based resampled segment
+        const int iframe = f - fprefix[sgi];
+        const double t = S.t1 + (double)iframe * dt;
+        const long long index = x_to_nearest(J.out_x1, J.out_dx, t - S.windowDuration / 2);    // Sound_into_Sound
+        const int nwin = S.nwin;
+        double2 a[32];
+        double acc = 0.0;
+        fr_static_for<0, 32>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const int m = 2 * (j + L * k);
+            double v0 = 0.0, v1 = 0.0;
+            if (active && m < nwin) {
+                const long long jj = index + m;                                  // 1-based sample of frame element m
+                const double ym = (jj - 1 >= 1 && jj - 1 <= J.nout) ? __ldg(y + jj - 1) : 0.0;
+                const double y0 = (jj >= 1 && jj <= J.nout) ? __ldg(y + jj) : 0.0;
+                const double y1 = (jj + 1 >= 1 && jj + 1 <= J.nout) ? __ldg(y + jj + 1) : 0.0;
+                if (jj >= 1 && jj <= J.nout) v0 = jj >= 2 ? y0 - emphasis * ym : y0;              // Sound_preEmphasis
+                if (m + 1 < nwin && jj + 1 >= 1 && jj + 1 <= J.nout) v1 = jj + 1 >= 2 ? y1 - emphasis * y0 : y1;
+            }
+            a[k] = make_double2(v0, v1);
+            acc += v0 + v1;
+        });
+        const double mean = group_sum(acc, gmask, L) / (double)nwin;             // Vector_subtractMean
+        const double imid = 0.5 * (double)(nwin + 1), edge = exp(-12.0);
+        fr_static_for<0, 32>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const int m = 2 * (j + L * k);
+            if (active && m < nwin) {
+                double w0, w1;
+                if (nwin == wtab_n) { w0 = __ldg(wtab + m); w1 = m + 1 < nwin ? __ldg(wtab + m + 1) : 0.0; }
+                else {
+                    const double d0 = (double)(m + 1) - imid, d1 = (double)(m + 2) - imid;
+                    w0 = (exp(-48.0 * d0 * d0 / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
+                    w1 = (exp(-48.0 * d1 * d1 / (double)(nwin + 1) / (double)(nwin + 1)) - edge) / (1.0 - edge);
+                }
+                a[k].x = (a[k].x - mean) * w0;
+                a[k].y = m + 1 < nwin ? (a[k].y - mean) * w1 : 0.0;
+            }
+        });
+        CewLog G;
+        G.dx2 = J.out_dx * J.out_dx;
+        G.df = 1.0 / (J.out_dx * 1024.0);
+        fw_roundtrip(a, xch, lane, j, L, twb512, wj, G);
+        // a[brev5(r)] = conj(y[n]), n = j + 16 r: cepstrum c[2n] = re, c[2n+1] = -im; the power cepstrum keeps c^2 for quefrency bins 0..512
+        if (active) {
+            double* row = cep + (size_t)f * nqmax;
+            fr_static_for<0, 17>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const int n = j + L * r;
+                const double2 v = a[fr_brev(r, 5)];
+                if (2 * n <= 512) row[2 * n] = v.x * v.x;
+                if (2 * n + 1 <= 512) row[2 * n + 1] = v.y * v.y;
+            });
         }
     }
 }
@@ -555,14 +651,31 @@ void launch_vuv_segments(const Clips& c, const PulseSet& ps, const CppSegs& sg, 
 }
 void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const ResampleJob* jobs, const double* sig,
                         const double2* tw, double emphasis, double dt, double* cep, int nqmax, int total_frames,
-                        const double* wtab, int wtab_n, cudaStream_t s) {
+                        const double* wtab, int wtab_n, cudaStream_t s, const double2* twb512, int* turn_counter) {
+    int skip = 0;
+    if (twb512 && turn_counter && nqmax >= 513) {
+        // frames of the usual 1024-point transform: warp-per-frame register FFT; the rest (short segments) below
+        cudaMemsetAsync(turn_counter, 0, sizeof(int), s);
+        const size_t smem_w = (size_t)CEW_WARPS * 1024 * 16;
+        cudaFuncSetAttribute(k_cepstrogram_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cepstrogram_w, 32 * CEW_WARPS, smem_w);
+        if (occ < 1) occ = 1;
+        int gw = sm_count() * occ;
+        const int nt2 = (total_frames + 2 * CEW_WARPS - 1) / (2 * CEW_WARPS);
+        if (gw > nt2) gw = nt2;
+        if (gw < 1) gw = 1;
+        k_cepstrogram_w<<<gw, 32 * CEW_WARPS, smem_w, s>>>(segs, fprefix, nsegs, jobs, sig, tw, twb512, emphasis, dt, cep, nqmax, wtab, wtab_n,
+                                                         turn_counter);
+        skip = 1024;
+    }
     static int nt = 0;
     if (!nt) { const char* e = getenv("MSHDS_NT_CEP"); nt = e && atoi(e) == 256 ? 256 : (e && atoi(e) == 128 ? 128 : NT_CEP_DEFAULT); }   // development switch
     const int cap = nt == 128 ? sm_count() * 12 : sm_count() * 8;
     int grid = total_frames < cap ? total_frames : cap;
     if (grid < 1) grid = 1;
     size_t smem = sizeof(double2) * 512 + sizeof(double) * 32;
-    k_cepstrogram<<<grid, nt, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax, wtab, wtab_n);
+    k_cepstrogram<<<grid, nt, smem, s>>>(segs, fprefix, nsegs, jobs, sig, tw, emphasis, dt, cep, nqmax, wtab, wtab_n, skip);
 }
 void launch_cpp_frames(const CepSeg* segs, const int* fprefix, int nsegs, const double* cep, int nqmax, int nTimeAvg,
                        double qAvgWindow, double* cpp_frame, int total_frames, cudaStream_t s) {

@@ -517,6 +517,7 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     size_t o_tile = sz(sizeof(int) * (nsegs + 2));
     size_t o_cseg = sz(sizeof(CepSeg) * (nsegs + 1)), o_fpre = sz(sizeof(int) * (nsegs + 2));
     size_t o_cep = sz(sizeof(double) * ((size_t)totalFrames * nqmax + 1)), o_cppf = sz(sizeof(double) * ((size_t)totalFrames + 1));
+    size_t o_turn = sz(sizeof(int) * 4);
     if (need > h->cpp_cap) {
         CK(cudaStreamSynchronize(s));
         if (h->cpp_buf) CK(cudaFree(h->cpp_buf));
@@ -534,6 +535,7 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
     int* d_fprefix = (int*)(B + o_fpre);
     double* d_cep = (double*)(B + o_cep);
     double* d_cppf = (double*)(B + o_cppf);
+    int* cep_turn = (int*)(B + o_turn);
     if (nsegs > 0) {
         int rc = upload_plan(h, plan, D, s);
         if (rc) return rc;
@@ -545,7 +547,8 @@ static int run_cpp_stage(mshds_handle* h, const Clips& c, const std::vector<long
         const double emphasis = exp(-2.0 * MSHDS_PI * 50.0 * (1.0 / fs10));
         const double* cep_win = nullptr;                 // same formula as the formant window (Sound_createGaussian)
         { int rcw = make_formant_window(h, 1000, &cep_win); if (rcw) return rcw; }
-        PB("cepstrogram_frames"); launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, cep_win, 1000, s); h->launches += 1; PE();
+        PB("cepstrogram_frames"); launch_cepstrogram(d_cseg, d_fprefix, nsegs, D.jobs, D.out, h->tw, emphasis, dt, d_cep, nqmax, totalFrames, cep_win, 1000, s,
+                                                      h->legacy_fft ? nullptr : h->twb512, cep_turn); h->launches += 2; PE();
         const int nTimeAvg = (int)floor(0.01 / dt);
         PB("cpps_frames"); launch_cpp_frames(d_cseg, d_fprefix, nsegs, d_cep, nqmax, nTimeAvg, 0.001, d_cppf, totalFrames, s); h->launches += 1; PE();
     }
