@@ -721,7 +721,15 @@ void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint,
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi
-// fon/Pitch.cpp Pitch_pathFinder: one warp per clip, lane = current candidate, sequential over frames.
+// fon/Pitch.cpp Pitch_pathFinder: one warp per clip, sequential over frames (the recurrence is evaluated with exactly the
+// reference's operation order: value = (delta[c1] - cost) + score, first maximum wins).
+//
+// Latency matters here: a 60 s recording is a chain of 12,000 dependent steps and nothing else runs when the batch is one
+// clip (BASELINE.json configs[0]).  Round 1 walked the <= 15 previous candidates in a serial compare chain (~800 cycles per
+// frame).  Now lane = (current candidate c2, half h): the two halves of the warp take previous candidates 0..7 and 8..14,
+// every lane forms its 8 values independently (instruction-level parallelism instead of a dependent chain), reduces them
+// with a tournament whose ties go to the lower index (= the first maximum of the sequential scan), and one shuffle joins
+// the halves (ties go to half 0).  ~5x fewer cycles per frame, bit-identical back-pointers.
 __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
     const int lane = threadIdx.x & 31;
     const int clip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -732,40 +740,67 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
     const PitchCfg& g = p.cfg[c.cls[clip]];
     const double corr = 0.01 / g.dt;
     const double jumpCost = g.jump_cost * corr, vuvCost = g.vuv_cost * corr;
+    const int c2 = lane & 15, half = lane >> 4;            // lanes 15 and 31 idle (MAXCAND = 15)
+    const int cbase = half * 8;                            // previous candidates cbase .. cbase + 7
 
-    double delta = -1e300, lf = -1.0;
+    double delta = -1e300, lf = -1.0;                      // state of candidate c2 of the previous frame (both halves hold a copy)
     int ncPrev = 0;
     // software pipeline: the candidate row of frame i+1 is in flight while frame i is resolved
     double nsc = -1e300, nclf = -1.0;
     int nnc = p.ncand[f0];
-    if (lane < MAXCAND) { nsc = p.cand_score[(size_t)f0 * MAXCAND + lane]; nclf = p.cand_lf[(size_t)f0 * MAXCAND + lane]; }
+    if (c2 < MAXCAND) { nsc = p.cand_score[(size_t)f0 * MAXCAND + c2]; nclf = p.cand_lf[(size_t)f0 * MAXCAND + c2]; }
     for (int i = 0; i < nF; i++) {
         const size_t fo = (size_t)(f0 + i);
         const int nc = nnc;
         const double sc = nsc, clf = nclf;
         if (i + 1 < nF) {
             nnc = p.ncand[fo + 1];
-            if (lane < MAXCAND) { nsc = p.cand_score[(fo + 1) * MAXCAND + lane]; nclf = p.cand_lf[(fo + 1) * MAXCAND + lane]; }
+            if (c2 < MAXCAND) { nsc = p.cand_score[(fo + 1) * MAXCAND + c2]; nclf = p.cand_lf[(fo + 1) * MAXCAND + c2]; }
         }
         if (i == 0) {
             delta = sc; lf = clf; ncPrev = nc;
             continue;
         }
         const bool curVoiceless = clf < 0.0;
-        double maximum = -1e30;
-        int place = 0;
-        for (int c1 = 0; c1 < ncPrev; c1++) {
-            double pd = __shfl_sync(FULL_MASK, delta, c1);
-            double plf = __shfl_sync(FULL_MASK, lf, c1);
-            bool prevVoiceless = plf < 0.0;
+        // the 8 previous candidates of this half: values formed independently, then a tournament (ties -> lower index)
+        double val[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c1 = cbase + k;
+            const double pd = __shfl_sync(FULL_MASK, delta, c1 & 15);          // lane c1 of half 0 holds candidate c1
+            const double plf = __shfl_sync(FULL_MASK, lf, c1 & 15);
+            const bool prevVoiceless = plf < 0.0;
             double cost;
             if (curVoiceless) cost = prevVoiceless ? 0.0 : vuvCost;
             else cost = prevVoiceless ? vuvCost : jumpCost * fabs(plf - clf);
-            double value = pd - cost + sc;
-            if (value > maximum) { maximum = value; place = c1; }
+            const double value = pd - cost + sc;
+            // candidates beyond ncPrev do not exist; the sequential scan starts from maximum = -1e30 and takes strictly larger values
+            val[k] = (c1 < ncPrev && value > -1e30) ? value : -1e30;
         }
-        if (lane < MAXCAND) p.psi[fo * 16 + lane] = (uint8_t)place;
-        delta = lane < nc ? maximum : -1e300;
+        int idx[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) idx[k] = cbase + k;
+#pragma unroll
+        for (int st = 1; st < 8; st <<= 1) {
+#pragma unroll
+            for (int k = 0; k + st < 8; k += 2 * st) {
+                const bool takeRight = val[k + st] > val[k];                       // tie: keep the lower index
+                val[k] = takeRight ? val[k + st] : val[k];
+                idx[k] = takeRight ? idx[k + st] : idx[k];
+            }
+        }
+        double maximum = val[0];
+        int place = idx[0];
+        {   // join the halves: half 1 wins only with a strictly larger value
+            const double om = __shfl_xor_sync(FULL_MASK, maximum, 16);
+            const int op = __shfl_xor_sync(FULL_MASK, place, 16);
+            const bool other_is_high = half == 0;                                  // my partner holds the higher candidate indices
+            const bool takeOther = other_is_high ? (om > maximum) : !(maximum > om);
+            if (takeOther) { maximum = om; place = op; }
+        }
+        if (maximum <= -1e30) place = 0;                                           // no candidate beat the initial maximum: place stays 0
+        if (half == 0 && c2 < MAXCAND) p.psi[fo * 16 + c2] = (uint8_t)place;
+        delta = c2 < nc ? maximum : -1e300;
         lf = clf;
         ncPrev = nc;
     }
@@ -784,12 +819,10 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
         int lo = hi - 31 < 0 ? 0 : hi - 31;
         int myFrame = hi - lane;                                // lane 0 = frame hi
         unsigned long long r0 = 0, r1 = 0;
-        double sf[1];
         if (myFrame >= lo && myFrame >= 1) {
             const unsigned long long* row = (const unsigned long long*)(p.psi + (size_t)(f0 + myFrame) * 16);
             r0 = row[0]; r1 = row[1];
         }
-        (void)sf;
         int myPlace = 0;
         for (int l = 0; l <= hi - lo; l++) {
             if (lane == l) myPlace = place;

@@ -206,14 +206,20 @@ __device__ double find_max_corr_warp(const WarpSound& S, double t1, double windo
 }
 
 // ------------------------------------------------------------------------------------------------ per-stretch walk
+// Work item = (voiced stretch, direction): the left and the right walk of a stretch start from the same first pulse and do
+// not depend on each other (the only coupling, the `addedRight` guard, is applied afterwards per clip), so they run on two
+// warps -- half the latency of the longest chain, which is what a batch of few long recordings waits for.  Raw points of
+// a stretch: left walk at raw[2 * region .. + cap), first pulse + right walk at raw[2 * region + cap .. + cap).
 __global__ void __launch_bounds__(PW * 32) k_pulses_stretch(Clips c, PitchPass p, PulseSet ps) {
     __shared__ double s_stage[PW][SPAN_MAX];
     __shared__ double s_r[PW][OFF_MAX + 4];
     __shared__ double s_p[PW][OFF_MAX + 4];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * PW + wib, nw = gridDim.x * PW;
-    const int total = ps.st_start[c.n];
-    for (int w = gw; w < total; w += nw) {
+    const int total = 2 * ps.st_start[c.n];
+    for (int w2 = gw; w2 < total; w2 += nw) {
+        const int w = w2 >> 1;
+        const bool go_right = (w2 & 1) != 0;
         const int clip = find_segment(ps.st_start, c.n, w);
         const int k = w - ps.st_start[clip];
         const int slot = p.fstart[clip] + k;
@@ -239,8 +245,8 @@ __global__ void __launch_bounds__(PW * 32) k_pulses_stretch(Clips c, PitchPass p
         const double cprime = ps.cprime;
         const long long region = (long long)ps.cap_start[clip] + (long long)floor(tleft * cprime) + 8LL * k;
         const int cap = (int)floor((tright - tleft) * cprime) + 8;
-        double* rt = ps.raw_t + region;
-        double* rthr = ps.raw_thr + region;
+        double* rt = ps.raw_t + 2 * region + (go_right ? cap : 0);
+        double* rthr = ps.raw_thr + 2 * region;
         int nl = 0, nr = 0;
         double addedRight = -1e308;
 
@@ -250,51 +256,55 @@ __global__ void __launch_bounds__(PW * 32) k_pulses_stretch(Clips c, PitchPass p
             double tmax = find_extremum_warp(S, tmiddle - 0.5 / f0middle, tmiddle + 0.5 / f0middle, lane);
             const double tsave = tmax;
             double peak;
-            // walk left
-            for (;;) {
-                double f0 = pitch_value_at(pv, tmax);
-                if (is_undef(f0)) break;
-                double tnew = tmax;
-                double correlation = find_max_corr_warp(S, tmax, 1.0 / f0, tmax - 1.25 / f0, tmax - 0.8 / f0, &tnew, &peak, lane);
-                tmax = tnew;
-                if (correlation == -1.0) tmax -= 1.0 / f0;
-                if (tmax < tleft) {
-                    if (correlation > 0.7 && peak > 0.023333 * globalPeak) {
-                        if (nl + 1 < cap) { if (lane == 0) { rt[nl] = tmax; rthr[nl] = 0.8 / f0; } nl++; }
+            if (!go_right) {
+                for (;;) {
+                    double f0 = pitch_value_at(pv, tmax);
+                    if (is_undef(f0)) break;
+                    double tnew = tmax;
+                    double correlation = find_max_corr_warp(S, tmax, 1.0 / f0, tmax - 1.25 / f0, tmax - 0.8 / f0, &tnew, &peak, lane);
+                    tmax = tnew;
+                    if (correlation == -1.0) tmax -= 1.0 / f0;
+                    if (tmax < tleft) {
+                        if (correlation > 0.7 && peak > 0.023333 * globalPeak) {
+                            if (nl < cap) { if (lane == 0) { rt[nl] = tmax; rthr[nl] = 0.8 / f0; } nl++; }
+                        }
+                        break;
                     }
-                    break;
-                }
-                if (correlation > 0.3 && (peak == 0.0 || peak > 0.01 * globalPeak)) {
-                    if (nl + 1 < cap) { if (lane == 0) { rt[nl] = tmax; rthr[nl] = 0.8 / f0; } nl++; }
-                }
-            }
-            // first point, then walk right
-            if (lane == 0) rt[nl] = tsave;
-            nr = 1;
-            tmax = tsave;
-            for (;;) {
-                double f0 = pitch_value_at(pv, tmax);
-                if (is_undef(f0)) break;
-                double tnew = tmax;
-                double correlation = find_max_corr_warp(S, tmax, 1.0 / f0, tmax + 0.8 / f0, tmax + 1.25 / f0, &tnew, &peak, lane);
-                tmax = tnew;
-                if (correlation == -1.0) tmax += 1.0 / f0;
-                if (tmax > tright) {
-                    if (correlation > 0.7 && peak > 0.023333 * globalPeak) {
-                        if (nl + nr < cap) { if (lane == 0) rt[nl + nr] = tmax; nr++; addedRight = tmax; }
+                    if (correlation > 0.3 && (peak == 0.0 || peak > 0.01 * globalPeak)) {
+                        if (nl < cap) { if (lane == 0) { rt[nl] = tmax; rthr[nl] = 0.8 / f0; } nl++; }
                     }
-                    break;
                 }
-                if (correlation > 0.3 && (peak == 0.0 || peak > 0.01 * globalPeak)) {
-                    if (nl + nr < cap) { if (lane == 0) rt[nl + nr] = tmax; nr++; addedRight = tmax; }
+            } else {
+                // first point, then walk right
+                if (lane == 0) rt[0] = tsave;
+                nr = 1;
+                for (;;) {
+                    double f0 = pitch_value_at(pv, tmax);
+                    if (is_undef(f0)) break;
+                    double tnew = tmax;
+                    double correlation = find_max_corr_warp(S, tmax, 1.0 / f0, tmax + 0.8 / f0, tmax + 1.25 / f0, &tnew, &peak, lane);
+                    tmax = tnew;
+                    if (correlation == -1.0) tmax += 1.0 / f0;
+                    if (tmax > tright) {
+                        if (correlation > 0.7 && peak > 0.023333 * globalPeak) {
+                            if (nr < cap) { if (lane == 0) rt[nr] = tmax; nr++; addedRight = tmax; }
+                        }
+                        break;
+                    }
+                    if (correlation > 0.3 && (peak == 0.0 || peak > 0.01 * globalPeak)) {
+                        if (nr < cap) { if (lane == 0) rt[nr] = tmax; nr++; addedRight = tmax; }
+                    }
                 }
             }
         }
         if (lane == 0) {
-            ps.raw_nleft[slot] = nl;
-            ps.raw_nright[slot] = nr;
-            ps.raw_added_right[slot] = addedRight;
-            ps.raw_region[slot] = region;
+            if (!go_right) {
+                ps.raw_nleft[slot] = nl;
+                ps.raw_region[slot] = 2 * region + ((long long)cap << 40);
+            } else {
+                ps.raw_nright[slot] = nr;
+                ps.raw_added_right[slot] = addedRight;
+            }
         }
     }
 }
@@ -312,13 +322,16 @@ __global__ void k_pulses_assemble(Clips c, PitchPass p, PulseSet ps) {
     double addedRight = -1e308;
     for (int k = 0; k < ns; k++) {
         const int slot = f0 + k;
-        const double* rt = ps.raw_t + ps.raw_region[slot];
-        const double* rthr = ps.raw_thr + ps.raw_region[slot];
+        const long long packed = ps.raw_region[slot];
+        const long long region2 = packed & ((1LL << 40) - 1);
+        const int cap = (int)(packed >> 40);
+        const double* rt = ps.raw_t + region2;
+        const double* rthr = ps.raw_thr + region2;
         const int nl = ps.raw_nleft[slot], nr = ps.raw_nright[slot];
         const int first = n;
         for (int i = nl - 1; i >= 0; i--)
             if (rt[i] - addedRight > rthr[i]) out[n++] = rt[i];
-        for (int i = 0; i < nr; i++) out[n++] = rt[nl + i];
+        for (int i = 0; i < nr; i++) out[n++] = rt[cap + i];
         double ar = ps.raw_added_right[slot];
         if (ar != -1e308) addedRight = ar;
         // sorted insertion of the new points (only the seam with the previous stretch can be out of order)

@@ -673,7 +673,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     memset(&pl_lt, 0, sizeof pl_lt);
     pl_lt.cprime = cprime;
     int* d_pcap = take<int>(h, n + 1);
-    double* raw_t = take<double>(h, ptotal); double* raw_thr = take<double>(h, ptotal);
+    double* raw_t = take<double>(h, 2 * ptotal); double* raw_thr = take<double>(h, 2 * ptotal);      // left / right walk halves
     int* st_il = take<int>(h, fub5); int* st_ir = take<int>(h, fub5);
     int* raw_nl = take<int>(h, fub5); int* raw_nr = take<int>(h, fub5);
     double* raw_ar = take<double>(h, fub5); long long* raw_reg = take<long long>(h, fub5);
