@@ -745,64 +745,82 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
 
     double delta = -1e300, lf = -1.0;                      // state of candidate c2 of the previous frame (both halves hold a copy)
     int ncPrev = 0;
-    // software pipeline: the candidate row of frame i+1 is in flight while frame i is resolved
-    double nsc = -1e300, nclf = -1.0;
-    int nnc = p.ncand[f0];
-    if (c2 < MAXCAND) { nsc = p.cand_score[(size_t)f0 * MAXCAND + c2]; nclf = p.cand_lf[(size_t)f0 * MAXCAND + c2]; }
-    for (int i = 0; i < nF; i++) {
-        const size_t fo = (size_t)(f0 + i);
-        const int nc = nnc;
-        const double sc = nsc, clf = nclf;
-        if (i + 1 < nF) {
-            nnc = p.ncand[fo + 1];
-            if (c2 < MAXCAND) { nsc = p.cand_score[(fo + 1) * MAXCAND + c2]; nclf = p.cand_lf[(fo + 1) * MAXCAND + c2]; }
-        }
-        if (i == 0) {
-            delta = sc; lf = clf; ncPrev = nc;
-            continue;
-        }
-        const bool curVoiceless = clf < 0.0;
-        // the 8 previous candidates of this half: values formed independently, then a tournament (ties -> lower index)
-        double val[8];
+    // The candidate rows are read in tiles of VT frames, one tile ahead: a row that is only one frame ahead arrives after a
+    // DRAM round trip (~1,000 cycles) and sets the pace of the whole chain (measured: 1,080 cycles per frame in round 1).
+    constexpr int VT = 8;
+    double tsc[VT], tlf[VT], nsc[VT], nlf[VT];
+    int tnc[VT], nnc[VT];
+    auto load_tile = [&](int i0, double (&sc_)[VT], double (&lf_)[VT], int (&nc_)[VT]) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int c1 = cbase + k;
-            const double pd = __shfl_sync(FULL_MASK, delta, c1 & 15);          // lane c1 of half 0 holds candidate c1
-            const double plf = __shfl_sync(FULL_MASK, lf, c1 & 15);
-            const bool prevVoiceless = plf < 0.0;
-            double cost;
-            if (curVoiceless) cost = prevVoiceless ? 0.0 : vuvCost;
-            else cost = prevVoiceless ? vuvCost : jumpCost * fabs(plf - clf);
-            const double value = pd - cost + sc;
-            // candidates beyond ncPrev do not exist; the sequential scan starts from maximum = -1e30 and takes strictly larger values
-            val[k] = (c1 < ncPrev && value > -1e30) ? value : -1e30;
-        }
-        int idx[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) idx[k] = cbase + k;
-#pragma unroll
-        for (int st = 1; st < 8; st <<= 1) {
-#pragma unroll
-            for (int k = 0; k + st < 8; k += 2 * st) {
-                const bool takeRight = val[k + st] > val[k];                       // tie: keep the lower index
-                val[k] = takeRight ? val[k + st] : val[k];
-                idx[k] = takeRight ? idx[k + st] : idx[k];
+        for (int u = 0; u < VT; u++) {
+            const int i = i0 + u;
+            sc_[u] = -1e300; lf_[u] = -1.0; nc_[u] = 0;
+            if (i < nF) {
+                const size_t fo = (size_t)(f0 + i);
+                nc_[u] = p.ncand[fo];
+                if (c2 < MAXCAND) { sc_[u] = p.cand_score[fo * MAXCAND + c2]; lf_[u] = p.cand_lf[fo * MAXCAND + c2]; }
             }
         }
-        double maximum = val[0];
-        int place = idx[0];
-        {   // join the halves: half 1 wins only with a strictly larger value
-            const double om = __shfl_xor_sync(FULL_MASK, maximum, 16);
-            const int op = __shfl_xor_sync(FULL_MASK, place, 16);
-            const bool other_is_high = half == 0;                                  // my partner holds the higher candidate indices
-            const bool takeOther = other_is_high ? (om > maximum) : !(maximum > om);
-            if (takeOther) { maximum = om; place = op; }
+    };
+    load_tile(0, nsc, nlf, nnc);
+    for (int i0 = 0; i0 < nF; i0 += VT) {
+#pragma unroll
+        for (int u = 0; u < VT; u++) { tsc[u] = nsc[u]; tlf[u] = nlf[u]; tnc[u] = nnc[u]; }
+        if (i0 + VT < nF) load_tile(i0 + VT, nsc, nlf, nnc);
+#pragma unroll
+        for (int u = 0; u < VT; u++) {
+            const int i = i0 + u;
+            if (i >= nF) break;
+            const size_t fo = (size_t)(f0 + i);
+            const int nc = tnc[u];
+            const double sc = tsc[u], clf = tlf[u];
+            if (i == 0) {
+                delta = sc; lf = clf; ncPrev = nc;
+                continue;
+            }
+            const bool curVoiceless = clf < 0.0;
+            // the 8 previous candidates of this half: values formed independently, then a tournament (ties -> lower index)
+            double val[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c1 = cbase + k;
+                const double pd = __shfl_sync(FULL_MASK, delta, c1 & 15);          // lane c1 of half 0 holds candidate c1
+                const double plf = __shfl_sync(FULL_MASK, lf, c1 & 15);
+                const bool prevVoiceless = plf < 0.0;
+                double cost;
+                if (curVoiceless) cost = prevVoiceless ? 0.0 : vuvCost;
+                else cost = prevVoiceless ? vuvCost : jumpCost * fabs(plf - clf);
+                const double value = pd - cost + sc;
+                // candidates beyond ncPrev do not exist; the sequential scan starts from maximum = -1e30 and takes strictly larger values
+                val[k] = (c1 < ncPrev && value > -1e30) ? value : -1e30;
+            }
+            int idx[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) idx[k] = cbase + k;
+#pragma unroll
+            for (int st = 1; st < 8; st <<= 1) {
+#pragma unroll
+                for (int k = 0; k + st < 8; k += 2 * st) {
+                    const bool takeRight = val[k + st] > val[k];                       // tie: keep the lower index
+                    val[k] = takeRight ? val[k + st] : val[k];
+                    idx[k] = takeRight ? idx[k + st] : idx[k];
+                }
+            }
+            double maximum = val[0];
+            int place = idx[0];
+            {   // join the halves: half 1 wins only with a strictly larger value
+                const double om = __shfl_xor_sync(FULL_MASK, maximum, 16);
+                const int op = __shfl_xor_sync(FULL_MASK, place, 16);
+                const bool other_is_high = half == 0;                                  // my partner holds the higher candidate indices
+                const bool takeOther = other_is_high ? (om > maximum) : !(maximum > om);
+                if (takeOther) { maximum = om; place = op; }
+            }
+            if (maximum <= -1e30) place = 0;                                           // no candidate beat the initial maximum: place stays 0
+            if (half == 0 && c2 < MAXCAND) p.psi[fo * 16 + c2] = (uint8_t)place;
+            delta = c2 < nc ? maximum : -1e300;
+            lf = clf;
+            ncPrev = nc;
         }
-        if (maximum <= -1e30) place = 0;                                           // no candidate beat the initial maximum: place stays 0
-        if (half == 0 && c2 < MAXCAND) p.psi[fo * 16 + c2] = (uint8_t)place;
-        delta = c2 < nc ? maximum : -1e300;
-        lf = clf;
-        ncPrev = nc;
     }
     // end of the most probable path: first maximum over the last frame's candidates
     int place = 0;
