@@ -721,33 +721,33 @@ void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint,
 }
 
 // ------------------------------------------------------------------------------------------------ Viterbi
-// fon/Pitch.cpp Pitch_pathFinder: one warp per clip, sequential over frames (the recurrence is evaluated with exactly the
-// reference's operation order: value = (delta[c1] - cost) + score, first maximum wins).
+// fon/Pitch.cpp Pitch_pathFinder.  The recurrence is evaluated with exactly the reference's arithmetic,
+// value = (delta[c1] - cost) + score, and its tie rule (the first maximum wins), so the back-pointers are bit-identical to
+// a sequential float64 loop.
 //
 // Latency matters here: a 60 s recording is a chain of 12,000 dependent steps and nothing else runs when the batch is one
-// clip (BASELINE.json configs[0]).  Round 1 walked the <= 15 previous candidates in a serial compare chain (~800 cycles per
-// frame).  Now lane = (current candidate c2, half h): the two halves of the warp take previous candidates 0..7 and 8..14,
-// every lane forms its 8 values independently (instruction-level parallelism instead of a dependent chain), reduces them
-// with a tournament whose ties go to the lower index (= the first maximum of the sequential scan), and one shuffle joins
-// the halves (ties go to half 0).  ~5x fewer cycles per frame, bit-identical back-pointers.
-__global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
-    const int lane = threadIdx.x & 31;
-    const int clip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (clip >= c.n) return;
+// clip (BASELINE.json configs[0]).  Round 1 used one warp per clip with a serial compare chain over the <= 15 previous
+// candidates: 1,080 cycles per frame; a warp-level rewrite with more instruction-level parallelism did not help -- ncu
+// showed a single warp issuing one instruction every 5 cycles, i.e. the step is instruction-count bound (335 per frame).
+// Now ONE CTA of 256 threads owns a clip: thread (c2, c1) = (tid / 16, tid % 16) forms the one value of its candidate
+// pair, the 16 lanes of a half-warp reduce over c1 with four shuffle steps (ties go to the lower index), the state lives in
+// double-buffered shared memory and each frame costs one block barrier.  Candidate rows are prefetched in register tiles
+// of 4 frames.  The total thread-instruction count per frame is what the warp version spent on idle and duplicated lanes.
+#define VIT_NT 256
+__global__ void __launch_bounds__(VIT_NT, 4) k_pitch_viterbi(Clips c, PitchPass p) {
+    __shared__ double s_delta[2][16], s_lf[2][16];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int clip = blockIdx.x;
     const int nF = p.nF[clip];
     if (nF < 1) return;
     const int f0 = p.fstart[clip];
     const PitchCfg& g = p.cfg[c.cls[clip]];
     const double corr = 0.01 / g.dt;
     const double jumpCost = g.jump_cost * corr, vuvCost = g.vuv_cost * corr;
-    const int c2 = lane & 15, half = lane >> 4;            // lanes 15 and 31 idle (MAXCAND = 15)
-    const int cbase = half * 8;                            // previous candidates cbase .. cbase + 7
+    const int c2 = tid >> 4, c1 = tid & 15;                 // c2 == 15 and c1 == 15 are idle (MAXCAND = 15)
+    const unsigned hmask = 0xffffu << (lane & 16);          // the half-warp that shares this c2
 
-    double delta = -1e300, lf = -1.0;                      // state of candidate c2 of the previous frame (both halves hold a copy)
-    int ncPrev = 0;
-    // The candidate rows are read in tiles of VT frames, one tile ahead: a row that is only one frame ahead arrives after a
-    // DRAM round trip (~1,000 cycles) and sets the pace of the whole chain (measured: 1,080 cycles per frame in round 1).
-    constexpr int VT = 8;
+    constexpr int VT = 4;
     double tsc[VT], tlf[VT], nsc[VT], nlf[VT];
     int tnc[VT], nnc[VT];
     auto load_tile = [&](int i0, double (&sc_)[VT], double (&lf_)[VT], int (&nc_)[VT]) {
@@ -763,6 +763,7 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
         }
     };
     load_tile(0, nsc, nlf, nnc);
+    int cur = 0, ncPrev = 0;
     for (int i0 = 0; i0 < nF; i0 += VT) {
 #pragma unroll
         for (int u = 0; u < VT; u++) { tsc[u] = nsc[u]; tlf[u] = nlf[u]; tnc[u] = nnc[u]; }
@@ -775,59 +776,44 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
             const int nc = tnc[u];
             const double sc = tsc[u], clf = tlf[u];
             if (i == 0) {
-                delta = sc; lf = clf; ncPrev = nc;
+                if (c1 == 0) { s_delta[cur][c2] = sc; s_lf[cur][c2] = clf; }
+                ncPrev = nc;
+                __syncthreads();
                 continue;
             }
-            const bool curVoiceless = clf < 0.0;
-            // the 8 previous candidates of this half: values formed independently, then a tournament (ties -> lower index)
-            double val[8];
+            const double pd = s_delta[cur][c1], plf = s_lf[cur][c1];
+            const bool curVoiceless = clf < 0.0, prevVoiceless = plf < 0.0;
+            double cost;
+            if (curVoiceless) cost = prevVoiceless ? 0.0 : vuvCost;
+            else cost = prevVoiceless ? vuvCost : jumpCost * fabs(plf - clf);
+            const double value = pd - cost + sc;
+            // candidates beyond ncPrev do not exist; the sequential scan starts from maximum = -1e30 and only takes larger values
+            double best = (c1 < ncPrev && value > -1e30) ? value : -1e30;
+            int place = c1;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int c1 = cbase + k;
-                const double pd = __shfl_sync(FULL_MASK, delta, c1 & 15);          // lane c1 of half 0 holds candidate c1
-                const double plf = __shfl_sync(FULL_MASK, lf, c1 & 15);
-                const bool prevVoiceless = plf < 0.0;
-                double cost;
-                if (curVoiceless) cost = prevVoiceless ? 0.0 : vuvCost;
-                else cost = prevVoiceless ? vuvCost : jumpCost * fabs(plf - clf);
-                const double value = pd - cost + sc;
-                // candidates beyond ncPrev do not exist; the sequential scan starts from maximum = -1e30 and takes strictly larger values
-                val[k] = (c1 < ncPrev && value > -1e30) ? value : -1e30;
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(hmask, best, o);
+                const int op = __shfl_xor_sync(hmask, place, o);
+                if (ob > best || (ob == best && op < place)) { best = ob; place = op; }
             }
-            int idx[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) idx[k] = cbase + k;
-#pragma unroll
-            for (int st = 1; st < 8; st <<= 1) {
-#pragma unroll
-                for (int k = 0; k + st < 8; k += 2 * st) {
-                    const bool takeRight = val[k + st] > val[k];                       // tie: keep the lower index
-                    val[k] = takeRight ? val[k + st] : val[k];
-                    idx[k] = takeRight ? idx[k + st] : idx[k];
-                }
+            if (best <= -1e30) place = 0;
+            if (c1 == 0 && c2 < MAXCAND) {
+                p.psi[fo * 16 + c2] = (uint8_t)place;
+                s_delta[cur ^ 1][c2] = c2 < nc ? best : -1e300;
+                s_lf[cur ^ 1][c2] = clf;
             }
-            double maximum = val[0];
-            int place = idx[0];
-            {   // join the halves: half 1 wins only with a strictly larger value
-                const double om = __shfl_xor_sync(FULL_MASK, maximum, 16);
-                const int op = __shfl_xor_sync(FULL_MASK, place, 16);
-                const bool other_is_high = half == 0;                                  // my partner holds the higher candidate indices
-                const bool takeOther = other_is_high ? (om > maximum) : !(maximum > om);
-                if (takeOther) { maximum = om; place = op; }
-            }
-            if (maximum <= -1e30) place = 0;                                           // no candidate beat the initial maximum: place stays 0
-            if (half == 0 && c2 < MAXCAND) p.psi[fo * 16 + c2] = (uint8_t)place;
-            delta = c2 < nc ? maximum : -1e300;
-            lf = clf;
             ncPrev = nc;
+            cur ^= 1;
+            __syncthreads();
         }
     }
+    if (tid >= 32) return;
     // end of the most probable path: first maximum over the last frame's candidates
     int place = 0;
     {
-        double best = __shfl_sync(FULL_MASK, delta, 0);
+        double best = s_delta[cur][0];
         for (int ci = 1; ci < ncPrev; ci++) {
-            double d = __shfl_sync(FULL_MASK, delta, ci);
+            const double d = s_delta[cur][ci];
             if (d > best) { best = d; place = ci; }
         }
     }
@@ -861,7 +847,7 @@ __global__ void __launch_bounds__(128) k_pitch_viterbi(Clips c, PitchPass p) {
 }
 
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s) {
-    k_pitch_viterbi<<<(c.n + 3) / 4, 128, 0, s>>>(c, p);
+    k_pitch_viterbi<<<c.n, VIT_NT, 0, s>>>(c, p);
 }
 
 // ------------------------------------------------------------------------------------------------ statistics
