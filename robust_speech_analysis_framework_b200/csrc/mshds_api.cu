@@ -42,8 +42,8 @@ struct mshds_handle {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // latency-bound single-warp-per-clip kernels (Viterbi, pulse walks, interval logic) are issued on a side stream so that
     // they run underneath the frame kernels of the next analysis; `cur` is the stream work is being issued on right now
-    cudaStream_t side = nullptr, cur = nullptr, copy = nullptr;
-    cudaEvent_t ev[12] = {};
+    cudaStream_t side[4] = {}, cur = nullptr, copy = nullptr;
+    cudaEvent_t ev[16] = {};
     bool overlap = true;
     std::string err;
     long long launches = 0;
@@ -673,16 +673,15 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     memset(&pl_lt, 0, sizeof pl_lt);
     pl_lt.cprime = cprime;
     int* d_pcap = take<int>(h, n + 1);
-    double* raw_t = take<double>(h, 2 * ptotal); double* raw_thr = take<double>(h, 2 * ptotal);      // left / right walk halves
-    int* st_il = take<int>(h, fub5); int* st_ir = take<int>(h, fub5);
-    int* raw_nl = take<int>(h, fub5); int* raw_nr = take<int>(h, fub5);
-    double* raw_ar = take<double>(h, fub5); long long* raw_reg = take<long long>(h, fub5);
+    // every pulse set owns its raw scratch: the three walks run on different side streams
     auto alloc_pulses = [&](PulseSet* ps) {
         ps->cprime = cprime; ps->cap_start = d_pcap;
         ps->t = take<double>(h, ptotal); ps->count = take<int>(h, n); ps->valid = take<int>(h, n);
         ps->st_count = take<int>(h, n); ps->st_start = take<int>(h, n + 1);
-        ps->st_ileft = st_il; ps->st_iright = st_ir; ps->raw_t = raw_t; ps->raw_thr = raw_thr;
-        ps->raw_nleft = raw_nl; ps->raw_nright = raw_nr; ps->raw_added_right = raw_ar; ps->raw_region = raw_reg;
+        ps->st_ileft = take<int>(h, fub5); ps->st_iright = take<int>(h, fub5);
+        ps->raw_t = take<double>(h, 2 * ptotal); ps->raw_thr = take<double>(h, 2 * ptotal);      // left / right walk halves
+        ps->raw_nleft = take<int>(h, fub5); ps->raw_nright = take<int>(h, fub5);
+        ps->raw_added_right = take<double>(h, fub5); ps->raw_region = take<long long>(h, fub5);
     };
     alloc_pulses(&pl_lt);
     PulseSet pl_fm, pl_cp;
@@ -780,14 +779,20 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     // what `s` has issued so far and switches issue to it; MAIN() switches back; MARK(ev) records a point on the side stream
     // that `s` can later WAIT(ev) for.  With MSHDS_NO_OVERLAP=1 everything is issued on `s` in the same order.  Profiling spans
     // of side-stream work are named "~...": their durations include time spent sharing the SMs with the main stream.
-    cudaStream_t side = h->overlap ? h->side : s;
+    // Four side streams: the path finders / pulse walks of different analyses do not depend on each other, and with a single
+    // recording in the batch (BASELINE.json configs[0]) their serial chains ARE the latency of the call.
+    const bool ovl = h->overlap;
     cudaStream_t q = s;                          // stream the next launch goes to
     h->cur = s;
     int evn = 0;
-    auto SIDE = [&]() { if (side != s) { cudaEvent_t e = h->ev[evn++]; cudaEventRecord(e, s); cudaStreamWaitEvent(side, e, 0); } q = side; h->cur = side; };
+    auto SIDE = [&](int k) {
+        cudaStream_t side = ovl ? h->side[k] : s;
+        if (side != s) { cudaEvent_t e = h->ev[evn++]; cudaEventRecord(e, s); cudaStreamWaitEvent(side, e, 0); }
+        q = side; h->cur = side;
+    };
     auto MAIN = [&]() { q = s; h->cur = s; };
-    auto MARK = [&]() { cudaEvent_t e = h->ev[evn++]; if (side != s) cudaEventRecord(e, side); return e; };
-    auto WAIT = [&](cudaEvent_t e) { if (side != s) cudaStreamWaitEvent(s, e, 0); };
+    auto MARK = [&]() { cudaEvent_t e = h->ev[evn++]; if (q != s) cudaEventRecord(e, q); return e; };     // on the current side stream
+    auto WAIT = [&](cudaEvent_t e) { if (ovl) cudaStreamWaitEvent(s, e, 0); };
     const int fhint20 = (int)(fub20 > 0x3fffffff ? 0x3fffffff : fub20), fhint75 = (int)(fub75 > 0x3fffffff ? 0x3fffffff : fub75);
 
     // ---- per-clip statistics (mean, global peaks); also clears status / feature rows
@@ -798,7 +803,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("pitch_ac_frames[wide 50-600Hz]"); launch_pitch_frames(c, wide, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_refine"); launch_pitch_refine(c, wide, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, wide, fhint, q); h->launches += 1; PE();
-    SIDE();
+    SIDE(0);
     PB("~viterbi"); launch_pitch_viterbi(c, wide, q); h->launches += 1; PE();
     const cudaEvent_t ev_wide = MARK();
     MAIN();
@@ -810,7 +815,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("pitch_ac_frames[speechrate 30-450Hz]"); launch_pitch_frames(c, srp, h->tw, fhint20, q); h->launches += 1; PE();
     PB("k_pitch_refine"); launch_pitch_refine(c, srp, h->tw, fhint20, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, srp, fhint20, q); h->launches += 1; PE();
-    SIDE();
+    SIDE(1);
     PB("~viterbi"); launch_pitch_viterbi(c, srp, q); h->launches += 1; PE();
     PB("~speechrate_logic"); launch_speechrate(c, isr, isr_stats, srp, srs, h->tw, q); h->launches += 1; PE();
     MAIN();
@@ -825,10 +830,12 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("k_pitch_score"); launch_pitch_score(c, mainp, fhint, q); h->launches += 1; PE();
     PB("k_pitch_refine"); launch_pitch_refine(c, cpp_p, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, cpp_p, fhint, q); h->launches += 1; PE();
-    SIDE();
+    SIDE(0);
     PB("~viterbi"); launch_pitch_viterbi(c, mainp, q); h->launches += 1; PE();
     launch_pitch_stats(c, mainp, q); h->launches += 1;
     const cudaEvent_t ev_mainpitch = MARK();
+    MAIN();
+    SIDE(2);
     PB("~viterbi"); launch_pitch_viterbi(c, cpp_p, q); h->launches += 1; PE();
     // ---- _extract_CPP (:253-301), first half: pulses of the vt=0.3 pitch and the voiced intervals
     PB("~pulses"); launch_pulses(c, cpp_p, pl_cp, q); h->launches += 5; PE();
@@ -853,7 +860,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("pitch_ac_frames[ltas]"); launch_pitch_frames(c, ltp, h->tw, fhint75, q); h->launches += 1; PE();
     PB("k_pitch_refine"); launch_pitch_refine(c, ltp, h->tw, fhint75, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, ltp, fhint75, q); h->launches += 1; PE();
-    SIDE();
+    SIDE(1);
     PB("~viterbi"); launch_pitch_viterbi(c, ltp, q); h->launches += 1; PE();
     PB("~pulses"); launch_pulses(c, ltp, pl_lt, q); h->launches += 5; PE();
     const cudaEvent_t ev_ltas = MARK();
@@ -866,7 +873,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     PB("pitch_cc_frames[formant]"); launch_pitch_frames(c, ccp, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_refine"); launch_pitch_refine(c, ccp, h->tw, fhint, q); h->launches += 1; PE();
     PB("k_pitch_score"); launch_pitch_score(c, ccp, fhint, q); h->launches += 1; PE();
-    SIDE();
+    SIDE(3);
     PB("~viterbi"); launch_pitch_viterbi(c, ccp, q); h->launches += 1; PE();
     PB("~pulses"); launch_pulses(c, ccp, pl_fm, q); h->launches += 5; PE();
     const cudaEvent_t ev_fmt = MARK();
@@ -882,7 +889,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     // ---- _extract_CPP, second half (one small read-back, then resample / cepstrogram / CPPS of every voiced interval)
     WAIT(ev_vuv);
     cudaStream_t rb = s;
-    if (side != s) { rb = h->copy; cudaStreamWaitEvent(rb, ev_vuv, 0); }
+    if (ovl) { rb = h->copy; cudaStreamWaitEvent(rb, ev_vuv, 0); }
     if ((rc = run_cpp_stage(h, c, off_host, lens, x1_host, sg, scap, seg_prefix, fs, q, rb))) return rc;
 
     WAIT(ev_fmt);
@@ -987,8 +994,8 @@ int mshds_create(int device, mshds_handle** out) {
         return MSHDS_ERR_CUDA;
     }
     h->stream = h->own_stream;
-    if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    for (auto& st : h->side) if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     for (auto& e : h->ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     { const char* e = getenv("MSHDS_NO_OVERLAP"); h->overlap = !(e && atoi(e)); }     // development switch
     // twiddle table exp(-2 pi i j / TW_N), j < TW_N/2
@@ -1038,7 +1045,7 @@ void mshds_destroy(mshds_handle* h) {
     cudaFree(h->twb1024);
     cudaFree(h->arena);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    if (h->side) cudaStreamDestroy(h->side);
+    for (auto& st : h->side) if (st) cudaStreamDestroy(st);
     if (h->copy) cudaStreamDestroy(h->copy);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
