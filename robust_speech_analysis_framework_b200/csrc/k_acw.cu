@@ -241,9 +241,10 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(ACW_NT, 2) k_ac_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
+template <int OCC>
+__global__ void __launch_bounds__(ACW_NT, OCC) k_ac_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
                                                              const __grid_constant__ AcwParams A, const double2* __restrict__ tw) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* xch_all = smem;                                        // ACW_WARPS x 16 KB
     unsigned char* stage0 = smem + ACW_WARPS * ACW_XCH_BYTES;             // 2 x stage_bytes
     __shared__ __align__(8) unsigned long long bars[2];
@@ -396,16 +397,23 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
     cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
     if (p.dual_cand_f) cudaMemsetAsync(p.dual_qcount, 0, sizeof(int), s);
-    cudaFuncSetAttribute(k_ac_frames_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_ac_frames_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ac_frames_w, ACW_NT, smem);
-    if (occ < 1) occ = 1;
-    int grid = sm_count() * occ;
+    static int occ_want = 0;
+    if (!occ_want) { const char* e = getenv("MSHDS_ACW_OCC"); occ_want = e && atoi(e) == 3 ? 3 : 2; }     // development switch (A/B)
     const int nturn = (max_frames_hint + ACW_TURN - 1) / ACW_TURN;
-    if (max_frames_hint > 0 && grid > nturn) grid = nturn;
-    if (grid < 1) grid = 1;
-    k_ac_frames_w<<<grid, ACW_NT, smem, s>>>(c, p, A, tw);
+#define ACW_LAUNCH(O) \
+    do { \
+        cudaFuncSetAttribute(k_ac_frames_w<O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaFuncSetAttribute(k_ac_frames_w<O>, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        int occ = 0; \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ac_frames_w<O>, ACW_NT, smem); \
+        if (occ < 1) occ = 1; \
+        int grid = sm_count() * occ; \
+        if (max_frames_hint > 0 && grid > nturn) grid = nturn; \
+        if (grid < 1) grid = 1; \
+        k_ac_frames_w<O><<<grid, ACW_NT, smem, s>>>(c, p, A, tw); \
+    } while (0)
+    if (occ_want == 3) ACW_LAUNCH(3); else ACW_LAUNCH(2);
+#undef ACW_LAUNCH
     // candidates: one warp per frame, as many warps per SM as the scratch allows
     const size_t smem2 = region * ACC_WARPS;
     cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(32 * CEW_WARPS, 2) k_cepstrogram_w(const CepSe
                                                                      const double2* __restrict__ tw, const double2* __restrict__ twb512,
                                                                      double emphasis, double dt, double* __restrict__ cep, int nqmax,
                                                                      const double* __restrict__ wtab, int wtab_n, int* __restrict__ turn_counter) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     constexpr int L = 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 15, gidx = lane >> 4;
     const unsigned gmask = 0xffffu << (16 * gidx);

@@ -147,7 +147,7 @@ __device__ __forceinline__ void spw_fetch(const Clips& c, const SpecPass& p, con
 __global__ void __launch_bounds__(SPW_NT, 2) k_spec_frames_w(const __grid_constant__ Clips c, const __grid_constant__ SpecPass p,
                                                              const __grid_constant__ PitchPass pp, const __grid_constant__ SpwParams A,
                                                              const double2* __restrict__ tw) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* xch_all = smem;
     unsigned char* stage0 = smem + SPW_WARPS * SPW_XCH_BYTES;
     __shared__ __align__(8) unsigned long long bars[2];
