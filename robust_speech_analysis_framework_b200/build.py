@@ -1,19 +1,25 @@
-"""Builds libmshds_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Builds libmshds_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Each .cu is compiled to an object of its own (in parallel, only when it or a header changed) and the objects are linked into
+the shared library; no relocatable device code is needed (no device function crosses a translation unit)."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmshds_b200.so")
+HEADER = os.path.join(HERE, "..", "include", "mshds_b200.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # float64 reference arithmetic: no implicit FMA contraction (hot loops call fma() explicitly), IEEE div/sqrt
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -21,11 +27,15 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER]
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mshds_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -33,8 +43,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    subprocess.check_call(cmd)
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_time = max(os.path.getmtime(h) for h in _headers())
+    jobs = []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time)
+        jobs.append((src, obj, stale))
+
+    def compile_one(job):
+        src, obj, stale = job
+        if stale:
+            subprocess.check_call([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, jobs))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + objs)
     return LIB
 
 

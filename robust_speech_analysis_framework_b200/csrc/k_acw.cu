@@ -364,28 +364,55 @@ __global__ void __launch_bounds__(32 * ACC_WARPS) k_ac_candidates(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
-// returns false when this pass cannot run on the warp kernel (transform larger than 1024 points, scratch does not fit)
-bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw, const double2* twb512, const double2* twb1024,
-                           long long total_elems, int max_frames_hint, cudaStream_t s) {
-    int span = 0;
+// scratch of one warp of k_ac_candidates, the largest over the speaker classes
+static size_t acc_region_bytes(const PitchPass& p) {
     size_t region = 0;
     for (int k = 0; k < 3; k++) {
         const PitchCfg& g = p.cfg[k];
-        if (g.method != 0 || (g.M != 512 && g.M != 1024)) return false;
-        const int Lk = g.M / 32;
-        if (g.brent_ixmax / 2 >= 12 * Lk || (g.nsamp_window & 1)) return false;           // read-out loop covers r < 12
         const int Bs = g.brent_ixmax < g.maximumLag + 32 ? g.brent_ixmax : g.maximumLag + 32;
         int pkcap = g.maximumLag / 2 + 2;
         if (pkcap > 320) pkcap = 320;
         const size_t need = (((size_t)(2 * Bs + 2) * 8 + 15) & ~(size_t)15) + (size_t)pkcap * 24 + 6 * 128 + (((size_t)pkcap * 4 + 15) & ~(size_t)15) +
                             2 * 64 + 16 + 64;
         if (need > region) region = need;
+    }
+    return (region + 127) & ~(size_t)127;
+}
+
+// candidates: one warp per frame, as many warps per SM as the scratch allows (also serves the cross-correlation frames of
+// k_ccs.cu); returns false when the scratch does not fit
+bool launch_ac_candidates(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s) {
+    const size_t region = acc_region_bytes(p);
+    const size_t smem2 = region * ACC_WARPS;
+    if (smem2 > 200 * 1024) return false;
+    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int occ2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ac_candidates, 32 * ACC_WARPS, smem2);
+    if (occ2 < 1) occ2 = 1;
+    int grid2 = sm_count() * occ2;
+    const int need_blocks = (max_frames_hint + ACC_WARPS - 1) / ACC_WARPS;
+    if (max_frames_hint > 0 && grid2 > need_blocks) grid2 = need_blocks;
+    if (grid2 < 1) grid2 = 1;
+    k_ac_candidates<<<grid2, 32 * ACC_WARPS, smem2, s>>>(c, p, tw, (int)region);
+    return true;
+}
+
+// returns false when this pass cannot run on the warp kernel (transform larger than 1024 points, scratch does not fit)
+bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw, const double2* twb512, const double2* twb1024,
+                           long long total_elems, int max_frames_hint, cudaStream_t s) {
+    int span = 0;
+    for (int k = 0; k < 3; k++) {
+        const PitchCfg& g = p.cfg[k];
+        if (g.method != 0 || (g.M != 512 && g.M != 1024)) return false;
+        const int Lk = g.M / 32;
+        if (g.brent_ixmax / 2 >= 12 * Lk || (g.nsamp_window & 1)) return false;           // read-out loop covers r < 12
         const int reach = g.halfnsamp_window > g.nsamp_period ? g.halfnsamp_window : g.nsamp_period;
         const int hop = (int)ceil(g.dt / c.dx) + 1;
         const int sp = 2 * reach + 2 + (ACW_TURN - 1) * hop + 16;
         if (sp > span) span = sp;
     }
-    region = (region + 127) & ~(size_t)127;
+    const size_t region = acc_region_bytes(p);
     AcwParams A;
     A.esz = c.pcm.p64 ? 8 : 2;
     A.pcm_bytes = c.pcm.p64 ? (const unsigned char*)c.pcm.p64 : (const unsigned char*)c.pcm.p16;
@@ -414,17 +441,6 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
     } while (0)
     if (occ_want == 3) ACW_LAUNCH(3); else ACW_LAUNCH(2);
 #undef ACW_LAUNCH
-    // candidates: one warp per frame, as many warps per SM as the scratch allows
-    const size_t smem2 = region * ACC_WARPS;
-    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    cudaFuncSetAttribute(k_ac_candidates, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    int occ2 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_ac_candidates, 32 * ACC_WARPS, smem2);
-    if (occ2 < 1) occ2 = 1;
-    int grid2 = sm_count() * occ2;
-    const int need_blocks = (max_frames_hint + ACC_WARPS - 1) / ACC_WARPS;
-    if (max_frames_hint > 0 && grid2 > need_blocks) grid2 = need_blocks;
-    if (grid2 < 1) grid2 = 1;
-    k_ac_candidates<<<grid2, 32 * ACC_WARPS, smem2, s>>>(c, p, tw, (int)region);
+    launch_ac_candidates(c, p, tw, max_frames_hint, s);
     return true;
 }

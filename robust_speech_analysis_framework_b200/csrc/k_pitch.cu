@@ -507,6 +507,12 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
     // autocorrelation passes with transforms of <= 1024 complex points run warp-per-frame with TMA-staged samples (k_acw.cu)
     if (!is_cc && !c.legacy_fft && c.twb512 &&
         launch_ac_frames_warp(c, p, tw, c.twb512, c.twb1024, c.total_samples, max_frames_hint, s)) return;
+    // int16 cross-correlation passes share their block products between overlapping frames (k_ccs.cu); the candidates of
+    // to_pitch_cc then come from the warp-per-frame candidate kernel, the harmonicity pass queues its maxima itself
+    if (is_cc && !c.legacy_cc && launch_cc_frames_shared(c, p, max_frames_hint, s)) {
+        if (!p.hnr_mode) launch_ac_candidates(c, p, tw, max_frames_hint, s);
+        return;
+    }
     FrameSmem L = frames_smem_layout(p, is_cc);
     size_t smem = (size_t)L.total;
     const int nsm = sm_count();

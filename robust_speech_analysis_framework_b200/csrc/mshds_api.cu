@@ -53,6 +53,7 @@ struct mshds_handle {
     double2* twb512 = nullptr;          // pass twiddles of the warp-resident transforms (fftreg.cuh), [32][M / 32]
     double2* twb1024 = nullptr;
     int legacy_fft = 0;
+    int legacy_cc = 0;
     std::map<int, std::pair<double*, double*>> ac_windows;      // nsamp_window -> (window, windowR)
     std::map<long long, double*> kaiser;                        // key -> window
     std::map<int, double*> gauss_spec;
@@ -581,7 +582,7 @@ static int process_chunk(mshds_handle* h, SPtr d_pcm, const std::vector<long lon
     c.x1 = d_x1; c.xmax = d_xmax;
     c.cls = take<int>(h, n);
     c.status = d_status; c.feat = d_feat;
-    c.total_samples = off_host[n]; c.twb512 = h->twb512; c.twb1024 = h->twb1024; c.legacy_fft = h->legacy_fft;
+    c.total_samples = off_host[n]; c.twb512 = h->twb512; c.twb1024 = h->twb1024; c.legacy_fft = h->legacy_fft; c.legacy_cc = h->legacy_cc;
     void* stat_scratch = arena_take(h, (size_t)n * 16);
 
     // ---- pitch pass configurations (parselmouth defaults unless mshds_extractor.py passes a value)
@@ -1024,6 +1025,7 @@ int mshds_create(int device, mshds_handle** out) {
             cudaMemcpy(*dst, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     }
     { const char* e = getenv("MSHDS_LEGACY_FFT"); h->legacy_fft = e && atoi(e); }
+    { const char* e = getenv("MSHDS_LEGACY_CC"); h->legacy_cc = e && atoi(e); }
     *out = h;
     return MSHDS_OK;
 }
@@ -1069,6 +1071,7 @@ int mshds_set_option(mshds_handle* h, const char* name, long long value) {
     if (!h || !name) return MSHDS_ERR_ARG;
     const std::string n(name);
     if (n == "legacy_fft") h->legacy_fft = value != 0;
+    else if (n == "legacy_cc") h->legacy_cc = value != 0;
     else if (n == "overlap") h->overlap = value != 0;
     else if (n == "nvtx") h->nvtx = value != 0;
     else { h->err = "unknown option: " + n; return MSHDS_ERR_ARG; }

@@ -226,6 +226,49 @@ def test_warp_resident_fft_frames_equal_the_shared_memory_ones(ex):
     assert np.array_equal(new[:, SPEECHRATE], old[:, SPEECHRATE])
 
 
+def test_shared_block_cross_correlation_equals_frame_by_frame(ex, orc):
+    """k_ccs.cu (block products shared between overlapping frames, exact for int16 input) against the frame-by-frame
+    cross-correlation kernel ("legacy_cc") and the oracle: harmonicity contour, to_pitch_cc contour, formant pulses.  Clips of
+    both speaker classes, odd lengths (frame centres on sample boundaries), a short clip (runs shorter than the ring), a clip
+    with a large DC offset (the mean correction cancels most of the raw products) and digital silence inside a clip."""
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    clips = [synth_clip(300 + i, d).numpy() for i, d in enumerate([4.0, 3.00006, 0.35, 5.1, 2.2])]
+    dc = synth_clip(310, 3.0).numpy().astype(np.int32) // 4 + 9000
+    clips.append(dc.astype(np.int16))
+    gap = synth_clip(311, 3.0).numpy().copy()
+    gap[16000:24000] = 0
+    clips.append(gap)
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    keys = ("hnr_r", "pitch_cc_f", "pulses_fmt")
+    new, nst = ex.extract_host(pcm, off)
+    cn = {k: [ex.debug_fetch(k, c) for c in range(len(clips))] for k in keys}
+    ex.set_option("legacy_cc", 1)
+    try:
+        old, ost = ex.extract_host(pcm, off)
+        co = {k: [ex.debug_fetch(k, c) for c in range(len(clips))] for k in keys}
+    finally:
+        ex.set_option("legacy_cc", 0)
+    assert np.array_equal(nst, ost)
+    for k in keys:
+        for ci, (a, b) in enumerate(zip(cn[k], co[k])):
+            assert len(a) == len(b), (k, ci)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a == 0, b == 0), f"{k} clip {ci}: decisions differ"
+            np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9, equal_nan=True, err_msg=f"{k} clip {ci}")
+    assert_features_close(new, old, "shared-block CC vs frame-by-frame CC")
+    assert np.array_equal(new[:, SPEECHRATE], old[:, SPEECHRATE])
+    want, wst = orc.extract(pcm, off, 16000.0, nthreads=os.cpu_count() or 1)
+    assert_features_close(new, want, "shared-block CC vs oracle")
+    assert np.array_equal(nst, wst)
+    # exact arithmetic on int16 products: the grouping of frames into runs cannot show in the result
+    ex.set_chunk_samples(70000)
+    try:
+        chunked, _ = ex.extract_host(pcm, off)
+    finally:
+        ex.set_chunk_samples(1 << 27)
+    assert np.array_equal(chunked, new, equal_nan=True)
+
+
 def _sharded_worker(rank, world, port, pcm, off, q):
     import torch
     import torch.distributed as dist
