@@ -6,17 +6,37 @@
 #include "common.cuh"
 #include "fftreg.cuh"
 
+// Pass twiddles exp(-2 pi i j q / M), row q of a [32][L] table, as seen by lane j.  FwTwGlobal reads the table through the
+// read-only cache; FwTwShared reads a copy the CTA staged in shared memory (fw_stage_twiddles) -- the frame kernels run only two
+// warps per scheduler (255 registers), which cannot hide an L1/L2 round trip in front of every twiddle multiply (ncu, round 2:
+// 40 % of the stall samples of k_ac_frames_w were DMULs waiting on the long scoreboard), but do hide a shared-memory one.
+struct FwTwGlobal {
+    const double2* base; int L;                 // base = table + j
+    __device__ __forceinline__ FwTwGlobal(const double2* twb, int j, int L_) : base(twb + j), L(L_) {}
+    __device__ __forceinline__ double2 operator()(int q) const { return __ldg(base + q * L); }
+};
+struct FwTwShared {
+    const double2* base; int L;                 // base = shared-memory copy of the table + j
+    __device__ __forceinline__ FwTwShared(const double2* twb_smem, int j, int L_) : base(twb_smem + j), L(L_) {}
+    __device__ __forceinline__ double2 operator()(int q) const { return base[q * L]; }
+};
+// all NT threads of the CTA: copy a [32][L] table (32 L complex doubles) into shared memory; the caller synchronises
+template <int NT>
+__device__ __forceinline__ void fw_stage_twiddles(double2* dst_smem, const double2* __restrict__ twb, int L) {
+    for (int i = threadIdx.x; i < 32 * L; i += NT) dst_smem[i] = __ldg(twb + i);
+}
+
 // One transform of the frame(s) of this warp.  `a` holds pass-A input in logical order (element k = z[j + L k]); on return
 // `a` holds logical element r (k = j + L r) of the result at a[fr_slot<L>(r)].  xch: this lane's frame exchange region
 // (M complex doubles); twb: [32][L] table of exp(-2 pi i j q / M).
-template <int L, int SIGN>
-__device__ __forceinline__ void fw_transform(double2 (&a)[32], double2* xch, int j, const double2* __restrict__ twb) {
+template <int L, int SIGN, class TW>
+__device__ __forceinline__ void fw_transform(double2 (&a)[32], double2* xch, int j, const TW twf) {
     fr_fft<32, SIGN>(a);
     fr_static_for<0, 32>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         double2 v = a[fr_brev(q, 5)];
         if constexpr (q > 0) {
-            double2 t = __ldg(twb + q * L + j);                 // exp(-2 pi i j q / M); conjugate for the inverse
+            double2 t = twf(q);                                 // exp(-2 pi i j q / M); conjugate for the inverse
             if (SIGN > 0) t.y = -t.y;
             v = fr_mul(v, t);
         }
@@ -138,8 +158,8 @@ __device__ __forceinline__ void fw_fft32(double2 (&a)[32], bool two_halves) {
     fr_dif_stages<32, 8, -1>(a);
 }
 
-template <class G>
-__device__ __forceinline__ void fw_roundtrip(double2 (&a)[32], double2* xch, int lane, int j, int L, const double2* __restrict__ twb,
+template <class G, class TW>
+__device__ __forceinline__ void fw_roundtrip(double2 (&a)[32], double2* xch, int lane, int j, int L, const TW twf,
                                              double2 wj /* exp(-2 pi i j / N) */, G gf) {
     const int grp = lane & ~(L - 1);
     const int pl = grp | ((L - j) & (L - 1));
@@ -151,7 +171,7 @@ __device__ __forceinline__ void fw_roundtrip(double2 (&a)[32], double2* xch, int
         fr_static_for<0, 32>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             double2 v = a[fr_brev(q, 5)];
-            if constexpr (q > 0) v = fr_mul(v, __ldg(twb + q * L + j));   // exp(-2 pi i j q / M)
+            if constexpr (q > 0) v = fr_mul(v, twf(q));                   // exp(-2 pi i j q / M)
             xch[q * L + (j ^ (q & 7))] = v;
         });
         __syncwarp();

@@ -31,6 +31,8 @@
 #define ACW_NT (32 * ACW_WARPS)
 #define ACW_TURN 8
 #define ACW_XCH_BYTES (1024 * 16)          // exchange buffer per warp: 1024 complex doubles
+#define ACW_TW1024_BYTES (32 * 32 * 16)    // dynamic shared memory: [pass twiddles 1024][pass twiddles 512][exchange x warps][2 stages]
+#define ACW_TW_BYTES (ACW_TW1024_BYTES + 32 * 16 * 16)
 
 struct AcwParams : StageParams {
     const double2* twb512;            // [32][16] exp(-2 pi i j q / 512)
@@ -170,7 +172,8 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
     const int W = g.nsamp_window, B = g.brent_ixmax;
     const int esz = A.esz;
     double2* xch = (double2*)(xw + (size_t)gidx * (ACW_XCH_BYTES / 2));     // this frame's exchange region (L = 16: half)
-    const double2* twb = L == 32 ? A.twb1024 : A.twb512;
+    extern __shared__ __align__(16) unsigned char acw_smem[];               // the kernel's dynamic shared memory: tables first
+    const FwTwShared twf((const double2*)(acw_smem + (L == 32 ? 0 : ACW_TW1024_BYTES)), j, L);
 
     const double x1 = c.x1[sg.clip];
     const double t = p.t1[sg.clip] + (double)(sg.k0 + fi) * g.dt;
@@ -214,7 +217,7 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
 
     // ---- autocorrelation = inverse FFT of |FFT|^2: the SAME transform code runs twice
     const double2 wj = __ldg(tw + j * (TW_N / (64 * L)));                 // exp(-2 pi i j / N), N = 64 L
-    fw_roundtrip(a, xch, lane, j, L, twb, wj, FwIdentity());
+    fw_roundtrip(a, xch, lane, j, L, twf, wj, FwIdentity());
     // a[brev5(r)] = conj(y[n]), n = j + L r, y[n] = ac[2n] + i ac[2n+1].  Lags 0..B go through shared memory in natural
     // order; the normalised correlation r[i] = ac[i] / (ac[0] windowR[i]) is written by a compact loop (coalesced rows)
     double* acs = (double*)xch;
@@ -245,8 +248,8 @@ template <int OCC>
 __global__ void __launch_bounds__(ACW_NT, OCC) k_ac_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
                                                              const __grid_constant__ AcwParams A, const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* xch_all = smem;                                        // ACW_WARPS x 16 KB
-    unsigned char* stage0 = smem + ACW_WARPS * ACW_XCH_BYTES;             // 2 x stage_bytes
+    unsigned char* xch_all = smem + ACW_TW_BYTES;                         // ACW_WARPS x 16 KB
+    unsigned char* stage0 = xch_all + ACW_WARPS * ACW_XCH_BYTES;          // 2 x stage_bytes
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ AcwSeg segs[2];
 
@@ -255,6 +258,8 @@ __global__ void __launch_bounds__(ACW_NT, OCC) k_ac_frames_w(const __grid_consta
     const int nturn = (total + ACW_TURN - 1) / ACW_TURN;
     int cur_f = 0, turn_end = 0;                                          // thread 0's position in its current turn
     if (tid == 0) mbar_init_pair(bars);
+    fw_stage_twiddles<ACW_NT>((double2*)smem, A.twb1024, 32);            // visible after the first barrier of the loop below
+    fw_stage_twiddles<ACW_NT>((double2*)(smem + ACW_TW1024_BYTES), A.twb512, 16);
     __syncthreads();
     if (tid == 0) acw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[0], stage0, &bars[0]);
     unsigned phase0 = 0, phase1 = 0;
@@ -419,7 +424,7 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
     A.total_elems = total_elems;
     A.stage_bytes = (span * A.esz + 32 + 127) & ~127;
     A.twb512 = twb512; A.twb1024 = twb1024;
-    const size_t smem = (size_t)ACW_WARPS * ACW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
+    const size_t smem = (size_t)ACW_TW_BYTES + (size_t)ACW_WARPS * ACW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
     if (smem > 110 * 1024 || region * ACC_WARPS > 200 * 1024) return false;
     cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
     cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);

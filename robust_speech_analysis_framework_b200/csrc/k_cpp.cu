@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) k_cepstrogram(const CepSeg* __restrict__ 
 // points, fftwarp.cuh fw_roundtrip with G = log power): pre-emphasis, mean, Gaussian window, FFT, log, inverse FFT and the
 // squared cepstrum without a block barrier.  Frames of shorter segments (other transform sizes) stay on k_cepstrogram.
 #define CEW_WARPS 4
+#define CEW_TW_BYTES (32 * 16 * 16)           // shared-memory copy of the [32][16] pass twiddles
 struct CewLog {
     double dx2, df;
     __device__ __forceinline__ double operator()(double p) const { return log(p * dx2 + 1e-300) * df; }
@@ -144,7 +145,10 @@ __global__ void __launch_bounds__(32 * CEW_WARPS, 2) k_cepstrogram_w(const CepSe
     constexpr int L = 16;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = lane & 15, gidx = lane >> 4;
     const unsigned gmask = 0xffffu << (16 * gidx);
-    double2* xch = (double2*)(smem + (size_t)warp * (1024 * 16) + (size_t)gidx * (512 * 16));
+    double2* xch = (double2*)(smem + CEW_TW_BYTES + (size_t)warp * (1024 * 16) + (size_t)gidx * (512 * 16));
+    fw_stage_twiddles<32 * CEW_WARPS>((double2*)smem, twb512, 16);       // [pass twiddles][exchange x warps]
+    __syncthreads();
+    const FwTwShared twf((const double2*)smem, j, L);
     const int total = fprefix[nsegs];
     const double2 wj = __ldg(tw + j * (TW_N / 1024));
     // a warp takes two consecutive frames per turn (neighbouring frames share 98 % of their samples: L1 hits)
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(32 * CEW_WARPS, 2) k_cepstrogram_w(const CepSe
         CewLog G;
         G.dx2 = J.out_dx * J.out_dx;
         G.df = 1.0 / (J.out_dx * 1024.0);
-        fw_roundtrip(a, xch, lane, j, L, twb512, wj, G);
+        fw_roundtrip(a, xch, lane, j, L, twf, wj, G);
         // a[brev5(r)] = conj(y[n]), n = j + 16 r: cepstrum c[2n] = re, c[2n+1] = -im; the power cepstrum keeps c^2 for quefrency bins 0..512
         if (active) {
             double* row = cep + (size_t)f * nqmax;
@@ -656,7 +660,7 @@ void launch_cepstrogram(const CepSeg* segs, const int* fprefix, int nsegs, const
     if (twb512 && turn_counter && nqmax >= 513) {
         // frames of the usual 1024-point transform: warp-per-frame register FFT; the rest (short segments) below
         cudaMemsetAsync(turn_counter, 0, sizeof(int), s);
-        const size_t smem_w = (size_t)CEW_WARPS * 1024 * 16;
+        const size_t smem_w = (size_t)CEW_TW_BYTES + (size_t)CEW_WARPS * 1024 * 16;
         cudaFuncSetAttribute(k_cepstrogram_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cepstrogram_w, 32 * CEW_WARPS, smem_w);

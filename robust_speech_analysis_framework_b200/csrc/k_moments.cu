@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(256) k_spec_frames(Clips c, SpecPass p, PitchP
 #define SPW_NT (32 * SPW_WARPS)
 #define SPW_TURN 8
 #define SPW_XCH_BYTES (512 * 16 * 2)          // two frames of 512 complex doubles per warp
+#define SPW_TW_BYTES (32 * 16 * 16)           // shared-memory copy of the [32][16] pass twiddles
 
 struct SpwParams : StageParams {
     const double2* twb512;
@@ -148,8 +149,8 @@ __global__ void __launch_bounds__(SPW_NT, 2) k_spec_frames_w(const __grid_consta
                                                              const __grid_constant__ PitchPass pp, const __grid_constant__ SpwParams A,
                                                              const double2* __restrict__ tw) {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* xch_all = smem;
-    unsigned char* stage0 = smem + SPW_WARPS * SPW_XCH_BYTES;
+    unsigned char* xch_all = smem + SPW_TW_BYTES;                 // [pass twiddles][exchange x warps][2 stages]
+    unsigned char* stage0 = xch_all + SPW_WARPS * SPW_XCH_BYTES;
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ StageSeg segs[2];
     constexpr int L = 16;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(SPW_NT, 2) k_spec_frames_w(const __grid_consta
     const int nturn = (total + SPW_TURN - 1) / SPW_TURN;
     int cur_f = 0, turn_end = 0;
     if (tid == 0) mbar_init_pair(bars);
+    fw_stage_twiddles<SPW_NT>((double2*)smem, A.twb512, 16);
     __syncthreads();
     if (tid == 0) spw_fetch(c, p, A, total, nturn, cur_f, turn_end, &segs[0], stage0, &bars[0]);
     unsigned phase0 = 0, phase1 = 0;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(SPW_NT, 2) k_spec_frames_w(const __grid_consta
                 }
                 a[k] = make_double2(v0, v1);
             });
-            fw_transform<L, -1>(a, xch, j, A.twb512);
+            fw_transform<L, -1>(a, xch, j, FwTwShared((const double2*)smem, j, L));
             double P[32];
             fw_powers<L, 20>(a, lane, j, wj, P);                           // bins j + 16 r, r < 20: the 320 bands of 15.625 Hz
             double se = 0.0, sfe = 0.0;
@@ -256,7 +258,7 @@ static bool launch_spec_frames_warp(const Clips& c, const SpecPass& p, const Pit
     A.stage_bytes = ((p.nsamp_window + (SPW_TURN - 1) * hop + 16) * A.esz + 32 + 127) & ~127;
     A.twb512 = c.twb512;
     A.turn_counter = turn_counter;
-    const size_t smem = (size_t)SPW_WARPS * SPW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
+    const size_t smem = (size_t)SPW_TW_BYTES + (size_t)SPW_WARPS * SPW_XCH_BYTES + 2 * (size_t)A.stage_bytes;
     cudaMemsetAsync(turn_counter, 0, sizeof(int), s);
     cudaFuncSetAttribute(k_spec_frames_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_spec_frames_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
