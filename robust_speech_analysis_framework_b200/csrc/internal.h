@@ -99,7 +99,7 @@ struct Clips {
     const double2* twb512;     // [32][16]  exp(-2 pi i j q / 512): pass twiddles of the warp-resident transforms (fftreg.cuh)
     const double2* twb1024;    // [32][32]  exp(-2 pi i j q / 1024)
     int legacy_fft;            // 1: CTA-per-frame shared-memory transforms (development switch "legacy_fft")
-    int legacy_cc;             // 1: frame-by-frame cross-correlation (development switch "legacy_cc")
+    int legacy_cc;             // development switch "legacy_cc": 1 = frame-by-frame cross-correlation, 2 = CTA block-ring kernel
 };
 
 // Glottal pulse sets (PointProcess) of one pitch pass
@@ -168,6 +168,7 @@ bool launch_ac_frames_warp(const Clips& c, const PitchPass& p, const double2* tw
                            long long total_elems, int max_frames_hint, cudaStream_t s);      // k_acw.cu
 bool launch_ac_candidates(const Clips& c, const PitchPass& p, const double2* tw, int max_frames_hint, cudaStream_t s);   // k_acw.cu
 bool launch_cc_frames_shared(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);                // k_ccs.cu
+bool launch_cc_frames_warp(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s);                  // k_ccs.cu
 void launch_pitch_viterbi(const Clips& c, const PitchPass& p, cudaStream_t s);
 void launch_pitch_class(const Clips& c, const PitchPass& p, cudaStream_t s);                 // _pitch_values
 void launch_pitch_stats(const Clips& c, const PitchPass& p, cudaStream_t s);                 // mean_F0, stdev semitones

@@ -125,6 +125,58 @@ __device__ __forceinline__ void ccs_extend(const int16_t* __restrict__ pcm, long
     totQ += __shfl_sync(FULL_MASK, iq, 31);
 }
 
+// What follows the correlation of one frame (executed by ONE warp; rr[0 .. maximumLag + 1] = the frame's r in shared memory):
+// relative local peak, then either the frame's maxima as items for k_hnr_refine (harmonicity) or the hand-over flag for
+// k_ac_candidates (to_pitch_cc).
+__device__ __forceinline__ void ccs_frame_tail(const Clips& c, const PitchPass& p, const PitchCfg& g, int clip, int fidx,
+                                               const double* rr, double localPeak, double gpeak, int Lm, double dx, int lane) {
+    const double intensity = localPeak > gpeak ? 1.0 : localPeak / gpeak;
+    if (p.hnr_mode) {
+        double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
+        uvs = g.vt + (uvs > 0 ? uvs : 0);
+        if (localPeak != 0.0 && uvs < 1.0) {
+            // every maximum of r is an item for k_hnr_refine: count them, reserve the queue slots with ONE
+            // atomic per frame (a single address takes the atomics of the whole grid), then write the items
+            const double thr = 0.5 * g.vt;
+            const int B = g.brent_ixmax;
+            const int upper = Lm < B ? Lm : B;
+            int count = 0;
+            for (int i0 = 2; i0 < upper; i0 += 32) {
+                const int i = i0 + lane;
+                bool flag = false;
+                if (i < upper) { const double ri = rr[i]; flag = ri > thr && ri > rr[i - 1] && ri >= rr[i + 1]; }
+                count += __popc(__ballot_sync(FULL_MASK, flag));
+            }
+            if (count > 0) {
+                unsigned long long q0 = 0;
+                if (lane == 0) q0 = atomicAdd(p.qcount64, (unsigned long long)count);
+                q0 = __shfl_sync(FULL_MASK, q0, 0);
+                for (int i0 = 2; i0 < upper; i0 += 32) {
+                    const int i = i0 + lane;
+                    bool flag = false;
+                    double ri = 0.0, rm = 0.0, rp = 0.0;
+                    if (i < upper) { ri = rr[i]; rm = rr[i - 1]; rp = rr[i + 1]; flag = ri > thr && ri > rm && ri >= rp; }
+                    const unsigned m = __ballot_sync(FULL_MASK, flag);
+                    if (flag) {
+                        const double dr = 0.5 * (rp - rm), d2r = 2 * ri - rm - rp;
+                        const double freq = 1.0 / dx / (i + dr / d2r);
+                        const unsigned long long item = ((unsigned long long)(unsigned)fidx << 32) |
+                                                        ((unsigned long long)i << 8) | (freq > 0.3 / dx ? 1ull : 0ull);
+                        const unsigned long long q = q0 + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+                        if (q < p.q64_cap) p.queue64[q] = item;
+                        else atomicOr(&c.status[clip], ST_HNR);      // cannot happen: capacity is the worst case
+                    }
+                    q0 += (unsigned long long)__popc(m);
+                }
+            }
+        }
+        if (lane == 0) { p.inten[fidx] = intensity; p.best_bits[fidx] = 0ull; }
+    } else if (lane == 0) {
+        p.inten[fidx] = intensity;
+        p.ncand[fidx] = localPeak != 0.0 ? 1 : 0;        // hand-over to k_ac_candidates
+    }
+}
+
 // products of one block: part[ch][lag - 1] = sum over slice ch of the block of x[j] x[j + lag], lag = 1..ngroups*TL
 template <int TL>
 __device__ __forceinline__ void ccs_products(const double* __restrict__ xa0, double* __restrict__ part, int LS, int H, int ngroups,
@@ -316,51 +368,7 @@ __global__ void __launch_bounds__(CCS_NT, 2) k_cc_frames_s(const __grid_constant
                         double localPeak = s_red[0];
 #pragma unroll
                         for (int w = 1; w <= CCS_PW; w++) localPeak = fmax(localPeak, s_red[w]);
-                        const double intensity = localPeak > gpeak ? 1.0 : localPeak / gpeak;
-                        if (p.hnr_mode) {
-                            double uvs = g.sil <= 0 ? 0.0 : 2.0 - intensity / (g.sil / (1.0 + g.vt));
-                            uvs = g.vt + (uvs > 0 ? uvs : 0);
-                            if (localPeak != 0.0 && uvs < 1.0) {
-                                // every maximum of r is an item for k_hnr_refine: count them, reserve the queue slots with ONE
-                                // atomic per frame (a single address takes the atomics of the whole grid), then write the items
-                                const double thr = 0.5 * g.vt;
-                                const int B = g.brent_ixmax;
-                                const int upper = Lm < B ? Lm : B;
-                                int count = 0;
-                                for (int i0 = 2; i0 < upper; i0 += 32) {
-                                    const int i = i0 + lane;
-                                    bool flag = false;
-                                    if (i < upper) { const double ri = rr[i]; flag = ri > thr && ri > rr[i - 1] && ri >= rr[i + 1]; }
-                                    count += __popc(__ballot_sync(FULL_MASK, flag));
-                                }
-                                if (count > 0) {
-                                    unsigned long long q0 = 0;
-                                    if (lane == 0) q0 = atomicAdd(p.qcount64, (unsigned long long)count);
-                                    q0 = __shfl_sync(FULL_MASK, q0, 0);
-                                    for (int i0 = 2; i0 < upper; i0 += 32) {
-                                        const int i = i0 + lane;
-                                        bool flag = false;
-                                        double ri = 0.0, rm = 0.0, rp = 0.0;
-                                        if (i < upper) { ri = rr[i]; rm = rr[i - 1]; rp = rr[i + 1]; flag = ri > thr && ri > rm && ri >= rp; }
-                                        const unsigned m = __ballot_sync(FULL_MASK, flag);
-                                        if (flag) {
-                                            const double dr = 0.5 * (rp - rm), d2r = 2 * ri - rm - rp;
-                                            const double freq = 1.0 / dx / (i + dr / d2r);
-                                            const unsigned long long item = ((unsigned long long)(unsigned)fidx << 32) |
-                                                                            ((unsigned long long)i << 8) | (freq > 0.3 / dx ? 1ull : 0ull);
-                                            const unsigned long long q = q0 + (unsigned long long)__popc(m & ((1u << lane) - 1u));
-                                            if (q < p.q64_cap) p.queue64[q] = item;
-                                            else atomicOr(&c.status[clip], ST_HNR);      // cannot happen: capacity is the worst case
-                                        }
-                                        q0 += (unsigned long long)__popc(m);
-                                    }
-                                }
-                            }
-                            if (lane == 0) { p.inten[fidx] = intensity; p.best_bits[fidx] = 0ull; }
-                        } else if (lane == 0) {
-                            p.inten[fidx] = intensity;
-                            p.ncand[fidx] = localPeak != 0.0 ? 1 : 0;        // hand-over to k_ac_candidates
-                        }
+                        ccs_frame_tail(c, p, g, clip, fidx, rr, localPeak, gpeak, Lm, dx, lane);
                     }
 #undef PSV
 #undef PQV
@@ -375,6 +383,296 @@ __global__ void __launch_bounds__(CCS_NT, 2) k_cc_frames_s(const __grid_constant
             f += nseg;
         }
     }
+}
+
+// ================================================================================================ warp-per-run version
+// k_cc_frames_w: the same exact arithmetic with the block ring replaced by SLIDING sums held in registers, and the CTA-wide
+// pipeline (five warps, three block barriers per frame: ncu showed 37 % of the stall samples of k_cc_frames_s on the barrier
+// and the FP64 pipe at 10 %) replaced by ONE WARP PER RUN of consecutive frames with no block barrier at all:
+//
+//   C_k+1[lag] = C_k[lag] + sum_{j in [hi_k, hi_k+1)} s[j] s[j + lag] - sum_{j in [lo_k, lo_k+1)} s[j] s[j + lag]
+//
+// (window [lo, hi) of frame k, hi = lo + W).  Every term is an integer multiple of 2^-30 far below 2^53, so adding and
+// subtracting is exact: no drift, the result does not depend on where a run starts, and it is bit-identical to
+// k_cc_frames_s.  A lane owns TL consecutive lags (TL = 5, 7, 9: 32 TL >= maximumLag + 1) with their running sums in
+// registers; per frame it forms 2 x (frame step) x TL products from two short sample windows in shared memory (the lag
+// window slides through a register ring: one broadcast load + one conflict-free load per TL DFMA).  The raw-sample sums of
+// the normalisation follow the same way: A_0 and sum s^2 slide with integer warp reductions, A_lag = A_0 + a prefix scan of
+// s[hi + m - 1] - s[lo + m - 1] over the lags (lane-local sums + one warp scan); the local mean slides as an integer sum,
+// the local peak is an integer min / max.  The first frame of a run is built by sliding an empty window open (W / 96 block
+// additions ~ the cost of 7 ordinary frames).
+#define CCW_WARPS 8
+#define CCW_NT (32 * CCW_WARPS)
+#define CCW_DMAX 96                              // largest window advance (and start-up block) in samples
+#define CCW_XW (CCW_DMAX + 32 * 9 + 8)           // doubles per edge window
+#define CCW_RR 352                               // doubles of the r row copy (lags 0 .. 32 TL)
+#define CCW_WARP_DOUBLES (2 * CCW_XW + CCW_RR)
+
+struct CcwParams {
+    const int16_t* pcm;
+    int run;                // frames per turn
+};
+
+// samples [base, base + count) of the clip (1-based, zero outside) -> xw[0 .. count) as float64; integer sum and sum of squares of
+// the first blk (<= 96) of them
+__device__ __forceinline__ void ccw_load(const int16_t* __restrict__ pcm, int nx, int base, int count, int blk, double* xw, int lane,
+                                         int& s_out, long long& q_out) {
+    int ps = 0;
+    unsigned pq = 0;
+    for (int e0 = 0; e0 < count; e0 += 128) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + 32 * u + lane, i = base + e;
+            v[u] = (e < count && i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + 32 * u + lane;
+            if (e < count) xw[e] = (double)v[u] * (1.0 / 32768.0);
+            if (e < blk) { ps += v[u]; pq += (unsigned)(v[u] * v[u]); }
+        }
+    }
+    s_out = __reduce_add_sync(FULL_MASK, ps);
+    const unsigned ql = __reduce_add_sync(FULL_MASK, pq & 0xffffu), qh = __reduce_add_sync(FULL_MASK, pq >> 16);
+    q_out = ((long long)qh << 16) + (long long)ql;
+}
+
+// integer sum of the clip samples a .. b (1-based, inclusive, zero outside the clip), minus those of a2 .. b2: one reduction
+__device__ __forceinline__ int ccw_isum2(const int16_t* __restrict__ pcm, int nx, int a, int b, int a2, int b2, int lane) {
+    int acc = 0;
+    for (int i = a + lane; i <= b; i += 32) acc += (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
+    for (int i = a2 + lane; i <= b2; i += 32) acc -= (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
+    return __reduce_add_sync(FULL_MASK, acc);
+}
+
+// C[u] +/-= sum_{t < len} x[t] x[t + lag], lag = 1 + TL lane + u; xw[e] = sample (block start + e)
+template <int TL, bool NEG>
+__device__ __forceinline__ void ccw_products(const double* __restrict__ xw, int len, int lane, double (&C)[TL]) {
+    const double* xl = xw + 1 + TL * lane;
+    double yw[TL];
+#pragma unroll
+    for (int u = 0; u < TL; u++) yw[u] = xl[u];
+    int t0 = 0;
+    for (; t0 + TL <= len; t0 += TL) {
+#pragma unroll
+        for (int t = 0; t < TL; t++) {
+            const double xv = NEG ? -xw[t0 + t] : xw[t0 + t];
+#pragma unroll
+            for (int u = 0; u < TL; u++) C[u] = fma(xv, yw[(u + t) % TL], C[u]);
+            yw[t] = xl[t0 + t + TL];
+        }
+    }
+    if (t0 < len) {
+#pragma unroll
+        for (int t = 0; t < TL; t++) {
+            if (t0 + t < len) {
+                const double xv = NEG ? -xw[t0 + t] : xw[t0 + t];
+#pragma unroll
+                for (int u = 0; u < TL; u++) C[u] = fma(xv, yw[(u + t) % TL], C[u]);
+                yw[t] = xl[t0 + t + TL];
+            }
+        }
+    }
+}
+
+// nseg consecutive frames (k0 ..) of one clip, flat frame index f ..: executed by one warp
+template <int TL>
+__device__ __noinline__ void ccw_segment(const Clips& c, const PitchPass& p, const int16_t* __restrict__ pcm_all, int clip, int f,
+                                         int nseg, int k0) {
+    extern __shared__ __align__(16) unsigned char ccw_smem[];     // the kernel's dynamic shared memory: one region per warp
+    const int lane = threadIdx.x & 31;
+    double* xn = (double*)ccw_smem + (size_t)(threadIdx.x >> 5) * CCW_WARP_DOUBLES;
+    double* xo = xn + CCW_XW;
+    double* rr = xo + CCW_XW;
+    const PitchCfg& g = p.cfg[c.cls[clip]];
+    const int W = g.nsamp_window, Lm = g.maximumLag, np = g.nsamp_period, hp = g.halfnsamp_period, hw = g.halfnsamp_window;
+    const int Ls = stored_lags(g);
+    const long long base = c.off[clip];
+    const int nx = (int)(c.off[clip + 1] - base);
+    const int16_t* pcm = pcm_all + base;
+    const double x1 = c.x1[clip], t1 = p.t1[clip], dx = c.dx, gpeak = c.gpeak[clip];
+    constexpr int NL = 32 * TL;                   // lags 1 .. NL are carried
+
+    double C[TL];
+    int A0i = 0, Mi = 0;
+    long long Q0i = 0;
+    int lo_prev = 0, left_prev = 0;
+    bool have = false;
+    for (int kk = 0; kk < nseg; kk++) {
+        long long lo_ll, left_ll;
+        int Lloc;
+        ccs_geom(g, x1, dx, t1, k0 + kk, (long long)nx, lo_ll, Lloc, left_ll);
+        const int lo = (int)lo_ll, left = (int)left_ll;
+        const int d = lo - lo_prev, dl = left - left_prev;
+        int dn;                                   // xn[dn + e] = s[hi + e], xo[dn + e] = s[lo + e]
+        if (have && d >= 0 && d <= CCW_DMAX && dl >= 0 && dl <= CCW_DMAX) {
+            int sN, sO;
+            long long qN, qO;
+            ccw_load(pcm, nx, lo_prev + W, d + NL + 1, d, xn, lane, sN, qN);
+            ccw_load(pcm, nx, lo_prev, d + NL + 1, d, xo, lane, sO, qO);
+            A0i += sN - sO;
+            Q0i += qN - qO;
+            __syncwarp();
+            ccw_products<TL, false>(xn, d, lane, C);
+            ccw_products<TL, true>(xo, d, lane, C);
+            Mi += ccw_isum2(pcm, nx, left_prev + np + 1, left + np, left_prev - np + 1, left - np, lane);
+            dn = d;
+        } else {
+            // the window is slid open from empty: blocks of <= CCW_DMAX samples
+#pragma unroll
+            for (int u = 0; u < TL; u++) C[u] = 0.0;
+            A0i = 0; Q0i = 0;
+            int len = 0;
+            for (int j0 = 0; j0 < W; j0 += CCW_DMAX) {
+                len = W - j0 < CCW_DMAX ? W - j0 : CCW_DMAX;
+                int sN;
+                long long qN;
+                __syncwarp();
+                ccw_load(pcm, nx, lo + j0, len + NL + 1, len, xn, lane, sN, qN);
+                A0i += sN;
+                Q0i += qN;
+                __syncwarp();
+                ccw_products<TL, false>(xn, len, lane, C);
+            }
+            int s0;
+            long long q0;
+            ccw_load(pcm, nx, lo - len, len + NL + 1, 0, xo, lane, s0, q0);     // so that xo[len + e] = s[lo + e] like xn
+            Mi = ccw_isum2(pcm, nx, left - np + 1, left + np, 1, 0, lane);
+            __syncwarp();
+            dn = len;
+            have = true;
+        }
+        lo_prev = lo; left_prev = left;
+
+        // ---- normalisation (same expressions as k_cc_frames_s; every sum below is exact)
+        const double mu = ((double)Mi * (1.0 / 32768.0)) / (double)(2 * np);
+        const double A0 = (double)A0i * (1.0 / 32768.0), Q0 = (double)Q0i * (1.0 / 1073741824.0);
+        const double wmm = (double)W * mu * mu;
+        const double sx = fma(-2.0 * mu, A0, Q0) + wmm;
+        double da[TL], dq[TL];
+        {
+            const double* pn = xn + dn + TL * lane;
+            const double* po = xo + dn + TL * lane;
+            double sa = 0.0, sq = 0.0;
+#pragma unroll
+            for (int u = 0; u < TL; u++) {
+                const double a = pn[u], b = po[u];
+                sa += a - b;
+                sq += fma(a, a, -(b * b));
+                da[u] = sa; dq[u] = sq;
+            }
+            double ia = sa, iq = sq;                              // inclusive warp scan of the lane totals
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double ua = __shfl_up_sync(FULL_MASK, ia, o), uq = __shfl_up_sync(FULL_MASK, iq, o);
+                if (lane >= o) { ia += ua; iq += uq; }
+            }
+            const double ea = A0 + (ia - sa), eq = Q0 + (iq - sq);
+#pragma unroll
+            for (int u = 0; u < TL; u++) { da[u] += ea; dq[u] += eq; }     // A_lag, Q_lag of lag = 1 + TL lane + u
+        }
+        __syncwarp();                                             // xn / xo are free for the next frame; rr of the previous frame is consumed
+#pragma unroll
+        for (int u = 0; u < TL; u++) {
+            const int l = 1 + TL * lane + u;
+            double v = 0.0;
+            if (l <= Lloc) {
+                const double pr = fma(-mu, A0 + da[u], C[u]) + wmm;
+                const double sy = fma(-2.0 * mu, da[u], dq[u]) + wmm;
+                v = pr / sqrt(sx * sy);
+            }
+            rr[l] = v;
+        }
+        if (lane == 0) rr[0] = 1.0;
+        // local peak: max |s - mean| over the middle of the (centred) analysis window, from the integer extremes
+        double localPeak;
+        {
+            const int right = left + 1;
+            int a0 = right - hp, a1 = right + hp - 1;
+            if (a0 < right - hw) a0 = right - hw;
+            if (a1 > right + hw - 1) a1 = right + hw - 1;
+            int vmin = 32767, vmax = -32768;
+            for (int i = a0 + lane; i <= a1; i += 32) {
+                const int v = (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
+                vmin = v < vmin ? v : vmin;
+                vmax = v > vmax ? v : vmax;
+            }
+            vmin = __reduce_min_sync(FULL_MASK, vmin);
+            vmax = __reduce_max_sync(FULL_MASK, vmax);
+            localPeak = a1 >= a0 ? fmax(fabs((double)vmax * (1.0 / 32768.0) - mu), fabs((double)vmin * (1.0 / 32768.0) - mu)) : 0.0;
+        }
+        __syncwarp();
+        const int fidx = f + kk;
+        double* rrow = p.rbuf + (size_t)fidx * p.rstride;
+        for (int l = lane; l < Ls; l += 32) rrow[l] = l <= NL ? rr[l] : 0.0;
+        ccs_frame_tail(c, p, g, clip, fidx, rr, localPeak, gpeak, Lm, dx, lane);
+    }
+}
+
+__global__ void __launch_bounds__(CCW_NT, 2) k_cc_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
+                                                           const __grid_constant__ CcwParams A) {
+    const int lane = threadIdx.x & 31;
+    const int total = p.fstart[c.n];
+    const int nturn = (total + A.run - 1) / A.run;
+    for (;;) {
+        int turn = 0;
+        if (lane == 0) turn = atomicAdd(p.turn_counter, 1);
+        turn = __shfl_sync(FULL_MASK, turn, 0);
+        if (turn >= nturn) break;
+        int f = turn * A.run;
+        const int f_end = f + A.run < total ? f + A.run : total;
+        while (f < f_end) {
+            const int clip = find_segment(p.fstart, c.n, f);
+            const int cend = p.fstart[clip + 1];
+            const int nseg = (f_end < cend ? f_end : cend) - f;
+            const int k0 = f - p.fstart[clip];
+            const int Lm = p.cfg[c.cls[clip]].maximumLag;
+            if (Lm + 1 <= 32 * 5) ccw_segment<5>(c, p, A.pcm, clip, f, nseg, k0);
+            else if (Lm + 1 <= 32 * 7) ccw_segment<7>(c, p, A.pcm, clip, f, nseg, k0);
+            else ccw_segment<9>(c, p, A.pcm, clip, f, nseg, k0);
+            __syncwarp();
+            f += nseg;
+        }
+    }
+}
+
+// returns false when the pass cannot run on the warp kernel (float64 input, more than 288 lags, rows that do not fit)
+bool launch_cc_frames_warp(const Clips& c, const PitchPass& p, int max_frames_hint, cudaStream_t s) {
+    if (c.pcm.p64 || !c.pcm.p16) return false;
+    for (int k = 0; k < 3; k++) {
+        const PitchCfg& g = p.cfg[k];
+        if (g.method < 2) return false;
+        if (g.maximumLag + 1 > 32 * 9 || g.maximumLag + 2 > CCW_RR || g.nsamp_window < 1) return false;
+        if (g.maximumLag > g.brent_ixmax) return false;
+    }
+    CcwParams A;
+    A.pcm = c.pcm.p16;
+    const size_t smem = (size_t)CCW_WARPS * CCW_WARP_DOUBLES * sizeof(double);
+    cudaFuncSetAttribute(k_cc_frames_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_cc_frames_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cc_frames_w, CCW_NT, smem);
+    if (occ < 1) occ = 1;
+    const int warps = sm_count() * occ * CCW_WARPS;
+    // a run pays ~7 frames of start-up: long runs, but several turns per warp so that the tail stays short
+    int run = max_frames_hint > 0 ? (max_frames_hint + 4 * warps - 1) / (4 * warps) : 128;
+    if (run < 32) run = 32;
+    if (run > 128) run = 128;
+    static int run_env = -1;
+    if (run_env < 0) { const char* e = getenv("MSHDS_CCW_RUN"); run_env = e ? atoi(e) : 0; }      // development switch (A/B)
+    if (run_env > 0) run = run_env;
+    A.run = run;
+    int grid = sm_count() * occ;
+    const int nturn = (max_frames_hint + run - 1) / run;
+    const int need = (nturn + CCW_WARPS - 1) / CCW_WARPS;
+    if (max_frames_hint > 0 && grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
+    if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
+    else cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
+    k_cc_frames_w<<<grid, CCW_NT, smem, s>>>(c, p, A);
+    return true;
 }
 
 // returns false when the pass has to stay on the frame-by-frame kernel (float64 input, a frame step that is not a whole

@@ -509,7 +509,8 @@ void launch_pitch_frames(const Clips& c, const PitchPass& p, const double2* tw, 
         launch_ac_frames_warp(c, p, tw, c.twb512, c.twb1024, c.total_samples, max_frames_hint, s)) return;
     // int16 cross-correlation passes share their block products between overlapping frames (k_ccs.cu); the candidates of
     // to_pitch_cc then come from the warp-per-frame candidate kernel, the harmonicity pass queues its maxima itself
-    if (is_cc && !c.legacy_cc && launch_cc_frames_shared(c, p, max_frames_hint, s)) {
+    if (is_cc && c.legacy_cc != 1 &&
+        ((c.legacy_cc == 0 && launch_cc_frames_warp(c, p, max_frames_hint, s)) || launch_cc_frames_shared(c, p, max_frames_hint, s))) {
         if (!p.hnr_mode) launch_ac_candidates(c, p, tw, max_frames_hint, s);
         return;
     }

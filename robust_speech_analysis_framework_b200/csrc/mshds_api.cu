@@ -1025,7 +1025,7 @@ int mshds_create(int device, mshds_handle** out) {
             cudaMemcpy(*dst, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice) != cudaSuccess) { delete h; return MSHDS_ERR_CUDA; }
     }
     { const char* e = getenv("MSHDS_LEGACY_FFT"); h->legacy_fft = e && atoi(e); }
-    { const char* e = getenv("MSHDS_LEGACY_CC"); h->legacy_cc = e && atoi(e); }
+    { const char* e = getenv("MSHDS_LEGACY_CC"); h->legacy_cc = e ? atoi(e) : 0; }
     *out = h;
     return MSHDS_OK;
 }
@@ -1071,7 +1071,7 @@ int mshds_set_option(mshds_handle* h, const char* name, long long value) {
     if (!h || !name) return MSHDS_ERR_ARG;
     const std::string n(name);
     if (n == "legacy_fft") h->legacy_fft = value != 0;
-    else if (n == "legacy_cc") h->legacy_cc = value != 0;
+    else if (n == "legacy_cc") h->legacy_cc = (int)value;
     else if (n == "overlap") h->overlap = value != 0;
     else if (n == "nvtx") h->nvtx = value != 0;
     else { h->err = "unknown option: " + n; return MSHDS_ERR_ARG; }

@@ -250,6 +250,18 @@ def test_shared_block_cross_correlation_equals_frame_by_frame(ex, orc):
     finally:
         ex.set_option("legacy_cc", 0)
     assert np.array_equal(nst, ost)
+    # the CTA block-ring kernel (k_cc_frames_s, "legacy_cc" = 2) and the warp-per-run sliding sums (k_cc_frames_w, default) are
+    # both exact on int16 input: bit-identical rows
+    ex.set_option("legacy_cc", 2)
+    try:
+        ring, rst = ex.extract_host(pcm, off)
+        cr = {k: [ex.debug_fetch(k, c) for c in range(len(clips))] for k in keys}
+    finally:
+        ex.set_option("legacy_cc", 0)
+    assert np.array_equal(ring, new, equal_nan=True) and np.array_equal(rst, nst)
+    for k in keys:
+        for ci, (a, b) in enumerate(zip(cn[k], cr[k])):
+            assert np.array_equal(a, b, equal_nan=True), f"{k} clip {ci}: sliding sums differ from the block ring"
     for k in keys:
         for ci, (a, b) in enumerate(zip(cn[k], co[k])):
             assert len(a) == len(b), (k, ci)
