@@ -413,10 +413,19 @@ struct CcwParams {
     int run;                // frames per turn
 };
 
+// The straight-line code a warp executes per frame has to stay well inside the 32 KB instruction cache (the first version
+// inlined the loaders, the products and nine copies of the division / square root at every call site and for every TL: 13,600
+// instructions, 35 % of its stall samples waiting for instruction fetch).  Hence: helpers that do not touch the register
+// arrays are __noinline__, the products have ONE call site inside a two-trip loop, and the normalisation runs as a rolled
+// loop over rows passed through shared memory.
+
 // samples [base, base + count) of the clip (1-based, zero outside) -> xw[0 .. count) as float64; integer sum and sum of squares of
 // the first blk (<= 96) of them
-__device__ __forceinline__ void ccw_load(const int16_t* __restrict__ pcm, int nx, int base, int count, int blk, double* xw, int lane,
-                                         int& s_out, long long& q_out) {
+__device__ __noinline__ void ccw_load(const int16_t* __restrict__ pcm, int nx, int base, int count, int blk, int xw_off /* doubles */,
+                                      int& s_out, long long& q_out) {
+    extern __shared__ __align__(16) unsigned char ccw_smem[];
+    double* xw = (double*)ccw_smem + xw_off;
+    const int lane = threadIdx.x & 31;
     int ps = 0;
     unsigned pq = 0;
     for (int e0 = 0; e0 < count; e0 += 128) {
@@ -439,39 +448,92 @@ __device__ __forceinline__ void ccw_load(const int16_t* __restrict__ pcm, int nx
 }
 
 // integer sum of the clip samples a .. b (1-based, inclusive, zero outside the clip), minus those of a2 .. b2: one reduction
-__device__ __forceinline__ int ccw_isum2(const int16_t* __restrict__ pcm, int nx, int a, int b, int a2, int b2, int lane) {
+__device__ __noinline__ int ccw_isum2(const int16_t* __restrict__ pcm, int nx, int a, int b, int a2, int b2) {
+    const int lane = threadIdx.x & 31;
     int acc = 0;
     for (int i = a + lane; i <= b; i += 32) acc += (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
     for (int i = a2 + lane; i <= b2; i += 32) acc -= (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
     return __reduce_add_sync(FULL_MASK, acc);
 }
 
-// C[u] +/-= sum_{t < len} x[t] x[t + lag], lag = 1 + TL lane + u; xw[e] = sample (block start + e)
-template <int TL, bool NEG>
+// max |s - mu| over the clip samples a0 .. a1 from their integer extremes (rounding is monotone: the extremes give the maximum)
+__device__ __noinline__ double ccw_peak(const int16_t* __restrict__ pcm, int nx, int a0, int a1, double mu) {
+    const int lane = threadIdx.x & 31;
+    int vmin = 32767, vmax = -32768;
+    for (int i = a0 + lane; i <= a1; i += 32) {
+        const int v = (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
+        vmin = v < vmin ? v : vmin;
+        vmax = v > vmax ? v : vmax;
+    }
+    vmin = __reduce_min_sync(FULL_MASK, vmin);
+    vmax = __reduce_max_sync(FULL_MASK, vmax);
+    return a1 >= a0 ? fmax(fabs((double)vmax * (1.0 / 32768.0) - mu), fabs((double)vmin * (1.0 / 32768.0) - mu)) : 0.0;
+}
+
+// r[l] of lags 1 .. NL from the rows C (in xn), A_lag (in xo), Q_lag (in rr) -> rr and the frame's row in HBM; then the tail
+__device__ __noinline__ void ccw_finish(const Clips& c, const PitchPass& p, const PitchCfg& g, const int16_t* __restrict__ pcm, int nx,
+                                        int clip, int fidx, int left, int Lloc, int NL, double mu, double A0, double Q0, int warp_off) {
+    extern __shared__ __align__(16) unsigned char ccw_smem[];
+    double* xn = (double*)ccw_smem + warp_off;
+    double* xo = xn + CCW_XW;
+    double* rr = xo + CCW_XW;
+    const int lane = threadIdx.x & 31;
+    const int W = g.nsamp_window, Lm = g.maximumLag, hp = g.halfnsamp_period, hw = g.halfnsamp_window;
+    const int Ls = stored_lags(g);
+    const double wmm = (double)W * mu * mu;
+    const double sx = fma(-2.0 * mu, A0, Q0) + wmm;
+    double* rrow = p.rbuf + (size_t)fidx * p.rstride;
+#pragma unroll 1
+    for (int l = 1 + lane; l <= NL; l += 32) {
+        double v = 0.0;
+        if (l <= Lloc) {
+            const double Al = xo[l], Ql = rr[l];
+            const double pr = fma(-mu, A0 + Al, xn[l]) + wmm;
+            const double sy = fma(-2.0 * mu, Al, Ql) + wmm;
+            v = pr / sqrt(sx * sy);
+        }
+        rr[l] = v;
+        if (l < Ls) rrow[l] = v;
+    }
+    if (lane == 0) { rr[0] = 1.0; rrow[0] = 1.0; }
+    for (int l = NL + 1 + lane; l < Ls; l += 32) rrow[l] = 0.0;
+    // local peak: max |s - mean| over the middle of the (centred) analysis window
+    const int right = left + 1;
+    int a0 = right - hp, a1 = right + hp - 1;
+    if (a0 < right - hw) a0 = right - hw;
+    if (a1 > right + hw - 1) a1 = right + hw - 1;
+    const double localPeak = ccw_peak(pcm, nx, a0, a1, mu);
+    __syncwarp();
+    ccs_frame_tail(c, p, g, clip, fidx, rr, localPeak, c.gpeak[clip], Lm, c.dx, lane);
+}
+
+// C[u] += sum_{t < len} x[t] x[t + lag], lag = 1 + TL lane + u; xw[e] = sample (block start + e)
+template <int TL>
 __device__ __forceinline__ void ccw_products(const double* __restrict__ xw, int len, int lane, double (&C)[TL]) {
     const double* xl = xw + 1 + TL * lane;
     double yw[TL];
 #pragma unroll
     for (int u = 0; u < TL; u++) yw[u] = xl[u];
     int t0 = 0;
+#pragma unroll 1
     for (; t0 + TL <= len; t0 += TL) {
 #pragma unroll
         for (int t = 0; t < TL; t++) {
-            const double xv = NEG ? -xw[t0 + t] : xw[t0 + t];
+            const double xv = xw[t0 + t];
 #pragma unroll
             for (int u = 0; u < TL; u++) C[u] = fma(xv, yw[(u + t) % TL], C[u]);
             yw[t] = xl[t0 + t + TL];
         }
     }
-    if (t0 < len) {
+    // the last len % TL samples: the ring is dead afterwards, so it can be read at a run-time rotation through shared memory ...
+    // simpler: one more (partly predicated) trip
 #pragma unroll
-        for (int t = 0; t < TL; t++) {
-            if (t0 + t < len) {
-                const double xv = NEG ? -xw[t0 + t] : xw[t0 + t];
+    for (int t = 0; t < TL - 1; t++) {
+        if (t0 + t < len) {
+            const double xv = xw[t0 + t];
 #pragma unroll
-                for (int u = 0; u < TL; u++) C[u] = fma(xv, yw[(u + t) % TL], C[u]);
-                yw[t] = xl[t0 + t + TL];
-            }
+            for (int u = 0; u < TL; u++) C[u] = fma(xv, yw[(u + t) % TL], C[u]);
+            yw[t] = xl[t0 + t + TL];
         }
     }
 }
@@ -482,16 +544,16 @@ __device__ __noinline__ void ccw_segment(const Clips& c, const PitchPass& p, con
                                          int nseg, int k0) {
     extern __shared__ __align__(16) unsigned char ccw_smem[];     // the kernel's dynamic shared memory: one region per warp
     const int lane = threadIdx.x & 31;
-    double* xn = (double*)ccw_smem + (size_t)(threadIdx.x >> 5) * CCW_WARP_DOUBLES;
+    const int warp_off = (threadIdx.x >> 5) * CCW_WARP_DOUBLES;
+    double* xn = (double*)ccw_smem + warp_off;
     double* xo = xn + CCW_XW;
     double* rr = xo + CCW_XW;
     const PitchCfg& g = p.cfg[c.cls[clip]];
-    const int W = g.nsamp_window, Lm = g.maximumLag, np = g.nsamp_period, hp = g.halfnsamp_period, hw = g.halfnsamp_window;
-    const int Ls = stored_lags(g);
+    const int W = g.nsamp_window, np = g.nsamp_period;
     const long long base = c.off[clip];
     const int nx = (int)(c.off[clip + 1] - base);
     const int16_t* pcm = pcm_all + base;
-    const double x1 = c.x1[clip], t1 = p.t1[clip], dx = c.dx, gpeak = c.gpeak[clip];
+    const double x1 = c.x1[clip], t1 = p.t1[clip], dx = c.dx;
     constexpr int NL = 32 * TL;                   // lags 1 .. NL are carried
 
     double C[TL];
@@ -499,57 +561,56 @@ __device__ __noinline__ void ccw_segment(const Clips& c, const PitchPass& p, con
     long long Q0i = 0;
     int lo_prev = 0, left_prev = 0;
     bool have = false;
+#pragma unroll 1
     for (int kk = 0; kk < nseg; kk++) {
         long long lo_ll, left_ll;
         int Lloc;
         ccs_geom(g, x1, dx, t1, k0 + kk, (long long)nx, lo_ll, Lloc, left_ll);
         const int lo = (int)lo_ll, left = (int)left_ll;
         const int d = lo - lo_prev, dl = left - left_prev;
-        int dn;                                   // xn[dn + e] = s[hi + e], xo[dn + e] = s[lo + e]
-        if (have && d >= 0 && d <= CCW_DMAX && dl >= 0 && dl <= CCW_DMAX) {
+        const bool sliding = have && d >= 0 && d <= CCW_DMAX && dl >= 0 && dl <= CCW_DMAX;
+        int j0 = 0, dn = 0;                       // afterwards xn[dn + e] = s[hi + e], xo[dn + e] = s[lo + e]
+        if (!sliding) {                           // the window is slid open from empty, in blocks of <= CCW_DMAX samples
+#pragma unroll
+            for (int u = 0; u < TL; u++) C[u] = 0.0;
+            A0i = 0; Q0i = 0; Mi = 0;
+        }
+#pragma unroll 1
+        do {
+            int nb, ob, len, olen;
+            if (sliding) { nb = lo_prev + W; ob = lo_prev; len = d; olen = d; }
+            else { len = W - j0 < CCW_DMAX ? W - j0 : CCW_DMAX; nb = lo + j0; ob = lo - len; olen = 0; j0 += len; }
             int sN, sO;
             long long qN, qO;
-            ccw_load(pcm, nx, lo_prev + W, d + NL + 1, d, xn, lane, sN, qN);
-            ccw_load(pcm, nx, lo_prev, d + NL + 1, d, xo, lane, sO, qO);
+            __syncwarp();
+            ccw_load(pcm, nx, nb, len + NL + 1, len, warp_off, sN, qN);
+            ccw_load(pcm, nx, ob, len + NL + 1, olen, warp_off + CCW_XW, sO, qO);
             A0i += sN - sO;
             Q0i += qN - qO;
             __syncwarp();
-            ccw_products<TL, false>(xn, d, lane, C);
-            ccw_products<TL, true>(xo, d, lane, C);
-            Mi += ccw_isum2(pcm, nx, left_prev + np + 1, left + np, left_prev - np + 1, left - np, lane);
-            dn = d;
-        } else {
-            // the window is slid open from empty: blocks of <= CCW_DMAX samples
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                // C + new - old = -(-(C + new) + old): the subtraction costs two sign flips instead of a multiply per sample
+                if (pass == 1) {
 #pragma unroll
-            for (int u = 0; u < TL; u++) C[u] = 0.0;
-            A0i = 0; Q0i = 0;
-            int len = 0;
-            for (int j0 = 0; j0 < W; j0 += CCW_DMAX) {
-                len = W - j0 < CCW_DMAX ? W - j0 : CCW_DMAX;
-                int sN;
-                long long qN;
-                __syncwarp();
-                ccw_load(pcm, nx, lo + j0, len + NL + 1, len, xn, lane, sN, qN);
-                A0i += sN;
-                Q0i += qN;
-                __syncwarp();
-                ccw_products<TL, false>(xn, len, lane, C);
+                    for (int u = 0; u < TL; u++) C[u] = -C[u];
+                }
+                ccw_products<TL>(pass ? xo : xn, pass ? olen : len, lane, C);
+                if (pass == 1) {
+#pragma unroll
+                    for (int u = 0; u < TL; u++) C[u] = -C[u];
+                }
             }
-            int s0;
-            long long q0;
-            ccw_load(pcm, nx, lo - len, len + NL + 1, 0, xo, lane, s0, q0);     // so that xo[len + e] = s[lo + e] like xn
-            Mi = ccw_isum2(pcm, nx, left - np + 1, left + np, 1, 0, lane);
-            __syncwarp();
             dn = len;
-            have = true;
-        }
+        } while (!sliding && j0 < W);
+        if (sliding) Mi += ccw_isum2(pcm, nx, left_prev + np + 1, left + np, left_prev - np + 1, left - np);
+        else Mi = ccw_isum2(pcm, nx, left - np + 1, left + np, 1, 0);
+        have = true;
         lo_prev = lo; left_prev = left;
 
-        // ---- normalisation (same expressions as k_cc_frames_s; every sum below is exact)
+        // ---- raw-sample sums of every lag (exact), handed to the rolled normalisation loop through shared memory
         const double mu = ((double)Mi * (1.0 / 32768.0)) / (double)(2 * np);
         const double A0 = (double)A0i * (1.0 / 32768.0), Q0 = (double)Q0i * (1.0 / 1073741824.0);
-        const double wmm = (double)W * mu * mu;
-        const double sx = fma(-2.0 * mu, A0, Q0) + wmm;
         double da[TL], dq[TL];
         {
             const double* pn = xn + dn + TL * lane;
@@ -568,45 +629,18 @@ __device__ __noinline__ void ccw_segment(const Clips& c, const PitchPass& p, con
                 const double ua = __shfl_up_sync(FULL_MASK, ia, o), uq = __shfl_up_sync(FULL_MASK, iq, o);
                 if (lane >= o) { ia += ua; iq += uq; }
             }
-            const double ea = A0 + (ia - sa), eq = Q0 + (iq - sq);
+            const double ea = ia - sa, eq = iq - sq;              // exclusive: sum over the lower lanes
+            __syncwarp();                                         // every lane has read its window entries
 #pragma unroll
-            for (int u = 0; u < TL; u++) { da[u] += ea; dq[u] += eq; }     // A_lag, Q_lag of lag = 1 + TL lane + u
-        }
-        __syncwarp();                                             // xn / xo are free for the next frame; rr of the previous frame is consumed
-#pragma unroll
-        for (int u = 0; u < TL; u++) {
-            const int l = 1 + TL * lane + u;
-            double v = 0.0;
-            if (l <= Lloc) {
-                const double pr = fma(-mu, A0 + da[u], C[u]) + wmm;
-                const double sy = fma(-2.0 * mu, da[u], dq[u]) + wmm;
-                v = pr / sqrt(sx * sy);
+            for (int u = 0; u < TL; u++) {
+                const int l = 1 + TL * lane + u;
+                xn[l] = C[u];
+                xo[l] = A0 + (da[u] + ea);
+                rr[l] = Q0 + (dq[u] + eq);
             }
-            rr[l] = v;
-        }
-        if (lane == 0) rr[0] = 1.0;
-        // local peak: max |s - mean| over the middle of the (centred) analysis window, from the integer extremes
-        double localPeak;
-        {
-            const int right = left + 1;
-            int a0 = right - hp, a1 = right + hp - 1;
-            if (a0 < right - hw) a0 = right - hw;
-            if (a1 > right + hw - 1) a1 = right + hw - 1;
-            int vmin = 32767, vmax = -32768;
-            for (int i = a0 + lane; i <= a1; i += 32) {
-                const int v = (i >= 1 && i <= nx) ? (int)__ldg(pcm + i - 1) : 0;
-                vmin = v < vmin ? v : vmin;
-                vmax = v > vmax ? v : vmax;
-            }
-            vmin = __reduce_min_sync(FULL_MASK, vmin);
-            vmax = __reduce_max_sync(FULL_MASK, vmax);
-            localPeak = a1 >= a0 ? fmax(fabs((double)vmax * (1.0 / 32768.0) - mu), fabs((double)vmin * (1.0 / 32768.0) - mu)) : 0.0;
         }
         __syncwarp();
-        const int fidx = f + kk;
-        double* rrow = p.rbuf + (size_t)fidx * p.rstride;
-        for (int l = lane; l < Ls; l += 32) rrow[l] = l <= NL ? rr[l] : 0.0;
-        ccs_frame_tail(c, p, g, clip, fidx, rr, localPeak, gpeak, Lm, dx, lane);
+        ccw_finish(c, p, g, pcm, nx, clip, f + kk, left, Lloc, NL, mu, A0, Q0, warp_off);
     }
 }
 
