@@ -644,7 +644,8 @@ __device__ __noinline__ void ccw_segment(const Clips& c, const PitchPass& p, con
     }
 }
 
-__global__ void __launch_bounds__(CCW_NT, 2) k_cc_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
+template <int OCC>
+__global__ void __launch_bounds__(CCW_NT, OCC) k_cc_frames_w(const __grid_constant__ Clips c, const __grid_constant__ PitchPass p,
                                                            const __grid_constant__ CcwParams A) {
     const int lane = threadIdx.x & 31;
     const int total = p.fstart[c.n];
@@ -683,16 +684,19 @@ bool launch_cc_frames_warp(const Clips& c, const PitchPass& p, int max_frames_hi
     CcwParams A;
     A.pcm = c.pcm.p16;
     const size_t smem = (size_t)CCW_WARPS * CCW_WARP_DOUBLES * sizeof(double);
-    cudaFuncSetAttribute(k_cc_frames_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_cc_frames_w, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    static int occ_want = 0;
+    if (!occ_want) { const char* e = getenv("MSHDS_CCW_OCC"); occ_want = e && atoi(e) == 3 ? 3 : 2; }     // development switch (A/B)
+    const void* kfn = occ_want == 3 ? (const void*)k_cc_frames_w<3> : (const void*)k_cc_frames_w<2>;
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_cc_frames_w, CCW_NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, CCW_NT, smem);
     if (occ < 1) occ = 1;
     const int warps = sm_count() * occ * CCW_WARPS;
     // a run pays ~7 frames of start-up: long runs, but several turns per warp so that the tail stays short
     int run = max_frames_hint > 0 ? (max_frames_hint + 4 * warps - 1) / (4 * warps) : 128;
     if (run < 32) run = 32;
-    if (run > 128) run = 128;
+    if (run > 96) run = 96;
     static int run_env = -1;
     if (run_env < 0) { const char* e = getenv("MSHDS_CCW_RUN"); run_env = e ? atoi(e) : 0; }      // development switch (A/B)
     if (run_env > 0) run = run_env;
@@ -705,7 +709,8 @@ bool launch_cc_frames_warp(const Clips& c, const PitchPass& p, int max_frames_hi
     cudaMemsetAsync(p.turn_counter, 0, sizeof(int), s);
     if (p.hnr_mode) cudaMemsetAsync(p.qcount64, 0, sizeof(unsigned long long), s);
     else cudaMemsetAsync(p.qcount, 0, sizeof(int), s);
-    k_cc_frames_w<<<grid, CCW_NT, smem, s>>>(c, p, A);
+    if (occ_want == 3) k_cc_frames_w<3><<<grid, CCW_NT, smem, s>>>(c, p, A);
+    else k_cc_frames_w<2><<<grid, CCW_NT, smem, s>>>(c, p, A);
     return true;
 }
 

@@ -8,7 +8,7 @@ set -u
 mkdir -p gpurun_out
 what="${*:-configs launches full}"
 M="gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,dram__bytes_read.sum,dram__bytes_write.sum"
-K='regex:k_ac_frames_w|k_ac_candidates|k_pitch_frames|k_hnr_refine|k_pitch_refine|k_cepstrogram_w|k_cpp_frames_warp|k_formant_frames|k_spec_frames_w|k_sinc_fir|k_fft_inner|k_fft_strided|k_cc_frames_s|k_pulses_stretch|k_pitch_viterbi|k_ltas_accum|k_intensity_frames'
+K='regex:k_ac_frames_w|k_ac_candidates|k_pitch_frames|k_hnr_refine|k_pitch_refine|k_cepstrogram_w|k_cpp_frames_warp|k_formant_frames|k_spec_frames_w|k_sinc_fir|k_fft_inner|k_fft_strided|k_cc_frames_w|k_pulses_stretch|k_pitch_viterbi|k_ltas_accum|k_intensity_frames'
 if [[ $what == *configs* ]]; then
   for c in 0 2 3 4; do
     timeout 600 python bench.py --config $c --steps 2 --warmup 1 > gpurun_out/bench_config$c.json 2> gpurun_out/bench_config$c.err
@@ -30,7 +30,7 @@ if [[ $what == *full* ]]; then
   echo "full capture rc=$?"
   ncu -i $REP.ncu-rep --page raw --csv > gpurun_out/r02_top_kernels_raw.csv 2>> gpurun_out/ncu_full.log
   for k in k_ac_frames_w k_ac_candidates k_pitch_frames k_hnr_refine k_pitch_refine k_cepstrogram_w k_cpp_frames_warp k_formant_frames \
-           k_cc_frames_s k_sinc_fir k_fft_inner k_pulses_stretch k_ltas_accum k_intensity_frames k_spec_frames_w; do
+           k_cc_frames_w k_sinc_fir k_fft_inner k_pulses_stretch k_ltas_accum k_intensity_frames k_spec_frames_w; do
     ncu -i $REP.ncu-rep --page source --csv --kernel-id "::regex:$k:1" > gpurun_out/r02_src_$k.csv 2>/dev/null
     [ -s gpurun_out/r02_src_$k.csv ] || rm -f gpurun_out/r02_src_$k.csv
   done

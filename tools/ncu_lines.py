@@ -1,5 +1,5 @@
 """Development aid: attribute ncu warp-stall samples of one kernel to CUDA source lines.
-usage: ncu_lines.py <report.ncu-rep> <kernel-regex> <nth match (1-based)> <cubin-name-substring e.g. k_pitch> <mangled-substring>"""
+usage: ncu_lines.py <report.ncu-rep | exported source page .csv> <kernel-regex> <nth match (1-based)> <cubin-name-substring e.g. k_pitch> <mangled-substring> [top_n]"""
 import collections
 import csv
 import os
@@ -31,16 +31,23 @@ for l in sass.split("\n"):
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m and func and mangled in func:
         off2line[int(m.group(1), 16)] = (file, line)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f"::regex:{kre}:{nth}"], capture_output=True, text=True).stdout
+if rep.endswith(".csv"):
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-id", f"::regex:{kre}:{nth}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 print(rows[0][:2])
 hdr = rows[1]
 ai, ni, ii = hdr.index("Address"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 base = int(rows[2][ai], 16)
 agg, inst, tot = collections.Counter(), collections.Counter(), 0
+seen = set()
 for r in rows[2:]:
     try:
         a = int(r[ai], 16) - base
+        if a in seen:           # ncu repeats the table when the kernel-id matches more than one view
+            break
+        seen.add(a)
         n = int(r[ni])
     except Exception:
         continue
