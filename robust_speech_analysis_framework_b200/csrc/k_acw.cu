@@ -234,7 +234,17 @@ __device__ __noinline__ void acw_frame(const Clips& c, const PitchPass& p, const
         const int f = sg.f0 + fi;
         double* rrow = p.rbuf + (size_t)f * p.rstride;
         const double ac0 = acs[0];
-        for (int i = j; i <= B; i += L) rrow[i] = i == 0 ? 1.0 : acs[i] / (ac0 * __ldg(g.windowR + i));
+        // four window-autocorrelation values in flight per trip (two warps per scheduler cannot hide one L1/L2 round trip per lag)
+        for (int i0 = j; i0 <= B; i0 += 4 * L) {
+            double wr[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int i = i0 + u * L; wr[u] = i <= B ? __ldg(g.windowR + i) : 1.0; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * L;
+                if (i <= B) rrow[i] = i == 0 ? 1.0 : acs[i] / (ac0 * wr[u]);
+            }
+        }
         if (j == 0) {
             p.inten[f] = intensity;
             p.ncand[f] = localPeak != 0.0 ? 1 : 0;        // hand-over to k_ac_candidates: "the frame has a local peak"
