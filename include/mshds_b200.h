@@ -73,11 +73,16 @@ int mshds_reset_stream(mshds_handle* h);
 /* Development / test switches; none selects a CPU path or changes a result.  Unknown names return MSHDS_ERR_ARG.
  *   "legacy_fft"     1: CTA-per-frame shared-memory FFT frame kernels (round 1) instead of the warp-per-frame register FFT with
  *                       TMA-staged sample spans; same results up to the rounding of another exact FFT order (A/B timing, tests)
+ *   "legacy_cc"      1: frame-by-frame cross-correlation frames (round 1); 2: CTA block-ring kernel; 0 (default): one warp per
+ *                       run of frames with exact sliding sums.  1 differs from 0 / 2 by rounding only, 0 and 2 are bit-identical
  *   "overlap"        0: issue the latency-bound per-clip kernels on the main stream instead of the side stream
  *   "nvtx"           1: emit one NVTX range per pipeline stage */
 int mshds_set_option(mshds_handle* h, const char* name, long long value);
 
-/* Upper bound, in samples, of the sub-batches the handle processes at once (scratch memory scales with it). */
+/* Upper bound, in samples, of the sub-batches the handle processes at once (scratch memory scales with it: ~170 B per sample).
+ * Default: 2^27 samples (20 GB of scratch), grown automatically for batches of long recordings -- up to 128 recordings per
+ * sub-batch, at most 2^29 samples and half of the free device memory -- because the per-recording sequential stages (path
+ * finder, glottal-pulse walk) only fill the GPU through the number of recordings in flight.  Calling this fixes the size. */
 int mshds_set_chunk_samples(mshds_handle* h, long long max_samples);
 
 /* Human-readable description of the last non-zero return code of this handle. */

@@ -48,6 +48,7 @@ struct mshds_handle {
     std::string err;
     long long launches = 0;
     long long chunk_samples = 1LL << 27;
+    bool chunk_auto = true;             // no mshds_set_chunk_samples call yet: long recordings may get larger chunks (mshds_extract)
     // persistent tables
     double2* tw = nullptr;
     double2* twb512 = nullptr;          // pass twiddles of the warp-resident transforms (fftreg.cuh), [32][M / 32]
@@ -1081,6 +1082,7 @@ int mshds_set_option(mshds_handle* h, const char* name, long long value) {
 int mshds_set_chunk_samples(mshds_handle* h, long long max_samples) {
     if (!h || max_samples < 1) return MSHDS_ERR_ARG;
     h->chunk_samples = max_samples;
+    h->chunk_auto = false;
     return MSHDS_OK;
 }
 
@@ -1109,12 +1111,32 @@ int mshds_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, i
     const bool doubling = sample_rate == 8000;        // Sound_resample hands an exact doubling to Sound_upsample
     const double fs = 16000.0;
 
+    // Chunk size.  The path finders and pulse walks are sequential per recording (one CTA / a few warps each) and only fill the
+    // GPU through the number of recordings in flight: 2^27 samples are 279 clips of 30 s but only ~25 recordings of 5 minutes
+    // (BASELINE.json configs[2]: 13.1 k audio-s/s at 2^27, 16.2 k at 2^29).  Unless the caller fixed the size, long
+    // recordings therefore get chunks of up to 128 of them, bounded by 2^29 samples and by half of the free device memory
+    // (the scratch arena takes ~170 B per sample).
+    long long chunk_samples = h->chunk_samples;
+    if (h->chunk_auto && !front && n_clips > 0) {
+        const long long total = offsets[n_clips] - offsets[0];
+        const long long want = (total / n_clips) * 128;
+        if (want > chunk_samples) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+                const long long fit = (long long)((free_b + h->arena_cap) / 2 / 200);
+                long long grown = want < (1LL << 29) ? want : (1LL << 29);
+                if (grown > fit) grown = fit;
+                if (grown > total) grown = total;
+                if (grown > chunk_samples) chunk_samples = grown;
+            }
+        }
+    }
     int c0 = 0;
     while (c0 < n_clips) {
         // clips [c0, c1) form one chunk
         int c1 = c0;
         long long tot = 0;
-        while (c1 < n_clips && (c1 == c0 || tot + (offsets[c1 + 1] - offsets[c1]) <= h->chunk_samples)) {
+        while (c1 < n_clips && (c1 == c0 || tot + (offsets[c1 + 1] - offsets[c1]) <= chunk_samples)) {
             tot += offsets[c1 + 1] - offsets[c1];
             c1++;
         }
