@@ -12,24 +12,47 @@ import numpy as np
 
 
 def lpt_assign(lengths: Sequence[int], world_size: int) -> list[list[int]]:
-    """Greedy LPT: clips sorted by length (desc, stable) go to the currently least-loaded rank."""
-    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
-    loads = [0] * world_size
-    parts: list[list[int]] = [[] for _ in range(world_size)]
+    """Greedy LPT: clips sorted by length (desc, stable) go to the currently least-loaded rank (ties: lowest rank).  Clips of
+    equal length are interchangeable, so within every group of equal lengths the indices are then dealt out in input order,
+    rank by rank, keeping every rank's count of that length: same loads, but runs of consecutive clips stay together (a corpus
+    of equal-length clips shards into contiguous blocks that pack without a copy)."""
+    import heapq
+
+    lengths = np.asarray(lengths, dtype=np.int64)
+    n = len(lengths)
+    order = np.lexsort((np.arange(n), -lengths))                  # by length desc, then index
+    heap = [(0, r) for r in range(world_size)]
+    owner = np.empty(n, dtype=np.int64)
     for i in order:
-        r = min(range(world_size), key=lambda k: (loads[k], k))
-        parts[r].append(i)
-        loads[r] += int(lengths[i])
-    for p in parts:
-        p.sort()
-    return parts
+        load, r = heapq.heappop(heap)
+        owner[i] = r
+        heapq.heappush(heap, (load + int(lengths[i]), r))
+    # regroup equal lengths: order[] lists every length group contiguously, indices ascending inside a group
+    sorted_len = lengths[order]
+    bounds = np.flatnonzero(np.diff(sorted_len)) + 1
+    for g in np.split(order, bounds):
+        if len(g) < 2:
+            continue
+        counts = np.bincount(owner[g], minlength=world_size)
+        owner[g] = np.repeat(np.arange(world_size), counts)
+    return [np.flatnonzero(owner == r).tolist() for r in range(world_size)]
 
 
 def pack_subset(pcm: np.ndarray, offsets: np.ndarray, idx: Sequence[int]):
-    """Packed (pcm, offsets) of the chosen clips, in the given order."""
-    chunks = [pcm[offsets[i]: offsets[i + 1]] for i in idx]
-    offs = np.cumsum([0] + [len(c) for c in chunks]).astype(np.int64)
-    data = np.concatenate(chunks) if chunks else np.zeros(0, dtype=pcm.dtype)
+    """Packed (pcm, offsets) of the chosen clips, in the given order.  Runs of consecutive clips are copied as one slice; a
+    single run is returned as a view of `pcm` (no copy)."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if len(idx) == 0:
+        return np.zeros(0, dtype=pcm.dtype), np.zeros(1, dtype=np.int64)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lens = offsets[idx + 1] - offsets[idx]
+    offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    breaks = np.flatnonzero(np.diff(idx) != 1) + 1
+    starts = np.concatenate(([0], breaks))
+    ends = np.concatenate((breaks, [len(idx)]))
+    if len(starts) == 1:
+        return pcm[offsets[idx[0]]: offsets[idx[-1] + 1]], offs
+    data = np.concatenate([pcm[offsets[idx[a]]: offsets[idx[b - 1] + 1]] for a, b in zip(starts, ends)])
     return data, offs
 
 
