@@ -739,9 +739,9 @@ void launch_pitch_score(const Clips& c, const PitchPass& p, int max_frames_hint,
 // Now ONE CTA of 256 threads owns a clip: thread (c2, c1) = (tid / 16, tid % 16) forms the one value of its candidate
 // pair, the 16 lanes of a half-warp reduce over c1 with four shuffle steps (ties go to the lower index), the state lives in
 // double-buffered shared memory and each frame costs one block barrier.  Candidate rows are prefetched in register tiles
-// of 4 frames.  The total thread-instruction count per frame is what the warp version spent on idle and duplicated lanes.
+// of 8 frames.  The total thread-instruction count per frame is what the warp version spent on idle and duplicated lanes.
 #define VIT_NT 256
-__global__ void __launch_bounds__(VIT_NT, 4) k_pitch_viterbi(Clips c, PitchPass p) {
+__global__ void __launch_bounds__(VIT_NT, 2) k_pitch_viterbi(Clips c, PitchPass p) {
     __shared__ double s_delta[2][16], s_lf[2][16];
     const int tid = threadIdx.x, lane = tid & 31;
     const int clip = blockIdx.x;
@@ -754,7 +754,7 @@ __global__ void __launch_bounds__(VIT_NT, 4) k_pitch_viterbi(Clips c, PitchPass 
     const int c2 = tid >> 4, c1 = tid & 15;                 // c2 == 15 and c1 == 15 are idle (MAXCAND = 15)
     const unsigned hmask = 0xffffu << (lane & 16);          // the half-warp that shares this c2
 
-    constexpr int VT = 4;
+    constexpr int VT = 8;            // a tile has to cover a DRAM round trip: 4 frames did not (ncu: 27 % long-scoreboard stalls)
     double tsc[VT], tlf[VT], nsc[VT], nlf[VT];
     int tnc[VT], nnc[VT];
     auto load_tile = [&](int i0, double (&sc_)[VT], double (&lf_)[VT], int (&nc_)[VT]) {
