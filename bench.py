@@ -630,6 +630,19 @@ def bench_lld_sweep(args):
             rows.append({"n_fft": n_fft, "n_mel": n_mel, "audio_s_per_s": C.world * audio_s / (ms / 1e3),
                          "e2e_audio_s_per_s": C.world * audio_s / (ms_h / 1e3), "ms_per_step": ms,
                          "hbm_gbs": alg / (ms / 1e3) / 1e9, "hbm_frac": alg / (ms / 1e3) / 1e9 / hbm})
+    # the widest descriptor / functional set built so far (Androids.conf defaults: n_fft 512, 26 mel bands): 720 columns
+    full = dict(descriptor_set=1, functional_set=1)
+    out_full = torch.empty((clips, 720), dtype=torch.float64, device=C.dev)
+
+    def full_step():
+        ex.lld_extract_device(pcm_d.data_ptr(), off_np, out_full.data_ptr(), 16000, **full)
+
+    with torch.cuda.stream(C.stream):
+        for _ in range(3):
+            full_step()
+    ms_full, _ = C.timed(full_step, args.steps)
+    ms_full /= args.steps
+    full_row = {"columns": 720, "audio_s_per_s": C.world * audio_s / (ms_full / 1e3), "ms_per_step": ms_full}
     if C.rank != 0:
         C.close()
         return 0
@@ -647,6 +660,7 @@ def bench_lld_sweep(args):
                    "columns": "MFCC 1-12 + RMS energy + ZCR, smoothed + deltas, mean / stddev (56 columns; parity unpinned: no SMILExtract binary)"},
         "e2e": {"value": best["e2e_audio_s_per_s"], "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm_h.nbytes), "d2h_bytes_per_step": int(clips * 56 * 8)},
         "sweep": rows,
+        "androids_720_columns": full_row,
         "roofline": {"bound": "hbm", "achieved": best["hbm_gbs"], "peak": hbm, "unit": "GB/s", "frac": best["hbm_frac"], "peak_source": src,
                      "traffic": None},
         "cpu_baseline": {"value": nref * seconds / cpu_s, "unit": "audio-s/s", "cores": 1, "kind": "port",

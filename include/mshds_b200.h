@@ -160,9 +160,30 @@ int mshds_extract_contours(mshds_handle* h, const int16_t* pcm, const int64_t* o
  *               times 1 + (L / 2) sin(pi i / L) for cep_lifter L > 0
  *   smoothing   y_t = mean(x_{t-h} .. x_{t+h}), h = smooth_win / 2, frames beyond the ends of the recording repeat the end frame
  *   delta       d_t = sum_{i=1..delta_win} i (y_{t+i} - y_{t-i}) / (2 sum i^2), same end rule
- * Row layout of a frame: the D = n_mfcc + 2 (smoothed) descriptors mfcc[1..n_mfcc], energy, zcr, then -- if delta_win > 0 --
- * their D deltas: W = D or 2D values.  functionals: n_clips x 2W (W means, then W population standard deviations; NaN for a
- * clip without a complete frame).  frames_out (optional, may be NULL): all frame
+ * Second slice, descriptor_set = 1 (Androids.conf:134-140 cIntensity, :257-282 cSpectral), 16 more descriptors per frame, in
+ * this order; v = the pre-emphasised, windowed frame, |X[k]| its magnitude spectrum, S[k] = |X[k]|^2 (cSpectral squareInput),
+ * f_k = k fs / n_fft, k = 0 .. n_fft/2 (N bins):
+ *   intensity   (sum_j w[j] v[j]^2 / sum_j w[j]) / I0, I0 = 1e-6, w the Hamming window (cIntensity weights the frame once more)
+ *   loudness    intensity^0.3
+ *   fband       sum of S[k] over the bins with 250 <= f_k <= 650 Hz, and with 1000 <= f_k <= 4000 Hz (whole bins; OpenSMILE
+ *               interpolates the two edge bins)
+ *   rollOff     f_k of the first bin whose cumulative energy sum_{j<=k} S[j] reaches 25 / 50 / 75 / 90 % of sum S
+ *   flux        sqrt( sum_k (|X_t[k]| - |X_t-1[k]|)^2 / N ), 0 for the first frame of a recording
+ *   centroid    c = sum f_k S[k] / sum S;  variance = sum (f_k - c)^2 S[k] / sum S;  skewness, kurtosis = the third and fourth
+ *               central moments over variance^1.5 and variance^2 (not excess);  entropy = - sum p_k log2 p_k, p_k = S[k] / sum S
+ *   slope       least-squares slope of S[k] over f_k (per Hz);  flatness = exp(mean ln max(S[k], 1e-100)) / mean S[k]
+ *   NOT built: psySharpness, spectralHarmonicity (:276,:278), the SHS pitch / Viterbi smoother (:142-213), jitter / shimmer
+ *   (:231-248).  Open questions that cannot be settled without the SMILExtract binary are listed in DESIGN.md (float32
+ *   internals, htkcompatible sample scaling, edge-bin interpolation of the bands, time normalisation of the functionals).
+ * Row layout of a frame: the D (smoothed) descriptors mfcc[1..n_mfcc], energy, zcr [, the 16 above], then -- if
+ * delta_win > 0 -- their D deltas: W = D or 2D values, D = n_mfcc + 2 [+ 16].
+ * functionals: n_clips x NF x W, functional-major (NaN for a clip without a complete frame).  functional_set = 0: NF = 2,
+ * amean then stddev (population).  functional_set = 1: NF = 12 in the order of Androids.conf functL1 (:349-366) --
+ *   Extremes   max, min, range = max - min, maxPos, minPos (frame index of the first maximum / minimum), amean
+ *   Regression linregc1 = slope m and linregc2 = offset b of the least-squares line y = m t + b over t = 0 .. T-1 (frames),
+ *              linregerrQ = mean (y_t - (m t + b))^2
+ *   Moments    stddev (population), skewness = m3 / m2^1.5, kurtosis = m4 / m2^2 (both 0 for a contour that is constant up to
+ *              rounding: stddev <= 1e-12 of its largest absolute value)  frames_out (optional, may be NULL): all frame
  * rows, clips back to back; frame_offsets (optional HOST array, n_clips + 1) receives the first row of every clip.
  * flags: MSHDS_PCM_ON_DEVICE / MSHDS_OUT_ON_DEVICE as for mshds_extract (the latter covers functionals and frames_out).
  */
@@ -177,6 +198,8 @@ typedef struct mshds_lld_params {
     double cep_lifter;      /*       22      cMfcc default */
     int smooth_win;         /* frames 3      cContourSmoother default smaWin (Androids.conf lld/lld2/lld3); <= 1: no smoothing */
     int delta_win;          /* frames 2      cDeltaRegression deltawin (Androids.conf delta1..3); 0: no delta columns */
+    int descriptor_set;     /*       0       0: MFCC, energy, ZCR; 1: + cIntensity and cSpectral descriptors (16 more, see above) */
+    int functional_set;     /*       0       0: amean, stddev; 1: the twelve functionals of Androids.conf functL1 (see above) */
 } mshds_lld_params;
 void mshds_lld_default_params(mshds_lld_params* p);
 int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,

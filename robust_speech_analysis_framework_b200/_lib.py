@@ -44,7 +44,8 @@ class LldParams(C.Structure):
     """struct mshds_lld_params (include/mshds_b200.h)."""
     _fields_ = [("frame_size", C.c_double), ("frame_step", C.c_double), ("preemph", C.c_double), ("n_fft", C.c_int),
                 ("n_mel", C.c_int), ("mel_lo", C.c_double), ("mel_hi", C.c_double), ("n_mfcc", C.c_int),
-                ("cep_lifter", C.c_double), ("smooth_win", C.c_int), ("delta_win", C.c_int)]
+                ("cep_lifter", C.c_double), ("smooth_win", C.c_int), ("delta_win", C.c_int),
+                ("descriptor_set", C.c_int), ("functional_set", C.c_int)]
 
 
 def load(build_if_needed: bool = True) -> C.CDLL:
@@ -196,13 +197,14 @@ class Extractor:
         return p
 
     def lld_extract(self, pcm: np.ndarray, offsets: np.ndarray, sample_rate: int = 16000, want_frames: bool = False, **params):
-        """mshds_lld_extract on host arrays -> (functionals [n, 2D], frames [total, D] or None, frame_offsets [n + 1])."""
+        """mshds_lld_extract on host arrays -> (functionals [n, NF * D], frames [total, D] or None, frame_offsets [n + 1]);
+        D = width of a frame row, NF = 2 (amean, stddev) or 12 (functional_set = 1), functional-major."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         n = len(offsets) - 1
         p = self.lld_params(**params)
-        D = (p.n_mfcc + 2) * (2 if p.delta_win > 0 else 1)           # width of a frame row
-        fun = np.full((max(n, 0), 2 * D), np.nan)
+        D = (p.n_mfcc + 2 + (16 if p.descriptor_set else 0)) * (2 if p.delta_win > 0 else 1)           # width of a frame row
+        fun = np.full((max(n, 0), (12 if p.functional_set else 2) * D), np.nan)
         fo = np.zeros(n + 1, dtype=np.int64)
         frames = None
         if want_frames:

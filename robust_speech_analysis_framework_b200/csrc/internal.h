@@ -137,6 +137,9 @@ struct LldPass {
     int nf, ns;                 // frame length / step in samples
     int n_fft, M, logM;         // transform size, M = n_fft / 2
     int n_mel, n_mfcc;
+    int desc, fset, D0;         // descriptor_set, functional_set, raw descriptors per frame (n_mfcc + 2, + 16 with descriptor_set 1)
+    double fs, win_sum;         // sampling frequency, sum of the Hamming window (cIntensity)
+    double band_lo[2], band_hi[2], rolloff[4];   // cSpectral bands[] / rollOff[] (Androids.conf:261-266)
     double preemph, lifter, dct_scale, log_floor;
     const double* window;       // [nf] Hamming
     const double* melbin;       // [M + 1] mel value of every bin

@@ -1293,6 +1293,7 @@ void mshds_lld_default_params(mshds_lld_params* p) {
     if (!p) return;
     p->frame_size = 0.025; p->frame_step = 0.010; p->preemph = 0.97; p->n_fft = 0; p->n_mel = 26;
     p->mel_lo = 20.0; p->mel_hi = 8000.0; p->n_mfcc = 12; p->cep_lifter = 22.0; p->smooth_win = 3; p->delta_win = 2;
+    p->descriptor_set = 0; p->functional_set = 0;
 }
 
 int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offsets, int n_clips, int sample_rate,
@@ -1315,12 +1316,14 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     if (P.smooth_win < 0 || P.smooth_win > 101 || (P.smooth_win > 1 && P.smooth_win % 2 == 0) || P.delta_win < 0 || P.delta_win > 50) { h->err = "smooth_win must be odd (or <= 1), delta_win in [0, 50]"; return MSHDS_ERR_ARG; }
     const double hi = P.mel_hi < 0.5 * fs ? P.mel_hi : 0.5 * fs;
     if (!(P.mel_lo >= 0.0 && P.mel_lo < hi)) { h->err = "bad mel range"; return MSHDS_ERR_ARG; }
+    if (P.descriptor_set < 0 || P.descriptor_set > 1 || P.functional_set < 0 || P.functional_set > 1) { h->err = "descriptor_set / functional_set must be 0 or 1"; return MSHDS_ERR_ARG; }
     if (n_clips == 0) return MSHDS_OK;
     CK(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     h->cur = s;
     const bool pcm_dev = (flags & MSHDS_PCM_ON_DEVICE) != 0, out_dev = (flags & MSHDS_OUT_ON_DEVICE) != 0;
-    const int M = n_fft / 2, D0 = P.n_mfcc + 2;
+    const int M = n_fft / 2, D0 = P.n_mfcc + 2 + (P.descriptor_set ? 16 : 0);
+    const int NF = P.functional_set ? 12 : 2;          // functionals per contour
     const bool post = P.smooth_win > 1 || P.delta_win > 0;
     const int D = D0 * (P.delta_win > 0 ? 2 : 1);          // width of a final row
     int logM = 0; while ((1 << logM) < M) logM++;
@@ -1358,7 +1361,7 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     const size_t o_klo = sz(sizeof(int) * P.n_mel), o_khi = sz(sizeof(int) * P.n_mel), o_dct = sz(sizeof(double) * dct.size());
     const size_t o_raw = post ? sz(sizeof(double) * (size_t)(total_frames + 1) * D0) : 0;
     const size_t o_fr = (out_dev && frames_out) ? 0 : sz(sizeof(double) * (size_t)(total_frames + 1) * D);
-    const size_t o_fun = out_dev ? 0 : sz(sizeof(double) * (size_t)n_clips * 2 * D);
+    const size_t o_fun = out_dev ? 0 : sz(sizeof(double) * (size_t)n_clips * NF * D);
     const size_t o_pcm = pcm_dev ? 0 : sz((size_t)total * 2 + 16);
     if (need > h->lld_cap) {
         CK(cudaStreamSynchronize(s));
@@ -1386,8 +1389,13 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     L.final = (out_dev && frames_out) ? frames_out : (double*)(Bf + o_fr);
     L.frames = post ? (double*)(Bf + o_raw) : L.final;
     L.smooth_win = P.smooth_win; L.delta_win = P.delta_win; L.W = D;
+    L.desc = P.descriptor_set; L.fset = P.functional_set; L.D0 = D0; L.fs = fs;
+    L.win_sum = 0.0;
+    for (int j = 0; j < nf; j++) L.win_sum += window[j];
+    L.band_lo[0] = 250.0; L.band_hi[0] = 650.0; L.band_lo[1] = 1000.0; L.band_hi[1] = 4000.0;       // Androids.conf:261-262
+    L.rolloff[0] = 0.25; L.rolloff[1] = 0.50; L.rolloff[2] = 0.75; L.rolloff[3] = 0.90;                // Androids.conf:263-266
     double* d_fun = out_dev ? functionals : (double*)(Bf + o_fun);
-    PB("lld_frames[mfcc+energy+zcr]");
+    PB(P.descriptor_set ? "lld_frames[mfcc+energy+zcr+intensity+spectral]" : "lld_frames[mfcc+energy+zcr]");
     launch_lld_grid(n_clips, (const long long*)(Bf + o_off), nf, ns, L.nF, L.fstart, s);
     launch_lld_frames(L, d_pcm, (const long long*)(Bf + o_off), n_clips, h->tw, total_frames, s);
     PE();
@@ -1398,7 +1406,7 @@ int mshds_lld_extract(mshds_handle* h, const int16_t* pcm, const int64_t* offset
     h->launches += 4;
     CK(cudaGetLastError());
     if (!out_dev) {
-        CK(cudaMemcpyAsync(functionals, d_fun, sizeof(double) * (size_t)n_clips * 2 * D, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(functionals, d_fun, sizeof(double) * (size_t)n_clips * NF * D, cudaMemcpyDeviceToHost, s));
         if (frames_out && total_frames > 0)
             CK(cudaMemcpyAsync(frames_out, L.final, sizeof(double) * (size_t)total_frames * D, cudaMemcpyDeviceToHost, s));
     }

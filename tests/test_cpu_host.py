@@ -403,11 +403,16 @@ def test_lld_dataframe_contract(tmp_path, monkeypatch):
     pa, pb = str(tmp_path / "a.wav"), str(tmp_path / "b44.wav")
     _write_wav(pa, a)
     _write_wav(pb, a, fs=44100)
-    df = lx.extract_lld_functionals(pd.DataFrame({"filepath": [pa, str(tmp_path / "nope.wav"), pb]}), verbose=False)
+    frame = pd.DataFrame({"filepath": [pa, str(tmp_path / "nope.wav"), pb]})
+    df = lx.extract_lld_functionals(frame, verbose=False, descriptor_set=0, functional_set=0)      # the first slice
     assert list(df.columns) == ["filename"] + lx.functional_names() and df.shape == (3, 57)
     assert df.iloc[1, 1:].isna().all() and not df.iloc[0, 1:].isna().any() and not df.iloc[2, 1:].isna().any()
     assert df.columns[1] == "mfcc_sma[1]_amean" and df.columns[-1] == "pcm_zcr_sma_de_stddev"
     assert "pcm_RMSenergy_sma_amean" in df.columns and "mfcc_sma_de[12]_stddev" in df.columns
+    full = lx.extract_lld_functionals(frame, verbose=False)                                         # default: the widest set
+    assert full.shape == (3, 721) and list(full.columns[1:]) == lx.functional_names(descriptor_set=1, functional_set=1)
+    assert full.iloc[1, 1:].isna().all() and not full.iloc[0, 1:].isna().any()
+    assert np.allclose(full["mfcc_sma[1]_amean"].values[[0, 2]], df["mfcc_sma[1]_amean"].values[[0, 2]])
 
 
 def test_reference_probe_switches_to_the_real_extractor_when_it_is_importable(orc):
@@ -476,3 +481,34 @@ def test_register_fft_core_against_direct_dft(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "fftreg_host_test.cpp")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_lld_oracle_functionals_and_spectral_descriptors_known_answers():
+    """oracle/lld_oracle.py second slice against independent formulas: the twelve functionals vs numpy / scipy, spectral
+    descriptors of a pure tone (centroid and roll-off at the tone, tiny flatness, flux 0 for a stationary signal), and the
+    OpenSMILE-style column names of the host mirror."""
+    import scipy.stats as st
+    from oracle import lld_oracle as lo
+    from robust_speech_analysis_framework_b200.lld_extractor import functional_names
+    rng = np.random.default_rng(11)
+    y = rng.normal(size=(200, 3)) + np.linspace(0, 2, 200)[:, None] * np.array([1.0, -0.5, 0.0])[None, :]
+    F = lo.functionals12(y)
+    t = np.arange(200.0)
+    for c in range(3):
+        m, b = np.polyfit(t, y[:, c], 1)
+        np.testing.assert_allclose(F[6:8, c], [m, b], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(F[8, c], np.mean((y[:, c] - (m * t + b)) ** 2), rtol=1e-9)
+        np.testing.assert_allclose(F[9:12, c], [y[:, c].std(), st.skew(y[:, c]), st.kurtosis(y[:, c], fisher=False)], rtol=1e-9)
+        assert F[3, c] == np.argmax(y[:, c]) and F[4, c] == np.argmin(y[:, c]) and F[2, c] == F[0, c] - F[1, c]
+        np.testing.assert_allclose(F[5, c], y[:, c].mean(), rtol=1e-12)
+    fs = 16000.0
+    x = 0.5 * np.sin(2 * np.pi * 2000.0 * np.arange(int(0.5 * fs)) / fs)
+    rows = lo.frame_lld(x, fs, descriptor_set=1, smooth_win=0, delta_win=0)
+    q = rows[5:-5, 14:]
+    assert np.all(np.abs(q[:, 9] - 2000.0) < 40.0) and np.all(np.abs(q[:, 5] - 2000.0) <= fs / 512)      # centroid, 50 % roll-off
+    assert np.all(q[:, 15] < 1e-3) and np.all(q[:, 8] < 1e-2 * np.sqrt(q[:, 0] * 1e-6))                     # flatness, flux
+    assert np.all(q[:, 3] > 100 * q[:, 2])                                                                    # 1-4 kHz band holds the tone
+    np.testing.assert_allclose(q[:, 1], q[:, 0] ** 0.3, rtol=1e-12)
+    names = functional_names(descriptor_set=1, functional_set=1)
+    assert len(names) == 720 and names[0] == "mfcc_sma[1]_max" and "pcm_fftMag_spectralRollOff90.0_sma_de_kurtosis" in names
+    assert len(functional_names()) == 56 and functional_names()[0] == "mfcc_sma[1]_amean"

@@ -551,6 +551,49 @@ def test_lld_frames_and_functionals_match_the_numpy_restatement(ex, fs, params):
     np.testing.assert_allclose(fun, wfun, rtol=1e-9, atol=1e-9, equal_nan=True)
 
 
+@pytest.mark.parametrize("fs,params", [(16000, {}), (44100, {}), (16000, {"n_fft": 1024, "smooth_win": 0, "delta_win": 0})])
+def test_lld_spectral_descriptors_and_the_twelve_functionals_match_the_numpy_restatement(ex, fs, params):
+    """Second slice of the OpenSMILE path (descriptor_set = 1, functional_set = 1): cIntensity, 14 cSpectral descriptors and the
+    twelve functionals of Androids.conf functL1 against oracle/lld_oracle.py.  Frames: 1e-8 relative, absolute tolerance scaled
+    by the largest value of the column (band energies span 12 decades); roll-off bins and extreme positions are indices and
+    must agree exactly; functionals: 1e-6 relative with the same column scaling (third / fourth moments of near-constant
+    contours amplify the summation order)."""
+    from oracle import lld_oracle as lo
+    from robust_speech_analysis_framework_b200.lld_extractor import functional_names
+    from robust_speech_analysis_framework_b200.synth import synth_clip
+    rng = np.random.default_rng(5)
+    clips = [synth_clip(620 + i, d, fs=fs).numpy() for i, d in enumerate([1.5, 0.73, 2.2])]
+    clips += [np.zeros(0, np.int16), np.zeros(int(0.3 * fs), np.int16), (rng.normal(scale=3000, size=int(0.5 * fs))).astype(np.int16),
+              synth_clip(630, 0.03, fs=fs).numpy()]                                     # the last one has a single frame
+    pcm = np.concatenate(clips)
+    off = np.cumsum([0] + [len(c) for c in clips]).astype(np.int64)
+    kw = dict(descriptor_set=1, functional_set=1, **params)
+    fun, frames, fo = ex.lld_extract(pcm, off, fs, want_frames=True, **kw)
+    wfun, wrows = lo.extract(pcm, off, float(fs), **kw)
+    W = wrows[0].shape[1]
+    names = functional_names(12, params.get("smooth_win", 3), params.get("delta_win", 2), 1, 1)
+    assert fun.shape == wfun.shape == (len(clips), 12 * W) and len(names) == 12 * W
+    assert list(np.diff(fo)) == [len(r) for r in wrows] and frames.shape == (int(fo[-1]), W)
+    want = np.concatenate([r for r in wrows if len(r)])
+    scale = np.abs(want).max(axis=0) + 1e-300
+    assert np.all(np.abs(frames - want) <= 1e-8 * np.abs(want) + 1e-9 * scale[None, :]), "frame rows"
+    if not params.get("smooth_win", 3) and not params.get("delta_win", 2):
+        assert np.array_equal(frames[:, 18:22], want[:, 18:22])                         # raw roll-off points: bin frequencies
+    assert np.array_equal(np.isnan(fun), np.isnan(wfun)) and np.isnan(fun[3]).all()
+    for i in range(len(clips)):
+        if np.isnan(wfun[i]).all():
+            continue
+        g, w = fun[i].reshape(12, W), wfun[i].reshape(12, W)
+        sc = np.abs(wrows[i]).max(axis=0) + 1e-300
+        assert np.array_equal(g[3:5], w[3:5]), f"clip {i}: positions of the extremes"
+        for k in (0, 1, 2, 5, 7, 9):                                                    # values in the contour's own unit
+            assert np.all(np.abs(g[k] - w[k]) <= 1e-6 * np.abs(w[k]) + 1e-9 * sc), (i, k)
+        T = len(wrows[i])
+        assert np.all(np.abs(g[6] - w[6]) <= 1e-6 * np.abs(w[6]) + 1e-9 * sc / max(T, 1)), (i, "slope")
+        assert np.all(np.abs(g[8] - w[8]) <= 1e-6 * np.abs(w[8]) + 1e-9 * sc * sc), (i, "regression error")
+        np.testing.assert_allclose(g[10:12], w[10:12], rtol=1e-5, atol=1e-6, err_msg=f"clip {i}: skewness / kurtosis")
+
+
 def test_lld_device_entry_and_bad_arguments(ex):
     import torch
     from robust_speech_analysis_framework_b200 import _lib
@@ -562,7 +605,7 @@ def test_lld_device_entry_and_bad_arguments(ex):
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), host)
     for bad in ({"n_fft": 300}, {"n_fft": 256}, {"n_mel": 1}, {"n_mfcc": 26}, {"frame_step": 0.0}, {"mel_lo": 9000.0}, {"smooth_win": 4},
-                {"delta_win": -1}):
+                {"delta_win": -1}, {"descriptor_set": 2}, {"functional_set": -1}):
         with pytest.raises(_lib.MshdsError):
             ex.lld_extract(pcm, off, **bad)
 
