@@ -653,13 +653,22 @@ def test_frame_level_contours_match_the_oracle_objects(ex, orc):
 
 def test_float64_sample_entry(ex, orc, tmp_path):
     """MSHDS_PCM_FLOAT64: float64 samples (24/32-bit, multi-channel files) through the same kernels.  Samples that are exact
-    int16 / 32768 values must give the int16 path's rows bit for bit; a 24-bit-resolution signal is compared with the oracle."""
+    int16 / 32768 values must give the int16 path's rows bit for bit when both take the frame-by-frame cross-correlation
+    ("legacy_cc" = 1); by default int16 input takes the exact sliding sums, float64 input cannot (k_ccs.cu), so the harmonicity
+    and formant columns then agree to rounding only.  A 24-bit-resolution signal is compared with the oracle."""
     import pandas as pd
     from src.mshds_extractor import extract_mshds_features
     pcm, off, clips = _batch([2.5, 3.1], start=95)
-    a, sa = ex.extract_host(pcm, off)
     b, sb = ex.extract_host_f64(pcm.astype(np.float64) / 32768.0, off)
+    ex.set_option("legacy_cc", 1)
+    try:
+        a, sa = ex.extract_host(pcm, off)
+    finally:
+        ex.set_option("legacy_cc", 0)
     assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb)
+    a0, sa0 = ex.extract_host(pcm, off)
+    assert_features_close(a0, b, "int16 (sliding-sum cross-correlation) vs float64 entry")
+    assert np.array_equal(sa0, sb) and np.array_equal(a0[:, SPEECHRATE], b[:, SPEECHRATE])
     rng = np.random.default_rng(8)
     x = np.round((clips[0].astype(np.float64) / 32768.0 + rng.uniform(-0.5, 0.5, len(clips[0])) / 32768.0) * 8388608.0) / 8388608.0
     got, _ = ex.extract_host_f64(x, np.array([0, len(x)], np.int64))
