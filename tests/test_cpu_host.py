@@ -232,6 +232,25 @@ def test_lpt_sharding_is_a_partition_and_balanced():
     off = np.array([0, 10, 10, 25, 30])
     d, o = pack_subset(pcm, off, [3, 0, 1])
     assert list(o) == [0, 5, 15, 15] and list(d[:5]) == list(range(25, 30))
+    # equal-length clips are interchangeable: every rank gets ONE run of consecutive clips, which packs as a view (no copy)
+    eq = np.full(1000, 32000)
+    parts = lpt_assign(eq, 3)
+    assert [len(p) for p in parts] == [334, 333, 333]
+    assert all(p == list(range(p[0], p[0] + len(p))) for p in parts) and parts[1][0] == 334
+    big = np.arange(64, dtype=np.int16)
+    offs = np.arange(0, 65, 8)
+    v, o = pack_subset(big, offs, [2, 3, 4])
+    assert np.shares_memory(v, big) and list(v) == list(range(16, 40)) and list(o) == [0, 8, 16, 24]
+    c, o = pack_subset(big, offs, [0, 1, 5, 6, 3])                       # runs (0,1), (5,6), (3): copied run by run, order kept
+    assert not np.shares_memory(c, big) and list(o) == [0, 8, 16, 24, 32, 40]
+    assert list(c) == list(range(0, 16)) + list(range(40, 56)) + list(range(24, 32))
+    e, o = pack_subset(big, offs, [])
+    assert len(e) == 0 and list(o) == [0]
+    # mixed lengths: the regrouping of equal lengths never changes a rank's load
+    mixed = np.array([5, 9, 5, 5, 9, 2, 5, 9, 2, 5]) * 1000
+    parts = lpt_assign(mixed, 3)
+    assert sorted(i for p in parts for i in p) == list(range(10))
+    assert sorted(int(mixed[p].sum()) for p in parts) == [18000, 19000, 19000]
 
 
 def _free_port():
