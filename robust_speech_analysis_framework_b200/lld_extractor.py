@@ -101,3 +101,66 @@ def extract_lld_functionals(input_df, audio_file_column='filepath', verbose=True
     df = pd.DataFrame(feats, columns=cols)
     df.insert(0, "filename", filenames)
     return df
+
+
+# ------------------------------------------------------------------------------------------------ reference-shaped entry point
+_CONF_KEYS = {                      # component type -> {config key: (mshds_lld_params field, converter)}
+    "cFramer": {"frameSize": ("frame_size", float), "frameStep": ("frame_step", float)},
+    "cVectorPreemphasis": {"k": ("preemph", float)},
+    "cMelspec": {"lofreq": ("mel_lo", float), "hifreq": ("mel_hi", float), "nBands": ("n_mel", int)},
+    "cMfcc": {"lastMfcc": ("n_mfcc", int), "cepLifter": ("cep_lifter", float)},
+    "cContourSmoother": {"smaWin": ("smooth_win", int)},
+    "cDeltaRegression": {"deltawin": ("delta_win", int)},
+}
+_BUILT = {"cWaveSource", "cFramer", "cVectorPreemphasis", "cWindower", "cTransformFFT", "cFFTmagphase", "cMelspec", "cMfcc", "cEnergy",
+          "cMZcr", "cIntensity", "cSpectral", "cContourSmoother", "cDeltaRegression", "cFunctionals", "cCsvSink", "cComponentManager"}
+
+
+def parse_smile_config(path: str):
+    """The parameters of an OpenSMILE configuration file (Androids.conf) that map onto mshds_lld_params, and the component
+    types of the file that this library does not build.  Sections are '[instance:cType]', settings 'key = value', comments
+    start with ';' or '//' (/root/reference/Androids.conf:60-420)."""
+    params, missing, ctype = {}, [], None
+    with open(path, "r", errors="replace") as f:
+        for raw in f:
+            line = raw.split("//")[0].split(";")[0].strip()
+            if not line:
+                continue
+            if line.startswith("[") and line.endswith("]") and ":" in line:
+                ctype = line[1:-1].split(":", 1)[1].strip()
+                if ctype not in _BUILT and ctype not in missing:
+                    missing.append(ctype)
+                continue
+            if "=" in line and ctype in _CONF_KEYS:
+                key, val = (t.strip() for t in line.split("=", 1))
+                if key in _CONF_KEYS[ctype]:
+                    field, conv = _CONF_KEYS[ctype][key]
+                    try:
+                        params[field] = conv(float(val)) if conv is int else conv(val)
+                    except ValueError:
+                        pass
+    return params, missing
+
+
+def extract_opensmile_features(input_df, opensmile_exe_path=None, config_file_path=None, audio_file_column='filepath', verbose=True,
+                               device: int = 0):
+    """Drop-in for /root/reference/src/opensmile_extractor.py:9 `extract_opensmile_features`: same arguments and the same
+    shape of result -- one row per recording that could be processed (failed files are left out, :89-96), the feature columns
+    first and 'filename' last (:86), an empty DataFrame with the reference's warning when nothing was extracted (:98-100).
+    No SMILExtract binary is run: `opensmile_exe_path` is accepted and ignored, `config_file_path` (when it exists) supplies the
+    frame / pre-emphasis / mel / MFCC / smoothing / delta settings, and the descriptors come from mshds_lld_extract -- the 720
+    of the 911 Androids.conf columns built so far (components that are not built are named once when `verbose`)."""
+    import pandas as pd
+
+    params = {}
+    if config_file_path and os.path.exists(config_file_path):
+        params, missing = parse_smile_config(config_file_path)
+        if verbose and missing:
+            print(f"Note: components of '{os.path.basename(config_file_path)}' that this extractor does not build: {', '.join(missing)}")
+    df = extract_lld_functionals(input_df, audio_file_column=audio_file_column, verbose=verbose, device=device, **params)
+    ok = ~df.iloc[:, 1:].isna().all(axis=1)
+    df = df[ok].reset_index(drop=True)
+    if df.empty:
+        print("Warning: No features were successfully extracted. The returned DataFrame is empty.")
+        return pd.DataFrame()
+    return df[[c for c in df.columns if c != "filename"] + ["filename"]]

@@ -531,3 +531,65 @@ def test_lld_oracle_functionals_and_spectral_descriptors_known_answers():
     names = functional_names(descriptor_set=1, functional_set=1)
     assert len(names) == 720 and names[0] == "mfcc_sma[1]_max" and "pcm_fftMag_spectralRollOff90.0_sma_de_kurtosis" in names
     assert len(functional_names()) == 56 and functional_names()[0] == "mfcc_sma[1]_amean"
+
+
+def test_opensmile_drop_in_entry_point_and_config_parser(tmp_path, monkeypatch, capsys):
+    """extract_opensmile_features keeps the reference's signature and result shape (src/opensmile_extractor.py:9-103: feature
+    columns then 'filename', failed files left out, empty frame + warning when nothing worked) and takes its settings from the
+    OpenSMILE configuration file."""
+    import pandas as pd
+    from oracle import lld_oracle as lo
+    from robust_speech_analysis_framework_b200 import lld_extractor as lx, mshds_extractor as mx
+    from src.opensmile_extractor import extract_opensmile_features
+
+    conf = tmp_path / "Androids_fixed.conf"
+    conf.write_text("""
+[componentInstances:cComponentManager]
+instance[waveIn].type=cWaveSource
+[fr1:cFramer]
+reader.dmLevel=wave
+frameSize=0.0250   ; seconds
+frameStep = 0.010
+[pe2:cVectorPreemphasis]
+k=0.95
+[mspec:cMelspec]
+htkcompatible = 1
+lofreq = 50   // Hz
+hifreq = 7000
+[mfcc:cMfcc]
+firstMfcc = 1
+lastMfcc =  10
+[shs:cPitchShs]
+maxPitch = 620
+[pitchJitter:cPitchJitter]
+jitterLocal = 1
+[delta1:cDeltaRegression]
+deltawin=2
+[functL1:cFunctionals]
+frameSize=0.025
+frameStep=0
+""")
+    params, missing = lx.parse_smile_config(str(conf))
+    assert params == {"frame_size": 0.025, "frame_step": 0.01, "preemph": 0.95, "mel_lo": 50.0, "mel_hi": 7000.0, "n_mfcc": 10,
+                      "delta_win": 2}
+    assert missing == ["cPitchShs", "cPitchJitter"]
+    seen = {}
+
+    class Fake:
+        def lld_extract(self, pcm, offs, fs, want_frames=False, **p):
+            seen.update(p)
+            fun, _ = lo.extract(pcm, offs, float(fs), **p)           # the checker standing in for the CUDA call (test only)
+            return fun, None, None
+    monkeypatch.setattr(mx, "get_extractor", lambda device=0: Fake())
+    rng = np.random.default_rng(3)
+    pa = str(tmp_path / "a.wav")
+    _write_wav(pa, (rng.normal(scale=2000, size=8000)).astype(np.int16))
+    frame = pd.DataFrame({"filepath": [pa, str(tmp_path / "missing.wav")]})
+    df = extract_opensmile_features(frame, "C:/tools/opensmile/bin/SMILExtract.exe", str(conf), verbose=True)
+    out = capsys.readouterr().out
+    assert "cPitchShs" in out and "ERROR processing missing.wav" in out
+    assert seen["n_mfcc"] == 10 and seen["preemph"] == 0.95 and seen["descriptor_set"] == 1 and seen["functional_set"] == 1
+    assert df.shape == (1, (10 + 2 + 16) * 2 * 12 + 1) and df.columns[-1] == "filename" and df["filename"].iloc[0] == "a.wav"
+    assert df.columns[0] == "mfcc_sma[1]_max" and not df.iloc[0, :-1].isna().any()
+    empty = extract_opensmile_features(frame.iloc[1:], None, None, verbose=False)
+    assert empty.empty and "No features were successfully extracted" in capsys.readouterr().out
