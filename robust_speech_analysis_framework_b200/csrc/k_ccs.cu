@@ -22,7 +22,12 @@
 // Work per frame drops from W x maximumLag to (H + edge) x maximumLag multiply-adds + one pass over the ring: 13x fewer for
 // the harmonicity pass, 3x for the one-period window of to_pitch_cc.
 //
-// Structure: a CTA walks a run of consecutive frames of one recording.  Per step (= one new block): warps 0-3 form the
+// Two kernels share this derivation.  The default is k_cc_frames_w further down (one WARP per run of frames, the block sums
+// replaced by sliding sums in registers, no block barrier: 2.2x faster than the kernel described next); k_cc_frames_s, the first
+// implementation, is kept behind the development switch "legacy_cc" = 2 as an independent checker -- both are exact, so their
+// rows are bit-identical (tests/test_gpu_parity.py::test_shared_block_cross_correlation_equals_frame_by_frame).
+//
+// Structure of k_cc_frames_s: a CTA walks a run of consecutive frames of one recording.  Per step (= one new block): warps 0-3 form the
 // block's products (a thread owns 13 consecutive lags and a slice of the block; the lag window slides through registers as
 // a ring: 2 shared-memory loads per 13 DFMA), warp 4 meanwhile loads the next H samples and extends the prefix sums; then
 // all threads add the partial products into a ring of the last R blocks and assemble the frame that became complete

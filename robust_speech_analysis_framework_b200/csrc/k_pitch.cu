@@ -6,12 +6,16 @@
 // :320 (to_pitch_cc) -- i.e. fon/Sound_to_Pitch.cpp Sound_to_Pitch_any + Sound_into_PitchFrame and
 // fon/Pitch.cpp Pitch_pathFinder.
 //
-// Frame kernel: one CTA (128 or 256 threads) per frame, persistent grid over the flattened frame list of all clips, 8
-// consecutive frames per turn.  The frame is staged in shared memory, transformed with the packed real FFT of fft.cuh (AC) or
-// correlated directly with register-tiled lag windows (FCC); the first pass (maxima, parabolic frequency, sinc30 strength,
-// Praat's slot rule) runs in the CTA.  The correlation row and the <= 15 candidates leave the SM; the candidates that can
-// matter are queued for the refinement kernels (sinc70/700 + Brent, 4 / 8 lanes per item), then k_pitch_score and the
-// warp-per-clip Viterbi (issued on the side stream by mshds_api.cu).
+// Frame kernels.  The defaults live in their own files: autocorrelation frames with transforms of <= 1024 complex points run
+// warp-per-frame on register-resident FFTs fed by TMA-staged spans (k_acw.cu), int16 cross-correlation frames as exact sliding
+// sums, one warp per run of frames (k_ccs.cu).  The kernel HERE, k_pitch_frames, is the CTA-per-frame version of round 1
+// (128 or 256 threads per frame, persistent grid over the flattened frame list, 8 consecutive frames per turn, the frame staged in
+// shared memory, packed real FFT of fft.cuh for AC or register-tiled lag windows for FCC, first pass -- maxima, parabolic
+// frequency, sinc30 strength, Praat's slot rule -- in the CTA).  It still serves the 4096-point speech-rate pass (:104), float64
+// input behind the resampling front-end (cross-correlation) and the development switches "legacy_fft" / "legacy_cc" = 1, under
+// which the parity tests compare it with the new kernels.  In every variant the correlation row and the <= 15 candidates leave
+// the SM; the candidates that can matter are queued for the refinement kernels (sinc70/700 + Brent, 4 / 8 lanes per item), then
+// k_pitch_score and the CTA-per-clip Viterbi (issued on a side stream by mshds_api.cu).
 #include <cstdlib>
 #include "internal.h"
 #include "common.cuh"
