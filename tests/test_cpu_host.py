@@ -593,3 +593,33 @@ frameStep=0
     assert df.columns[0] == "mfcc_sma[1]_max" and not df.iloc[0, :-1].isna().any()
     empty = extract_opensmile_features(frame.iloc[1:], None, None, verbose=False)
     assert empty.empty and "No features were successfully extracted" in capsys.readouterr().out
+
+
+def test_sliding_sum_cross_correlation_is_exact_in_float64():
+    """The arithmetic claim behind k_cc_frames_w / k_cc_frames_s (k_ccs.cu): for int16 samples s = v / 32768 every product
+    s[j] s[j + lag] is an integer multiple of 2^-30 and window sums stay far below 2^53, so adding the products that enter a
+    window and subtracting those that leave it is EXACT in float64 -- no drift over a run of frames, whatever the order.  Checked
+    against Python integers: 400 frames of the harmonicity geometry (W = 1198, step 80, 268 lags), full-scale noise + DC."""
+    rng = np.random.default_rng(12)
+    W, H, L, nfr = 1198, 80, 268, 400
+    v = (rng.integers(-32768, 32768, size=W + H * nfr + L + 8)).astype(np.int64)
+    v[5000:9000] = 32767                                           # a full-scale DC stretch: the largest possible sums
+    s = v.astype(np.float64) / 32768.0
+    lags = np.array([1, 2, 17, 160, 267, 268])
+    C = np.array([np.dot(s[:W], s[l:l + W]) for l in lags])        # frame 0 (any summation order: exact as well)
+    Ci = [int(np.dot(v[:W], v[l:l + W])) for l in lags]
+    for k in range(1, nfr + 1):
+        lo, hi = (k - 1) * H, (k - 1) * H + W                      # [lo, lo + H) leaves, [hi, hi + H) enters
+        for n, l in enumerate(lags):
+            add = 0.0
+            for j in range(hi, hi + H):
+                add = add + s[j] * s[j + l]
+            sub = 0.0
+            for j in range(lo, lo + H):
+                sub = sub + s[j] * s[j + l]
+            C[n] = C[n] + add - sub
+            Ci[n] += int(np.dot(v[hi:hi + H], v[hi + l:hi + H + l])) - int(np.dot(v[lo:lo + H], v[lo + l:lo + H + l]))
+    direct = [int(np.dot(v[nfr * H:nfr * H + W], v[nfr * H + l:nfr * H + l + W])) for l in lags]
+    assert Ci == direct
+    assert [float(c) for c in C] == [ci / float(1 << 30) for ci in Ci]            # bit-exact, not approximately equal
+    assert max(abs(ci) for ci in Ci) < (1 << 53)
