@@ -138,8 +138,20 @@ def _read_other_container(path: str, wave_error: str):
             y = y.reshape(-1, nch).mean(axis=1)
         return np.ascontiguousarray(y), int(fs)
     kind = {b"fLaC": "FLAC", b"OggS": "Ogg", b"ID3": "MP3"}.get(magic[:4], {b"ID3": "MP3"}.get(magic[:3], "unknown"))
+    # FLAC / Ogg / MP3 / NIST ...: decoded through the optional `soundfile` package (libsndfile) when the installation has it --
+    # float64 frames, channels averaged in floating point like Praat's convert_to_mono (:416-417)
+    try:
+        import soundfile
+    except ImportError:
+        soundfile = None
+    if soundfile is not None:
+        try:
+            y, fs = soundfile.read(path, dtype="float64", always_2d=True)
+        except Exception as e:
+            raise AudioLoadError(f"audio container ({kind}) not readable by soundfile: {e}") from e
+        return np.ascontiguousarray(y.mean(axis=1)), int(fs)
     raise AudioLoadError(f"unsupported audio container ({kind}): parselmouth.Sound reads it, this drop-in decodes WAV (PCM / float) "
-                         f"and AIFF only -- convert the file to WAV")
+                         f"and AIFF only (plus whatever the optional `soundfile` package reads, which is not installed) -- convert the file to WAV")
 
 
 _TLS = threading.local()

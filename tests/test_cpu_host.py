@@ -216,6 +216,17 @@ def test_float_wav_and_aiff_are_decoded_and_other_containers_are_a_distinct_erro
     open(q, "wb").write(b"fLaC" + bytes(64))
     with pytest.raises(AudioLoadError, match="FLAC"):
         read_wav_mono(q)
+    # with the optional `soundfile` package present, other containers are decoded through it (stereo -> channel mean)
+    import sys
+    import types
+    fake = types.ModuleType("soundfile")
+    fake.read = lambda path, dtype="float64", always_2d=True: (np.array([[0.5, -0.5], [0.25, 0.75], [-1.0, 0.0]]), 22050)
+    sys.modules["soundfile"] = fake
+    try:
+        y, fs = read_wav_mono(q)
+    finally:
+        del sys.modules["soundfile"]
+    assert fs == 22050 and y.dtype == np.float64 and list(y) == [0.0, 0.5, -0.5]
 
 
 def test_lpt_sharding_is_a_partition_and_balanced():
