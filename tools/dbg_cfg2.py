@@ -1,3 +1,7 @@
+"""Which recordings of the ragged set (BASELINE.json configs[2]) have NaN columns, with their status words, batch vs alone
+(run on the GPU box).  Finding of round 2: ONE recording (index 170, 76 s) has F0 / slope / tilt / CPP / moments NaN with status
+0x60 in the batch and alone -- its main pitch pass finds no voiced frame -- and the CPU port returns the same row
+(`python tools/dbg_cfg2.py`; the CPU side was checked with oracle.mshds_oracle.extract on the same samples)."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.getcwd())
