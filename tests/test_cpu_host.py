@@ -634,3 +634,26 @@ def test_sliding_sum_cross_correlation_is_exact_in_float64():
     assert Ci == direct
     assert [float(c) for c in C] == [ci / float(1 << 30) for ci in Ci]            # bit-exact, not approximately equal
     assert max(abs(ci) for ci in Ci) < (1 << 53)
+
+
+def test_lld_oracle_reproduces_its_golden_vectors():
+    """tests/golden/lld_golden_v1.npz freezes oracle/lld_oracle.py (make_lld_golden.py): the restatement cannot drift silently.
+    Tolerance 1e-9 relative, absolute 1e-9 of each column's largest value (the numpy / BLAS build may reorder sums)."""
+    from oracle import lld_oracle as lo
+    from robust_speech_analysis_framework_b200.lld_extractor import functional_names
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lld_golden_v1.npz"))
+    pcm, off = g["pcm"], g["offsets"]
+    fun56, _ = lo.extract(pcm, off, 16000.0)
+    np.testing.assert_allclose(fun56, g["functionals_56"], rtol=1e-9, atol=1e-9, equal_nan=True)
+    fun, rows = lo.extract(pcm, off, 16000.0, descriptor_set=1, functional_set=1)
+    frames = np.concatenate([r for r in rows if len(r)])
+    assert [len(r) for r in rows] == list(g["frame_counts"])
+    sc = np.abs(g["frames_720"]).max(axis=0) + 1e-300
+    assert np.all(np.abs(frames - g["frames_720"]) <= 1e-9 * np.abs(g["frames_720"]) + 1e-9 * sc[None, :])
+    assert np.array_equal(np.isnan(fun), np.isnan(g["functionals_720"]))
+    assert list(g["names_720"]) == functional_names(descriptor_set=1, functional_set=1) and list(g["names_56"]) == functional_names()
+    ok = ~np.isnan(fun)
+    W = frames.shape[1]
+    pos = np.zeros(12 * W, bool); pos[3 * W:5 * W] = True                 # maxPos / minPos: indices, exact
+    assert np.array_equal(fun[:, pos], g["functionals_720"][:, pos], equal_nan=True)
+    np.testing.assert_allclose(fun[ok], g["functionals_720"][ok], rtol=1e-6, atol=1e-6 * float(np.abs(g["functionals_720"][ok]).max()))

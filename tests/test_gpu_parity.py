@@ -570,17 +570,25 @@ def test_lld_spectral_descriptors_and_the_twelve_functionals_match_the_numpy_res
     kw = dict(descriptor_set=1, functional_set=1, **params)
     fun, frames, fo = ex.lld_extract(pcm, off, fs, want_frames=True, **kw)
     wfun, wrows = lo.extract(pcm, off, float(fs), **kw)
-    W = wrows[0].shape[1]
     names = functional_names(12, params.get("smooth_win", 3), params.get("delta_win", 2), 1, 1)
-    assert fun.shape == wfun.shape == (len(clips), 12 * W) and len(names) == 12 * W
+    assert len(names) == wfun.shape[1]
+    _assert_lld_full_set_close(fun, frames, fo, wfun, wrows, raw=not params.get("smooth_win", 3) and not params.get("delta_win", 2))
+    assert np.isnan(fun[3]).all()
+
+
+def _assert_lld_full_set_close(fun, frames, fo, wfun, wrows, raw=False):
+    """(functionals, frame rows, frame offsets) of the 720-column set against the wanted ones (see the test above for the
+    tolerances); wrows: list of per-clip frame matrices."""
+    W = wrows[0].shape[1]
+    assert fun.shape == wfun.shape == (len(wrows), 12 * W)
     assert list(np.diff(fo)) == [len(r) for r in wrows] and frames.shape == (int(fo[-1]), W)
     want = np.concatenate([r for r in wrows if len(r)])
     scale = np.abs(want).max(axis=0) + 1e-300
     assert np.all(np.abs(frames - want) <= 1e-8 * np.abs(want) + 1e-9 * scale[None, :]), "frame rows"
-    if not params.get("smooth_win", 3) and not params.get("delta_win", 2):
+    if raw:
         assert np.array_equal(frames[:, 18:22], want[:, 18:22])                         # raw roll-off points: bin frequencies
-    assert np.array_equal(np.isnan(fun), np.isnan(wfun)) and np.isnan(fun[3]).all()
-    for i in range(len(clips)):
+    assert np.array_equal(np.isnan(fun), np.isnan(wfun))
+    for i in range(len(wrows)):
         if np.isnan(wfun[i]).all():
             continue
         g, w = fun[i].reshape(12, W), wfun[i].reshape(12, W)
@@ -592,6 +600,20 @@ def test_lld_spectral_descriptors_and_the_twelve_functionals_match_the_numpy_res
         assert np.all(np.abs(g[6] - w[6]) <= 1e-6 * np.abs(w[6]) + 1e-9 * sc / max(T, 1)), (i, "slope")
         assert np.all(np.abs(g[8] - w[8]) <= 1e-6 * np.abs(w[8]) + 1e-9 * sc * sc), (i, "regression error")
         np.testing.assert_allclose(g[10:12], w[10:12], rtol=1e-5, atol=1e-6, err_msg=f"clip {i}: skewness / kurtosis")
+
+
+def test_lld_golden_vectors(ex):
+    """tests/golden/lld_golden_v1.npz (outputs of the numpy restatement, frozen; generator: make_lld_golden.py): both descriptor
+    sets of mshds_lld_extract against the committed numbers."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lld_golden_v1.npz"))
+    pcm, off = g["pcm"], g["offsets"]
+    fun56, _, _ = ex.lld_extract(pcm, off, 16000)
+    np.testing.assert_allclose(fun56, g["functionals_56"], rtol=1e-9, atol=1e-9, equal_nan=True)
+    fun, frames, fo = ex.lld_extract(pcm, off, 16000, want_frames=True, descriptor_set=1, functional_set=1)
+    counts = list(g["frame_counts"])
+    starts = np.cumsum([0] + counts)
+    wrows = [g["frames_720"][starts[i]:starts[i + 1]] for i in range(len(counts))]
+    _assert_lld_full_set_close(fun, frames, fo, g["functionals_720"], wrows)
 
 
 def test_lld_device_entry_and_bad_arguments(ex):
