@@ -7,7 +7,8 @@
  * reference interface it stands in for.  Plain pointers and sizes only, no torch types.  INTEGRATION.md shows the
  * ctypes binding and the drop-in src/mshds_extractor.py shim.
  *
- * Threading: one handle per host thread / process; a handle owns one CUDA device, one stream and all scratch memory;
+ * Threading: one handle per host thread / process; a handle owns one CUDA device, its streams (the main one, which
+ * mshds_set_stream can replace by the caller's, four side streams and a read-back stream) and all scratch memory;
  * no global mutable state.  Calls block until results are in the caller's buffers (mirrors the synchronous reference).
  */
 #ifndef MSHDS_B200_H
